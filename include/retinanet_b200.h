@@ -1,0 +1,136 @@
+/* retinanet_b200 — C ABI of the B200-native dense per-anchor path of RetinaNet.
+ *
+ * The reference (benihime91/pytorch_retinanet) has NO FFI/plugin interface for this path: the
+ * boundary is plain Python method dispatch inside `Retinanet` (retinanet/models.py:266,270,284,287).
+ * This header is therefore the interface a native binding WOULD use; every entry point names the
+ * reference function (file:line, relative to the reference root) it replaces.  The Python host
+ * side in pytorch_retinanet_b200/ binds it with ctypes.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers on the current CUDA device unless the name ends in `_host`.
+ *  - All tensors are contiguous, row-major; floats are fp32, indices int64 unless stated.
+ *  - Memory is owned by the caller (torch allocates it); the library allocates nothing persistent
+ *    and never frees caller memory.  Work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *    no entry point synchronises the host.
+ *  - Return value: 0 on success; >0 = cudaError_t; <0 = argument error (RN_E_*).
+ *    rn_last_error() returns a thread-local description.  Nothing throws across the ABI.
+ *  - Anchors are normally shared by the batch ([A,4], anchor_image_stride = 0); per-image anchor
+ *    sets ([N,A,4]) are supported with anchor_image_stride = A (in anchors, not bytes).
+ *  - Ragged ground truth is packed: gt_boxes [sumG,4], gt_labels [sumG] (1-based class ids, as in
+ *    the reference, README.md:132) and gt_off [N+1] int32 prefix offsets.
+ */
+#ifndef RETINANET_B200_H_
+#define RETINANET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_ABI_VERSION 1
+
+#define RN_E_BADARG   (-1)  /* null pointer / negative size / unsupported combination          */
+#define RN_E_TOOLARGE (-2)  /* size exceeds a documented limit (levels, cell anchors, classes) */
+#define RN_E_WORKSPACE (-3) /* workspace too small                                             */
+
+#define RN_MAX_LEVELS 8
+
+typedef void *rn_stream_t; /* cudaStream_t */
+
+int rn_abi_version(void);
+const char *rn_last_error(void);
+
+/* ---- anchors ---------------------------------------------------------------------------------
+ * Replaces AnchorGenerator.grid_anchors / _compute_grid_offsets (retinanet/anchors.py:151-197) for
+ * all pyramid levels in one launch.  `cells` is the concatenation of the per-level cell-anchor
+ * tables ([sum_l na_l, 4], the BufferList of anchors.py:97-108, computed on the host in double as
+ * anchors.py:110-135).  level_desc_host[l] = {H_l, W_l, stride_l, na_l}.  Output anchor index inside
+ * a level is (y*W + x)*na + a, levels concatenated in order (anchors.py:228).                     */
+int rn_anchor_grid(const float *cells, const int32_t *level_desc_host /*[L][4]*/, int num_levels,
+                   double offset, float *out_anchors /*[A,4]*/, int64_t num_anchors, rn_stream_t stream);
+
+/* ---- matcher ----------------------------------------------------------------------------------
+ * Replaces matcher (retinanet/box_utils.py:51-80) + torchvision box_iou for a whole batch:
+ * fused IoU + first-index argmax + strict 0.5/0.4 thresholds.  matches[n,a] = -2 ignore,
+ * -1 background, g >= 0 index of the matched GT box inside image n.  Images with zero GT boxes
+ * get -2 everywhere (box_utils.py:70-71).
+ * Optional outputs (may be NULL):
+ *   codes   [N,A] int32 — packed per-anchor target used by rn_loss: -2 / -1 / (g | (label-1) << 20)
+ *                         (requires gt_labels; G per image < 2^20, classes < 2^11)
+ *   fg_count[N]   int32 — number of foreground anchors per image (must be zeroed by the caller). */
+int rn_match(const float *anchors /*[A,4] or [N,A,4]*/, int64_t A, int64_t anchor_image_stride,
+             const float *gt_boxes /*[sumG,4]*/,
+             const int64_t *gt_labels /*[sumG] or NULL*/, const int32_t *gt_off /*[N+1]*/, int N,
+             float fg_thr, float bg_thr, int64_t *matches /*[N,A] or NULL*/, int32_t *codes /*[N,A] or NULL*/,
+             int32_t *fg_count /*[N] or NULL*/, rn_stream_t stream);
+
+/* ---- box coding -------------------------------------------------------------------------------
+ * rn_encode replaces bbox_2_activ (box_utils.py:25-34); rn_decode replaces activ_2_bbox
+ * (box_utils.py:37-48) INCLUDING its quirk (sizes = a_wh * exp(dx,dy)).  weights_host = 4 floats. */
+int rn_encode(const float *boxes, const float *anchors, int64_t n, const float *weights_host,
+              float *out, rn_stream_t stream);
+int rn_decode(const float *activations, const float *anchors, int64_t n, const float *weights_host,
+              float *out, rn_stream_t stream);
+
+/* ---- losses -----------------------------------------------------------------------------------
+ * Replaces RetinaNetLosses.calc_loss/forward (retinanet/losses.py:49-145) given the packed codes
+ * written by rn_match: sigmoid focal loss on (logits + 1) with alpha applied inverted and weights
+ * from detached probabilities (losses.py:29-47,84), smooth-L1 on encoded targets (losses.py:19-27),
+ * both divided by max(1, F_n) per image, then averaged over `batch_div` images (losses.py:108-109,
+ * 138-140).
+ *   out_image [N,3]  = {cls_n / max(1,F_n), reg_n / max(1,F_n), F_n}   (fp32)
+ *   out_total [2]    = {sum_n cls_n/max(1,F_n), sum_n reg_n/max(1,F_n)} / batch_div
+ *   grad_logits / grad_bbox (optional, both or neither): d out_total[0] / d logits and
+ *   d out_total[1] / d bbox_preds, written for EVERY element (zeros where no gradient flows).
+ * Reductions are two-stage and order-fixed, so results are bit-reproducible run to run.
+ * workspace: rn_loss_workspace_bytes(N, A, C).                                                   */
+size_t rn_loss_workspace_bytes(int N, int64_t A, int C);
+int rn_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, const float *anchors,
+            int64_t anchor_image_stride, const float *gt_boxes /*[sumG,4]*/, const int32_t *gt_off /*[N+1]*/, const int32_t *codes /*[N,A]*/,
+            const int32_t *fg_count /*[N]*/, int N, int64_t A, int C, float alpha, float gamma, float beta,
+            const float *weights_host /*[4]*/, float batch_div, float *out_image /*[N,3]*/,
+            float *out_total /*[2]*/, float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/,
+            void *workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* In-place scale of a gradient buffer by a DEVICE scalar (autograd's grad_output); every block
+ * returns immediately when *scale == 1.0f, so the common case costs one launch and no traffic.    */
+int rn_scale_by_device_scalar(float *buf, int64_t n, const float *scale, rn_stream_t stream);
+
+/* ---- inference post-processing ----------------------------------------------------------------
+ * Replaces Retinanet.process_detections (retinanet/models.py:160-243) for a whole batch:
+ * sigmoid + strict score threshold, decode (with the reference quirk) + clip to im_hw, small-box
+ * filter (w,h >= 0.01), per-(image,class) greedy NMS (strict IoU > nms_thr, stable score order,
+ * ties -> lower anchor index), concatenation, labels+1, top `max_det` by (score desc, class asc,
+ * anchor asc).  pre_nms_topk > 0 additionally keeps only the top-k scores per (image, pyramid
+ * level) before NMS (an extension; 0 = exact reference behaviour); level_off_host [L+1] gives the
+ * anchor offsets of the levels and is only read when pre_nms_topk > 0.
+ *   out_boxes [N,max_det,4] fp32, out_scores [N,max_det] fp32, out_labels [N,max_det] int64,
+ *   out_count [N] int32 (number of valid rows per image).
+ *   out_status [2] int32: {candidates found, candidate capacity}; found > capacity means the
+ *   workspace was too small and the call must be repeated with a larger cand_capacity.
+ * workspace: rn_postprocess_workspace_bytes(N, A, C, cand_capacity, max_det).                      */
+size_t rn_postprocess_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
+int rn_postprocess(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, const float *anchors,
+                   int64_t anchor_image_stride, const int32_t *im_hw /*[N,2] (h,w)*/, int N, int64_t A, int C, float score_thr, double nms_thr,
+                   int max_det, const float *weights_host /*[4]*/, int pre_nms_topk,
+                   const int64_t *level_off_host /*[L+1] or NULL*/, int num_levels, int64_t cand_capacity,
+                   float *out_boxes, float *out_scores, int64_t *out_labels, int32_t *out_count,
+                   int32_t *out_status, void *workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* Stand-alone batched greedy NMS (torchvision `nms` semantics, tv:ops/boxes.py:20-48) over
+ * segments whose boxes are ALREADY sorted by score descending (ties: original order): boxes [K,4],
+ * seg_off [S+1] int32, keep_flags [K] uint8 out (1 = kept).  workspace >= 16*K bytes.            */
+int rn_nms_segments(const float *boxes, const int32_t *seg_off, int num_segments, int64_t total_boxes,
+                    double nms_thr, uint8_t *keep_flags, void *workspace, size_t workspace_bytes,
+                    rn_stream_t stream);
+
+/* Test hook: 0 = fast SFU math in rn_loss (default), 1 = libdevice-precise math.  Returns the
+ * previous mode.  Process-global.                                                                */
+int rn_loss_set_math_mode(int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RETINANET_B200_H_ */

@@ -1,0 +1,100 @@
+"""ctypes binding of the C ABI declared in ``include/retinanet_b200.h``.
+
+The shared library is built in-tree (``pytorch_retinanet_b200/lib/librn_b200.so``) by
+``pytorch_retinanet_b200/build.py`` / ``__graft_entry__.build()``.  There is NO fallback: if the
+library is missing and cannot be built, or a tensor is not a contiguous CUDA tensor of the expected
+dtype, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+_c = ctypes
+_vp, _i32, _i64, _f32, _f64, _sz = _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_float, _c.c_double, _c.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/retinanet_b200.h
+SIGNATURES = {
+    "rn_abi_version": (_c.c_int, []),
+    "rn_last_error": (_c.c_char_p, []),
+    "rn_anchor_grid": (_c.c_int, [_vp, _vp, _c.c_int, _f64, _vp, _i64, _vp]),
+    "rn_match": (_c.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _c.c_int, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "rn_encode": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "rn_decode": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "rn_loss_workspace_bytes": (_sz, [_c.c_int, _i64, _c.c_int]),
+    "rn_loss": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _c.c_int, _i64, _c.c_int, _f32, _f32, _f32, _vp,
+                           _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rn_scale_by_device_scalar": (_c.c_int, [_vp, _i64, _vp, _vp]),
+    "rn_postprocess_workspace_bytes": (_sz, [_c.c_int, _i64, _c.c_int, _i64, _c.c_int]),
+    "rn_postprocess": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _c.c_int, _i64, _c.c_int, _f32, _f64, _c.c_int, _vp,
+                                  _c.c_int, _vp, _c.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rn_nms_segments": (_c.c_int, [_vp, _vp, _c.c_int, _i64, _f64, _vp, _vp, _sz, _vp]),
+    "rn_loss_set_math_mode": (_c.c_int, [_c.c_int]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Loads (building first if the sources are newer and nvcc is present) the CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library -> fail loudly
+            if not os.path.exists(path):
+                raise NativeError(
+                    f"retinanet_b200: CUDA library {path} is missing and could not be built ({e}). "
+                    "Run `python __graft_entry__.py` (build()) on a machine with nvcc; there is no CPU fallback."
+                ) from e
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale: fail loudly
+        fn.restype, fn.argtypes = res, args
+    if lib.rn_abi_version() != 1:
+        raise NativeError(f"retinanet_b200: ABI version mismatch ({lib.rn_abi_version()} != 1)")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().rn_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor], dtype: Optional[torch.dtype] = None, what: str = "tensor") -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL).  Raises on CPU tensors: no fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError(f"retinanet_b200: {what} must be a CUDA tensor (got device {t.device}); there is no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise NativeError(f"retinanet_b200: {what} must have dtype {dtype} (got {t.dtype})")
+    if not t.is_contiguous():
+        raise NativeError(f"retinanet_b200: {what} must be contiguous")
+    return t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def host_floats(vals) -> ctypes.Array:
+    return (_f32 * len(vals))(*[float(v) for v in vals])

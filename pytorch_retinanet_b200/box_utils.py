@@ -1,0 +1,114 @@
+"""Drop-in box coding + Matcher (reference: retinanet/box_utils.py), CUDA only.
+
+Same function names, argument meaning and error behaviour (``assert match_thr > back_thr``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native
+from .config import BBOX_REG_WEIGHTS, IOU_THRESHOLDS_BACKGROUND, IOU_THRESHOLDS_FOREGROUND
+from .utilities import ifnone
+
+
+def convert_xywh(boxes: Tensor) -> Tensor:
+    """xyxy -> (cx, cy, w, h) (reference: box_utils.py:11-15).  Public helper kept for API parity; the
+    kernels fuse this conversion and never call it."""
+    center = (boxes[:, :2] + boxes[:, 2:]) / 2
+    sizes = boxes[:, 2:] - boxes[:, :2]
+    return torch.cat([center, sizes], 1)
+
+
+def convert_x1y1x2y2(boxes: Tensor) -> Tensor:
+    """(cx, cy, w, h) -> xyxy (reference: box_utils.py:18-22).  API-parity helper, see convert_xywh."""
+    return torch.cat([boxes[:, :2] - boxes[:, 2:] / 2, boxes[:, :2] + boxes[:, 2:] / 2], 1)
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _boxcode(fn_name: str, a: Tensor, anchors: Tensor) -> Tensor:
+    lib = _native.load()
+    a32, an32 = _f32c(a).reshape(-1, 4), _f32c(anchors).reshape(-1, 4)
+    if a32.shape != an32.shape:
+        raise ValueError(f"{fn_name}: shapes {tuple(a.shape)} and {tuple(anchors.shape)} differ")
+    out = torch.empty_like(a32)
+    with torch.cuda.device(a32.device):
+        rc = getattr(lib, fn_name)(_native.ptr(a32, what=fn_name + " input"), _native.ptr(an32, what="anchors"),
+                                   a32.shape[0], _native.host_floats(BBOX_REG_WEIGHTS), _native.ptr(out),
+                                   _native.stream_ptr(a32.device))
+    _native.check(rc, fn_name)
+    return out.reshape(a.shape)
+
+
+def bbox_2_activ(bboxes: Tensor, anchors: Tensor) -> Tensor:
+    """Regression targets of `bboxes` w.r.t. `anchors` (reference: box_utils.py:25-34)."""
+    return _boxcode("rn_encode", bboxes, anchors)
+
+
+def activ_2_bbox(activations: Tensor, anchors: Tensor) -> Tensor:
+    """Decode model activations to boxes (reference: box_utils.py:37-48, including its
+    ``sizes = a_wh * exp(dx,dy)`` quirk).  The reference divides ``activations`` in place by
+    BBOX_REG_WEIGHTS (= 1.0, a numeric no-op); this implementation leaves the input untouched."""
+    return _boxcode("rn_decode", activations, anchors)
+
+
+class PackedTargets:
+    """Ragged ground truth of a batch packed for the C ABI: boxes [sumG,4], labels [sumG], offsets [N+1]."""
+
+    def __init__(self, boxes: Sequence[Tensor], labels: Optional[Sequence[Tensor]], device: torch.device):
+        counts = [int(b.shape[0]) if b.numel() else 0 for b in boxes]
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        self.num_images = len(counts)
+        self.total = offs[-1]
+        live = [_f32c(b).reshape(-1, 4) for b, c in zip(boxes, counts) if c]
+        self.boxes = torch.cat(live) if live else torch.zeros((1, 4), dtype=torch.float32, device=device)
+        if labels is not None:
+            ll = [l.detach().to(torch.int64).reshape(-1) for l, c in zip(labels, counts) if c]
+            self.labels = torch.cat(ll).contiguous() if ll else torch.zeros((1,), dtype=torch.int64, device=device)
+            if self.labels.shape[0] != max(self.total, 1):
+                raise ValueError("targets: number of labels does not match number of boxes")
+        else:
+            self.labels = None
+        self.offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+        self.counts = counts
+
+
+def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_anchors: int,
+                match_thr: float, back_thr: float, want_matches: bool, want_codes: bool
+                ) -> Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor]]:
+    """Runs ``rn_match`` for a batch.  Returns (matches int64 [N,A] | None, codes int32 [N,A] | None, fg_count [N] | None)."""
+    lib = _native.load()
+    dev = anchors.device
+    N, A = packed.num_images, num_anchors
+    matches = torch.empty((N, A), dtype=torch.int64, device=dev) if want_matches else None
+    codes = torch.empty((N, A), dtype=torch.int32, device=dev) if want_codes else None
+    fg = torch.zeros((N,), dtype=torch.int32, device=dev) if want_codes else None
+    with torch.cuda.device(dev):
+        rc = lib.rn_match(_native.ptr(anchors, torch.float32, "anchors"), A, anchor_stride,
+                          _native.ptr(packed.boxes, torch.float32, "target boxes"),
+                          _native.ptr(packed.labels, torch.int64, "target labels") if want_codes else None,
+                          _native.ptr(packed.offsets), N, float(match_thr), float(back_thr),
+                          _native.ptr(matches), _native.ptr(codes), _native.ptr(fg), _native.stream_ptr(dev))
+    _native.check(rc, "rn_match")
+    return matches, codes, fg
+
+
+def matcher(anchors: Tensor, targets: Tensor, match_thr: float = None, back_thr: float = None) -> Tensor:
+    """Match `anchors` to `targets`: -1 = background, -2 = ignore, g >= 0 = GT index
+    (reference: box_utils.py:51-80).  Fused IoU + argmax + thresholds; no [G,A] matrix."""
+    match_thr = ifnone(match_thr, IOU_THRESHOLDS_FOREGROUND)
+    back_thr = ifnone(back_thr, IOU_THRESHOLDS_BACKGROUND)
+    assert match_thr > back_thr
+    an = _f32c(anchors).reshape(-1, 4)
+    if not an.is_cuda:
+        raise _native.NativeError("retinanet_b200.matcher: anchors must be a CUDA tensor; there is no CPU path")
+    packed = PackedTargets([targets.to(an.device)], None, an.device)
+    m, _, _ = match_batch(an, 0, packed, an.shape[0], match_thr, back_thr, True, False)
+    return m[0]

@@ -1,0 +1,405 @@
+// Fused sigmoid-focal + smooth-L1 loss (forward, and gradients in the same pass).
+// Replaces RetinaNetLosses.calc_loss / forward (retinanet/losses.py:19-145) given rn_match's codes.
+//
+// Roofline: HBM.  Algorithmic bytes per image: 4*A*C (logits) + 16*A (bbox) + 4*A (codes)
+// [+ 4*A*C + 16*A gradient writes]; anchors/GT are tiny and L2-resident.  No one-hot, no gathered
+// copy of the logits, no [A,C] temporaries: the per-anchor target column comes from the packed
+// code written by the matcher.
+//
+// Arithmetic (per logit v, reference semantics):
+//   x = v + 1                                   losses.py:84 (+1 on the LOGITS)
+//   p = sigmoid(x) (detached)                   losses.py:42
+//   t=0: w = alpha   * p^gamma      loss = w * softplus(x)       dL/dx = w * p
+//   t=1: w = (1-alpha)*(1-p)^gamma  loss = w * softplus(-x)      dL/dx = w * (p - 1)
+//        (alpha is applied inverted, losses.py:44; weights carry no gradient, losses.py:42)
+// Every element is first treated as a negative in a branch-free 128-bit vector loop; the (at most
+// one) positive column of a foreground anchor is then patched.  Anchors with code -2 (ignore)
+// contribute nothing and get zero gradient.
+// Math modes: FAST (default) uses ex2/rcp/lg2 SFU approximations, and a warp-uniform series path
+// when every logit of the warp is small (x <= -2.77, the overwhelmingly common case) that needs
+// only one ex2 + one rcp per element and is accurate to < 1e-7 relative — lg2.approx near 1 has
+// too much ABSOLUTE error for log1p(e) of tiny e, so it is only used for e > 1/16.
+// PRECISE uses expf/log1pf/IEEE division (test reference for the approximation error).
+// Reductions: fp32 per thread (<= a few hundred terms), fp64 from the warp level on, per-CTA
+// partials to the workspace and a fixed-order final kernel => bit-reproducible.
+#include "rn_common.cuh"
+
+namespace {
+
+constexpr int LOSS_BLOCK = 256;
+constexpr int LOSS_SPAN = 256;   // anchors per CTA
+constexpr int LOSS_U = 4;        // 128-bit loads in flight per thread
+
+static int g_math_mode = 0;      // 0 fast, 1 precise
+
+struct LossParams {
+    const float *logits;
+    const float4 *bbox;
+    const float4 *anchors;
+    const float4 *gt;
+    const int *gt_off;
+    const int *codes;
+    const int *fg_count;
+    float *grad_logits;
+    float4 *grad_bbox;
+    double *partials;            // [N][chunks][3]
+    long long A;
+    long long anchor_stride;
+    int C;
+    int chunks;
+    unsigned magic;              // ceil(2^32 / (C/VEC))
+    float alpha, gamma, beta, batch_div;
+    float4 wts;
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kSmallE = 0.0625f;               // series path valid for e <= 1/16
+constexpr float kSmallX = -2.7725887f;           // x <= ln(1/16)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// log1p(e) for 0 <= e <= 1/16: alternating series, truncation error e^6/7 < 1e-8
+__device__ __forceinline__ float log1p_small(float e) {
+    float s = fmaf(e, -1.0f / 6.0f, 0.2f);
+    s = fmaf(e, s, -0.25f);
+    s = fmaf(e, s, 1.0f / 3.0f);
+    s = fmaf(e, s, -0.5f);
+    s = fmaf(e, s, 1.0f);
+    return e * s;
+}
+
+// p = sigmoid(x), sp = softplus(x) = log(1 + exp(x))
+template <bool PRECISE>
+__device__ __forceinline__ void sigmoid_softplus(float x, float &p, float &sp) {
+    if (PRECISE) {
+        float e = expf(-fabsf(x));
+        float r = __fdiv_rn(1.0f, 1.0f + e);
+        p = x >= 0.0f ? r : e * r;
+        sp = fmaxf(x, 0.0f) + log1pf(e);
+    } else {
+        float e = ex2_approx(-fabsf(x) * kLog2e);
+        float d = 1.0f + e;
+        float r = rcp_approx(d);
+        p = x >= 0.0f ? r : e * r;
+        float l = e <= kSmallE ? log1p_small(e) : lg2_approx(d) * kLn2;
+        sp = fmaxf(x, 0.0f) + l;
+    }
+}
+// warp-uniform small-x path (x <= -2.77): e = exp(x) <= 1/16
+__device__ __forceinline__ void sigmoid_softplus_small(float v, float &p, float &sp) {
+    float e = ex2_approx(fmaf(v, kLog2e, kLog2e));   // exp(v + 1)
+    p = e * rcp_approx(1.0f + e);
+    sp = log1p_small(e);
+}
+
+template <bool GAMMA2>
+__device__ __forceinline__ float pow_gamma(float b, float gamma) {
+    if (GAMMA2) return b * b;
+    return b > 0.0f ? ex2_approx(gamma * lg2_approx(b)) : (gamma == 0.0f ? 1.0f : 0.0f);
+}
+
+__device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
+    __shared__ double s[3][LOSS_BLOCK / 32];
+    a = rn::warp_sum(a);
+    b = rn::warp_sum(b);
+    c = rn::warp_sum(c);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s[0][w] = a; s[1][w] = b; s[2][w] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = c = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOSS_BLOCK / 32; ++i) { a += s[0][i]; b += s[1][i]; c += s[2][i]; }
+    }
+}
+
+// VEC = 4: C % 4 == 0 and 16-byte aligned rows (128-bit path); VEC = 1: any C (scalar path).
+template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
+__global__ void __launch_bounds__(LOSS_BLOCK) loss_kernel(const LossParams P) {
+    const int n = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const long long a0 = (long long)chunk * LOSS_SPAN;
+    const int span = (int)min((long long)LOSS_SPAN, P.A - a0);
+    const long long row0 = (long long)n * P.A + a0;
+    const int CV = P.C / VEC;                       // vectors per anchor row
+    const int nvec = span * CV;
+    const int F = P.fg_count[n];
+    const float inv = 1.0f / (fmaxf((float)F, 1.0f) * P.batch_div);   // gradient scale
+    const float neg_gscale = P.alpha * inv;
+    const float *src = P.logits + row0 * P.C;
+    float *dst = WANT_GRAD ? P.grad_logits + row0 * P.C : nullptr;
+    const int *codes = P.codes + row0;
+
+    float acc_neg = 0.0f;   // sum p^g * softplus(x) over non-ignored elements treated as negatives
+    float acc_pos = 0.0f;   // correction + positive terms (already alpha-weighted)
+
+    for (int base = 0; base < nvec; base += LOSS_BLOCK * LOSS_U) {
+        float v[LOSS_U][VEC];
+        int code[LOSS_U], c0[LOSS_U];
+        bool valid[LOSS_U];
+#pragma unroll
+        for (int u = 0; u < LOSS_U; ++u) {
+            const int f = base + u * LOSS_BLOCK + threadIdx.x;
+            valid[u] = f < nvec;
+            code[u] = -2;
+            c0[u] = 0;
+            if (VEC == 4) {
+                float4 t = make_float4(-30.f, -30.f, -30.f, -30.f);
+                if (valid[u]) t = rn::ld_stream_f4((const float4 *)src + f);
+                v[u][0] = t.x; v[u][VEC > 1 ? 1 : 0] = t.y; v[u][VEC > 2 ? 2 : 0] = t.z; v[u][VEC > 3 ? 3 : 0] = t.w;
+            } else {
+                v[u][0] = valid[u] ? __ldg(src + f) : -30.f;
+            }
+            if (valid[u]) {
+                const int al = P.magic ? (int)__umulhi((unsigned)f, P.magic) : f;   // f / CV
+                c0[u] = (f - al * CV) * VEC;
+                code[u] = __ldg(codes + al);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < LOSS_U; ++u) {
+            float g[VEC];
+            const bool use = code[u] != -2;
+            float vmax = v[u][0];
+#pragma unroll
+            for (int k = 1; k < VEC; ++k) vmax = fmaxf(vmax, v[u][k]);
+            const bool small = !PRECISE && __all_sync(0xffffffffu, !use || vmax <= kSmallX - 1.0f);
+            float pk[VEC], spk[VEC];
+            if (small) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) sigmoid_softplus_small(v[u][k], pk[k], spk[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) sigmoid_softplus<PRECISE>(v[u][k] + 1.0f, pk[k], spk[k]);
+            }
+            float local = 0.0f;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float w = pow_gamma<GAMMA2>(pk[k], P.gamma);
+                local = fmaf(w, spk[k], local);
+                g[k] = w * pk[k] * neg_gscale;
+            }
+            if (use) {
+                acc_neg += local;
+                const int col = code[u] >= 0 ? (code[u] >> 20) : -1;
+                const int k = col - c0[u];
+                if (k >= 0 && k < VEC) {               // this vector holds the anchor's positive column
+                    float x = v[u][0];
+#pragma unroll
+                    for (int q = 1; q < VEC; ++q) x = (k == q) ? v[u][q] : x;
+                    x += 1.0f;
+                    float p, sp;
+                    sigmoid_softplus<PRECISE>(x, p, sp);
+                    const float wn = pow_gamma<GAMMA2>(p, P.gamma);
+                    const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
+                    acc_pos += wp * (sp - x) - P.alpha * wn * sp;   // softplus(-x) = softplus(x) - x
+                    const float gp = wp * (p - 1.0f) * inv;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) g[q] = (k == q) ? gp : g[q];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) g[k] = 0.0f;
+            }
+            if (WANT_GRAD && valid[u]) {
+                const int f = base + u * LOSS_BLOCK + threadIdx.x;
+                if (VEC == 4) {
+                    rn::st_stream_f4((float4 *)dst + f, make_float4(g[0], g[VEC > 1 ? 1 : 0], g[VEC > 2 ? 2 : 0],
+                                                                    g[VEC > 3 ? 3 : 0]));
+                } else {
+                    dst[f] = g[0];
+                }
+            }
+        }
+    }
+
+    // ---- regression: one thread per anchor of the span (losses.py:66-71, 19-27) ----
+    float reg = 0.0f;
+    if (threadIdx.x < span) {
+        const int code = __ldg(codes + threadIdx.x);
+        float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (code >= 0) {
+            const float4 gtb = P.gt[P.gt_off[n] + (code & 0xFFFFF)];
+            const float4 an = P.anchors[(long long)n * P.anchor_stride + a0 + threadIdx.x];
+            const float4 pr = P.bbox[row0 + threadIdx.x];
+            const float4 t = rn::encode_box(gtb, an, P.wts);
+            const float d[4] = {pr.x - t.x, pr.y - t.y, pr.z - t.z, pr.w - t.w};
+            float gr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float nabs = fabsf(d[k]);
+                if (P.beta < 1e-5f) {
+                    reg += nabs;
+                    gr[k] = d[k] > 0.0f ? inv : (d[k] < 0.0f ? -inv : 0.0f);
+                } else if (nabs < P.beta) {
+                    reg += 0.5f * nabs * nabs / P.beta;
+                    gr[k] = d[k] / P.beta * inv;
+                } else {
+                    reg += nabs - 0.5f * P.beta;
+                    gr[k] = d[k] > 0.0f ? inv : -inv;
+                }
+            }
+            gb = make_float4(gr[0], gr[1], gr[2], gr[3]);
+        }
+        if (WANT_GRAD) P.grad_bbox[row0 + threadIdx.x] = gb;
+    }
+
+    double s_neg = acc_neg, s_pos = acc_pos, s_reg = reg;
+    block_sum3(s_neg, s_pos, s_reg);
+    if (threadIdx.x == 0) {
+        double *o = P.partials + ((long long)n * P.chunks + chunk) * 2;
+        o[0] = (double)P.alpha * s_neg + s_pos;
+        o[1] = s_reg;
+    }
+}
+
+// Fixed-order final reduction: one warp per image over its chunk partials, then thread 0 over images.
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const double *__restrict__ partials,
+                                                            const int *__restrict__ fg_count, int N, int chunks,
+                                                            float batch_div, float *__restrict__ out_image,
+                                                            float *__restrict__ out_total) {
+    extern __shared__ double s_img[];   // [N][2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int n = warp; n < N; n += nw) {
+        double c = 0.0, r = 0.0;
+        for (int k = lane; k < chunks; k += 32) {
+            c += partials[((long long)n * chunks + k) * 2 + 0];
+            r += partials[((long long)n * chunks + k) * 2 + 1];
+        }
+        c = rn::warp_sum(c);
+        r = rn::warp_sum(r);
+        if (lane == 0) {
+            const int F = fg_count[n];
+            const double den = F > 0 ? (double)F : 1.0;     // clamp(F, min=1)  losses.py:108-109
+            c /= den;
+            r /= den;
+            s_img[2 * n] = c;
+            s_img[2 * n + 1] = r;
+            if (out_image) {
+                out_image[3 * n + 0] = (float)c;
+                out_image[3 * n + 1] = (float)r;
+                out_image[3 * n + 2] = (float)F;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0, r = 0.0;
+        for (int n = 0; n < N; ++n) { c += s_img[2 * n]; r += s_img[2 * n + 1]; }
+        out_total[0] = (float)(c / (double)batch_div);      // losses.py:138-140
+        out_total[1] = (float)(r / (double)batch_div);
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(float *__restrict__ buf, long long n, const float *__restrict__ scale) {
+    const float s = __ldg(scale);
+    if (s == 1.0f) return;
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float4 *b4 = (float4 *)buf;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = b4[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        b4[i] = v;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] *= s;
+}
+
+template <int VEC, bool WANT_GRAD, bool GAMMA2>
+void launch_loss(const LossParams &P, dim3 grid, cudaStream_t s, bool precise) {
+    if (precise)
+        loss_kernel<VEC, WANT_GRAD, GAMMA2, true><<<grid, LOSS_BLOCK, 0, s>>>(P);
+    else
+        loss_kernel<VEC, WANT_GRAD, GAMMA2, false><<<grid, LOSS_BLOCK, 0, s>>>(P);
+}
+template <int VEC, bool WANT_GRAD>
+void launch_loss_g(const LossParams &P, dim3 grid, cudaStream_t s, bool precise) {
+    if (P.gamma == 2.0f)
+        launch_loss<VEC, WANT_GRAD, true>(P, grid, s, precise);
+    else
+        launch_loss<VEC, WANT_GRAD, false>(P, grid, s, precise);
+}
+
+inline int loss_chunks(int64_t A) { return (int)((A + LOSS_SPAN - 1) / LOSS_SPAN); }
+
+}  // namespace
+
+extern "C" int rn_loss_set_math_mode(int mode) {
+    int old = g_math_mode;
+    g_math_mode = mode ? 1 : 0;
+    return old;
+}
+
+extern "C" size_t rn_loss_workspace_bytes(int N, int64_t A, int C) {
+    (void)C;
+    if (N <= 0 || A <= 0) return 16;
+    return (size_t)N * (size_t)loss_chunks(A) * 2 * sizeof(double);
+}
+
+extern "C" int rn_loss(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
+                       const float *gt_boxes,
+                       const int32_t *gt_off, const int32_t *codes, const int32_t *fg_count, int N, int64_t A, int C,
+                       float alpha, float gamma, float beta, const float *weights_host, float batch_div,
+                       float *out_image, float *out_total, float *grad_logits, float *grad_bbox, void *workspace,
+                       size_t workspace_bytes, rn_stream_t stream) {
+    RN_CHECK_ARG(logits && bbox && anchors && gt_off && codes && fg_count && out_total && weights_host, RN_E_BADARG,
+                 "rn_loss: null pointer");
+    RN_CHECK_ARG(N > 0 && A > 0 && C > 0, RN_E_BADARG, "rn_loss: N, A, C must be positive (got %d, %lld, %d)", N,
+                 (long long)A, C);
+    RN_CHECK_ARG(C <= 2048, RN_E_TOOLARGE, "rn_loss: C=%d exceeds 2048 classes", C);
+    RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_loss: N=%d exceeds 65535 images per call", N);
+    RN_CHECK_ARG((grad_logits == nullptr) == (grad_bbox == nullptr), RN_E_BADARG,
+                 "rn_loss: grad_logits and grad_bbox must be given together");
+    RN_CHECK_ARG(batch_div > 0.0f, RN_E_BADARG, "rn_loss: batch_div must be positive");
+    RN_CHECK_ARG(workspace && workspace_bytes >= rn_loss_workspace_bytes(N, A, C), RN_E_WORKSPACE,
+                 "rn_loss: workspace too small (%zu < %zu)", workspace_bytes, rn_loss_workspace_bytes(N, A, C));
+    RN_CHECK_ARG((size_t)N * 2 * sizeof(double) <= 96 * 1024, RN_E_TOOLARGE, "rn_loss: N too large for finalize");
+    cudaStream_t s = (cudaStream_t)stream;
+    LossParams P;
+    P.logits = logits; P.bbox = (const float4 *)bbox; P.anchors = (const float4 *)anchors;
+    P.gt = (const float4 *)gt_boxes; P.gt_off = gt_off; P.codes = codes; P.fg_count = fg_count;
+    P.grad_logits = grad_logits; P.grad_bbox = (float4 *)grad_bbox; P.partials = (double *)workspace;
+    P.A = A; P.anchor_stride = anchor_image_stride; P.C = C; P.chunks = loss_chunks(A);
+    P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
+    P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
+    const bool vec4 = (C % 4 == 0) && (((uintptr_t)logits & 15) == 0) && (!grad_logits || ((uintptr_t)grad_logits & 15) == 0);
+    const int CV = vec4 ? C / 4 : C;
+    P.magic = CV == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)CV - 1) / (unsigned)CV);
+    dim3 grid((unsigned)P.chunks, (unsigned)N);
+    const bool precise = g_math_mode == 1;
+    if (vec4) {
+        if (grad_logits) launch_loss_g<4, true>(P, grid, s, precise); else launch_loss_g<4, false>(P, grid, s, precise);
+    } else {
+        if (grad_logits) launch_loss_g<1, true>(P, grid, s, precise); else launch_loss_g<1, false>(P, grid, s, precise);
+    }
+    RN_CHECK_LAUNCH("rn_loss");
+    size_t smem = (size_t)N * 2 * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    loss_finalize_kernel<<<1, 256, smem, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
+                                              out_total);
+    RN_CHECK_LAUNCH("rn_loss_finalize");
+    return 0;
+}
+
+extern "C" int rn_scale_by_device_scalar(float *buf, int64_t n, const float *scale, rn_stream_t stream) {
+    RN_CHECK_ARG(buf && scale && n >= 0, RN_E_BADARG, "rn_scale_by_device_scalar: bad argument");
+    if (n == 0) return 0;
+    RN_CHECK_ARG(((uintptr_t)buf & 15) == 0, RN_E_BADARG, "rn_scale_by_device_scalar: buffer not 16-byte aligned");
+    scale_kernel<<<RN_SM_COUNT_B200 * 8, 256, 0, (cudaStream_t)stream>>>(buf, (long long)n, scale);
+    RN_CHECK_LAUNCH("rn_scale_by_device_scalar");
+    return 0;
+}

@@ -1,0 +1,199 @@
+// Fused anchor x GT IoU + first-index argmax + strict fg/bg thresholds for a whole batch.
+// Replaces matcher (retinanet/box_utils.py:51-80) + torchvision box_iou (tv:ops/boxes.py:319-371).
+//
+// Roofline: instruction throughput (ALU), not HBM — traffic is 16 B in + 8(+4) B out per anchor,
+// work is A x G IoU pairs.  The [G,A] IoU matrix of the reference is never materialised.
+//
+// Design
+//  * one thread per anchor, one CTA row per image; the image's GT boxes are staged in shared
+//    memory (box, area, "malformed" flag) in tiles of GT_TILE;
+//  * warp-cooperative culling: each warp reduces the bounding box of its 32 anchors with
+//    shuffles, then the 32 lanes test 32 GT boxes at a time against it and a ballot yields the
+//    list of GT boxes that can have non-zero intersection with ANY anchor of the warp; only those
+//    are evaluated.  A culled pair has clamp(rb-lt,0)=0 in at least one axis, so its IoU is
+//    exactly +0 — bit-identical to evaluating it;
+//  * the IEEE division is only issued for pairs whose IoU can reach bg_thr: pairs with
+//    inter < bg_thr*(1-2^-20)*union are provably below bg_thr after rounding and can neither
+//    change the fg/bg/ignore decision nor win the argmax of a foreground anchor;
+//  * every surviving pair is evaluated with individually rounded fp32 ops (__fmul_rn/__fadd_rn/
+//    __fsub_rn/__fdiv_rn, no FMA contraction) in the reference's operation order, so the result is
+//    bit-identical to torch on CPU or CUDA; ties keep the lowest GT index, NaN propagates
+//    (torch.max semantics);
+//  * culling/pruning rely on 0 < bg_thr < fg_thr and on well-formed boxes (finite, x2>=x1,
+//    y2>=y1, anchors with positive area); malformed GT boxes or anchors fall back — per GT box /
+//    per warp — to the unculled NaN-propagating path, other thresholds disable both tricks.
+#include "rn_common.cuh"
+
+namespace {
+
+constexpr int GT_TILE = 512;
+constexpr int MATCH_BLOCK = 256;
+
+// torch.max / torch.min / clamp(min=0) propagate NaN; fmaxf/fminf do not.
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+__device__ __forceinline__ float nan_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
+
+__device__ __forceinline__ float box_area(const float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// Full reference arithmetic, NaN-propagating (slow path for malformed boxes / exotic thresholds).
+__device__ __forceinline__ float iou_generic(const float4 g, float ag, const float4 a, float aa) {
+    float w = __fsub_rn(nan_min(g.z, a.z), nan_max(g.x, a.x));
+    float h = __fsub_rn(nan_min(g.w, a.w), nan_max(g.y, a.y));
+    w = (w != w) ? w : fmaxf(w, 0.0f);
+    h = (h != h) ? h : fmaxf(h, 0.0f);
+    float inter = __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(ag, aa), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+__device__ __forceinline__ bool box_well_formed(const float4 b) {
+    // finite coordinates and non-negative extent (NaN fails every comparison)
+    return (b.z >= b.x) && (b.w >= b.y) && (fabsf(b.x) <= 3.0e38f) && (fabsf(b.y) <= 3.0e38f) &&
+           (fabsf(b.z) <= 3.0e38f) && (fabsf(b.w) <= 3.0e38f);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(MATCH_BLOCK)
+match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_stride,
+             const float4 *__restrict__ gt,
+             const long long *__restrict__ labels, const int *__restrict__ gt_off, float fg_thr, float bg_thr,
+             float prune_c, long long *__restrict__ matches, int *__restrict__ codes, int *__restrict__ fg_count) {
+    __shared__ float4 s_box[GT_TILE];
+    __shared__ float s_area[GT_TILE];
+    __shared__ unsigned char s_bad[GT_TILE];
+
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const long long ai = (long long)blockIdx.x * MATCH_BLOCK + threadIdx.x;
+    const bool live = ai < A;
+    const int g0 = gt_off[n];
+    const int G = gt_off[n + 1] - g0;
+
+    float4 a = make_float4(0.f, 0.f, 1.f, 1.f);
+    if (live) a = anchors[(long long)n * anchor_stride + ai];
+    const float aa = box_area(a);
+
+    // warp-uniform: may this warp use culling / pruning / the non-NaN fast path?
+    bool warp_fast = FAST;
+    float bx1 = 0.f, by1 = 0.f, bx2 = 0.f, by2 = 0.f;
+    if (FAST) {
+        bool ok = !live || (box_well_formed(a) && aa > 0.0f && aa <= 3.0e38f);
+        warp_fast = __all_sync(0xffffffffu, ok);
+        bx1 = rn::warp_min(live ? a.x : INFINITY);
+        by1 = rn::warp_min(live ? a.y : INFINITY);
+        bx2 = rn::warp_max(live ? a.z : -INFINITY);
+        by2 = rn::warp_max(live ? a.w : -INFINITY);
+    }
+
+    float best = warp_fast ? 0.0f : -INFINITY;
+    int bi = 0;
+
+    for (int t0 = 0; t0 < G; t0 += GT_TILE) {
+        const int tn = min(GT_TILE, G - t0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < tn; j += MATCH_BLOCK) {
+            float4 g = gt[g0 + t0 + j];
+            float ag = box_area(g);
+            s_box[j] = g;
+            s_area[j] = ag;
+            s_bad[j] = !(box_well_formed(g) && ag <= 3.0e38f);
+        }
+        __syncthreads();
+
+        for (int base = 0; base < tn; base += 32) {
+            unsigned mask;
+            {
+                const int j = base + lane;
+                bool hit = j < tn;
+                if (hit && warp_fast) {
+                    float4 g = s_box[j];
+                    float w = __fsub_rn(fminf(g.z, bx2), fmaxf(g.x, bx1));
+                    float h = __fsub_rn(fminf(g.w, by2), fmaxf(g.y, by1));
+                    hit = s_bad[j] || (w > 0.0f && h > 0.0f);
+                }
+                mask = __ballot_sync(0xffffffffu, hit);
+            }
+            while (mask) {
+                const int j = base + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 g = s_box[j];
+                const float ag = s_area[j];
+                const int gi = t0 + j;
+                if (warp_fast && !s_bad[j]) {
+                    // well-formed pair: no NaN possible, IoU is +0 unless both extents are positive
+                    float w = __fsub_rn(fminf(g.z, a.z), fmaxf(g.x, a.x));
+                    float h = __fsub_rn(fminf(g.w, a.w), fmaxf(g.y, a.y));
+                    if (w > 0.0f && h > 0.0f) {
+                        float inter = __fmul_rn(w, h);
+                        float uni = __fsub_rn(__fadd_rn(ag, aa), inter);
+                        if (inter >= __fmul_rn(uni, prune_c)) {   // may reach bg_thr: exact quotient
+                            float v = __fdiv_rn(inter, uni);
+                            if (v > best) { best = v; bi = gi; }
+                        }
+                    }
+                } else {
+                    float v = iou_generic(g, ag, a, aa);
+                    if (best == best) {                             // NaN, once taken, stays
+                        if (v != v || v > best) { best = v; bi = gi; }
+                    }
+                }
+            }
+        }
+    }
+
+    long long m = -2;
+    if (G > 0) {
+        if (best < bg_thr) m = -1;
+        if (best > fg_thr) m = bi;
+    }
+    if (live) {
+        if (matches) matches[(long long)n * A + ai] = m;
+        if (codes) {
+            int code = (int)m;
+            if (m >= 0) {
+                int col = (int)labels[g0 + m] - 1;                  // labels are 1-based (README.md:132)
+                code = (int)m | (col << 20);
+            }
+            codes[(long long)n * A + ai] = code;
+        }
+    }
+    if (fg_count) {
+        unsigned fgm = __ballot_sync(0xffffffffu, live && m >= 0);
+        if (lane == 0 && fgm) atomicAdd(fg_count + n, __popc(fgm));
+    }
+}
+
+}  // namespace
+
+extern "C" int rn_match(const float *anchors, int64_t A, int64_t anchor_image_stride, const float *gt_boxes, const int64_t *gt_labels,
+                        const int32_t *gt_off, int N, float fg_thr, float bg_thr, int64_t *matches, int32_t *codes,
+                        int32_t *fg_count, rn_stream_t stream) {
+    RN_CHECK_ARG(anchors && gt_off, RN_E_BADARG, "rn_match: null anchors/gt_off");
+    RN_CHECK_ARG(A >= 0 && N >= 0, RN_E_BADARG, "rn_match: negative size");
+    RN_CHECK_ARG(anchor_image_stride == 0 || anchor_image_stride >= A, RN_E_BADARG, "rn_match: bad anchor_image_stride");
+    RN_CHECK_ARG(fg_thr > bg_thr, RN_E_BADARG, "rn_match: match_thr (%g) must exceed back_thr (%g) (box_utils.py:66)",
+                 (double)fg_thr, (double)bg_thr);
+    RN_CHECK_ARG(!codes || gt_labels, RN_E_BADARG, "rn_match: codes requested without gt_labels");
+    RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_match: N=%d exceeds 65535 images per call", N);
+    if (A == 0 || N == 0) return 0;
+    dim3 grid((unsigned)((A + MATCH_BLOCK - 1) / MATCH_BLOCK), (unsigned)N);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool fast = bg_thr > 0.0f;  // then fg_thr > bg_thr > 0: culling and pruning are exact
+    if (fast) {
+        // inter < uni*bg*(1-2^-20)  =>  fl(inter/uni) < bg   (rounding slack is 2^-23 per op)
+        float prune_c = bg_thr * (1.0f - 9.5367431640625e-07f);
+        match_kernel<true><<<grid, MATCH_BLOCK, 0, s>>>((const float4 *)anchors, A, anchor_image_stride,
+                                                        (const float4 *)gt_boxes,
+                                                        (const long long *)gt_labels, gt_off, fg_thr, bg_thr, prune_c,
+                                                        (long long *)matches, codes, fg_count);
+    } else {
+        match_kernel<false><<<grid, MATCH_BLOCK, 0, s>>>((const float4 *)anchors, A, anchor_image_stride,
+                                                        (const float4 *)gt_boxes,
+                                                         (const long long *)gt_labels, gt_off, fg_thr, bg_thr, 0.0f,
+                                                         (long long *)matches, codes, fg_count);
+    }
+    RN_CHECK_LAUNCH("rn_match");
+    return 0;
+}

@@ -1,0 +1,677 @@
+// Inference post-processing for a whole batch.
+// Replaces Retinanet.process_detections (retinanet/models.py:160-243) and the torchvision ops it
+// calls (clip_boxes_to_image, remove_small_boxes, nms).
+//
+// Pipeline (all on one stream, no host synchronisation):
+//  K1 score_filter   HBM-bound streaming pass over the [N,A,C] logits with 128-bit loads.  The
+//                    strict test sigmoid(x) > thr is decided by ONE float compare against a guard
+//                    logit x_lo (slightly below logit(thr)); only the rare survivors evaluate the
+//                    exact sigmoid 1/(1+exp(-x)) (bit-identical to torch's CUDA kernel), decode +
+//                    clip their box (reference quirk included) and apply the 0.01 small-box filter.
+//                    Survivors are staged in shared memory and flushed to a global pool with one
+//                    atomic per CTA; a histogram over (image,class) segments is built on the fly.
+//                    key = (~score_bits << 32) | anchor  — ascending key = score desc, anchor asc.
+//  K2 segment_scan   exclusive scan of the segment histogram (one CTA).
+//  K3 scatter        counting-sort scatter of the pool into segment-contiguous order.
+//  K4 nms            one CTA per (image,class) segment: bitonic sort of the keys (shared memory,
+//                    or in place in global memory for huge segments), then greedy NMS in chunks of
+//                    256: (a) suppression by previously kept boxes, (b) 256x256 IoU bitmask,
+//                    (c) warp-cooperative serial resolve of the bitmask, (d) compaction of the kept
+//                    boxes.  Exact torchvision CPU semantics: stable score order (ties -> lower
+//                    anchor index), suppress iff fl(inter/(a_i+a_j-inter)) > thr, per class only.
+//  K5 image_topk     one CTA per image: 4-pass 8-bit radix select of the max_det-th score over
+//                    all kept boxes, deterministic tie handling (class asc, anchor asc), bitonic
+//                    sort of the <= max_det winners, output write (labels + 1).
+#include "rn_common.cuh"
+
+namespace {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int PP_BLOCK = 256;
+constexpr int PP_SPAN = 256;       // anchors per CTA in K1
+constexpr int PP_U = 4;
+constexpr int PP_STAGE = 1024;     // staged candidates per CTA
+constexpr int NMS_CHUNK = 256;
+constexpr int SORT_SMEM = 2048;    // keys sorted in shared memory
+constexpr int MAX_DET_CAP = 1024;
+
+struct PPWorkspace {
+    u32 *pool_count;     // [1] candidates found (may exceed capacity)
+    int *seg_count;      // [S]
+    int *seg_off;        // [S+1]
+    int *cursor;         // [S]
+    int *kept_count;     // [S]
+    u64 *pool_key;       // [cap]
+    u32 *pool_seg;       // [cap]
+    u64 *sorted_key;     // [cap]
+    u64 *kept_key;       // [cap]
+    float4 *kept_box;    // [cap]
+    size_t zero_bytes;   // leading bytes that must be zeroed per call
+    size_t total_bytes;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+PPWorkspace carve(void *base, int N, int C, int64_t cap) {
+    PPWorkspace w;
+    const size_t S = (size_t)N * (size_t)C;
+    char *p = (char *)base;
+    size_t o = 0;
+    w.pool_count = (u32 *)(p + o); o += 256;
+    w.seg_count = (int *)(p + o); o = align_up(o + S * 4, 256);
+    w.zero_bytes = o;
+    w.seg_off = (int *)(p + o); o = align_up(o + (S + 1) * 4, 256);
+    w.cursor = (int *)(p + o); o = align_up(o + S * 4, 256);
+    w.kept_count = (int *)(p + o); o = align_up(o + S * 4, 256);
+    w.pool_key = (u64 *)(p + o); o = align_up(o + (size_t)cap * 8, 256);
+    w.pool_seg = (u32 *)(p + o); o = align_up(o + (size_t)cap * 4, 256);
+    w.sorted_key = (u64 *)(p + o); o = align_up(o + (size_t)cap * 8, 256);
+    w.kept_key = (u64 *)(p + o); o = align_up(o + (size_t)cap * 8, 256);
+    w.kept_box = (float4 *)(p + o); o = align_up(o + (size_t)cap * 16, 256);
+    w.total_bytes = o;
+    return w;
+}
+
+// decode + clip of one anchor: activ_2_bbox (box_utils.py:37-48) then clip_boxes_to_image
+// (tv:ops/boxes.py:149-182: x in [0,w], y in [0,h]).
+__device__ __forceinline__ float4 decode_clip(const float4 *__restrict__ bbox, const float4 *__restrict__ anchors,
+                                              long long row, long long anchor_row, float4 wts, float imw,
+                                              float imh) {
+    float4 b = rn::decode_box(__ldg(bbox + row), __ldg(anchors + anchor_row), wts);
+    b.x = rn::clampf(b.x, 0.0f, imw);
+    b.z = rn::clampf(b.z, 0.0f, imw);
+    b.y = rn::clampf(b.y, 0.0f, imh);
+    b.w = rn::clampf(b.w, 0.0f, imh);
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------- K1
+struct FilterParams {
+    const float *logits;
+    const float4 *bbox;
+    const float4 *anchors;
+    const int *im_hw;
+    long long A;
+    long long anchor_stride;
+    int C;
+    unsigned magic;
+    float x_lo, thr;
+    float4 wts;
+    u32 cap;
+    PPWorkspace w;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(PP_BLOCK) score_filter_kernel(const FilterParams P) {
+    __shared__ u64 st_key[PP_STAGE];
+    __shared__ u32 st_seg[PP_STAGE];
+    __shared__ int st_n;
+    __shared__ u32 st_base;
+
+    const int n = blockIdx.y;
+    const long long a0 = (long long)blockIdx.x * PP_SPAN;
+    const int span = (int)min((long long)PP_SPAN, P.A - a0);
+    const long long row0 = (long long)n * P.A + a0;
+    const int CV = P.C / VEC;
+    const int nvec = span * CV;
+    const float *src = P.logits + row0 * P.C;
+    const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
+    if (threadIdx.x == 0) st_n = 0;
+    __syncthreads();
+
+    for (int base = 0; base < nvec; base += PP_BLOCK * PP_U) {
+        float v[PP_U][VEC];
+#pragma unroll
+        for (int u = 0; u < PP_U; ++u) {
+            const int f = base + u * PP_BLOCK + threadIdx.x;
+            if (VEC == 4) {
+                float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                if (f < nvec) t = rn::ld_stream_f4((const float4 *)src + f);
+                v[u][0] = t.x; v[u][VEC > 1 ? 1 : 0] = t.y; v[u][VEC > 2 ? 2 : 0] = t.z; v[u][VEC > 3 ? 3 : 0] = t.w;
+            } else {
+                v[u][0] = f < nvec ? __ldg(src + f) : -INFINITY;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PP_U; ++u) {
+            float vmax = v[u][0];
+#pragma unroll
+            for (int k = 1; k < VEC; ++k) vmax = fmaxf(vmax, v[u][k]);
+            if (vmax > P.x_lo) {                                   // rare
+                const int f = base + u * PP_BLOCK + threadIdx.x;
+                const int al = P.magic ? (int)__umulhi((unsigned)f, P.magic) : f;
+                const int c0 = (f - al * CV) * VEC;
+                const long long anchor = a0 + al;
+                bool have_box = false, box_ok = false;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    if (!(v[u][k] > P.x_lo)) continue;
+                    const float s = rn::sigmoid_ref(v[u][k]);
+                    if (!(s > P.thr)) continue;                    // models.py:196 strict >
+                    if (!have_box) {
+                        const float4 b = decode_clip(P.bbox, P.anchors, row0 + al, (long long)n * P.anchor_stride + anchor, P.wts,
+                                                       imw, imh);
+                        // remove_small_boxes(min_size=1e-2), models.py:203
+                        box_ok = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);
+                        have_box = true;
+                    }
+                    if (!box_ok) break;
+                    const u64 key = ((u64)(~__float_as_uint(s)) << 32) | (u64)(u32)anchor;
+                    const u32 seg = (u32)(n * P.C + c0 + k);
+                    const int pos = atomicAdd(&st_n, 1);
+                    if (pos < PP_STAGE) {
+                        st_key[pos] = key;
+                        st_seg[pos] = seg;
+                    } else {                                       // staging full: go straight to the pool
+                        const u32 gp = atomicAdd(P.w.pool_count, 1u);
+                        if (gp < P.cap) {
+                            P.w.pool_key[gp] = key;
+                            P.w.pool_seg[gp] = seg;
+                            atomicAdd(P.w.seg_count + seg, 1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int staged = min(st_n, PP_STAGE);
+    if (staged == 0) return;
+    if (threadIdx.x == 0) st_base = atomicAdd(P.w.pool_count, (u32)staged);
+    __syncthreads();
+    const u32 gbase = st_base;
+    for (int i = threadIdx.x; i < staged; i += PP_BLOCK) {
+        const u32 gp = gbase + (u32)i;
+        if (gp < P.cap) {
+            P.w.pool_key[gp] = st_key[i];
+            P.w.pool_seg[gp] = st_seg[i];
+            atomicAdd(P.w.seg_count + st_seg[i], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K2
+__global__ void __launch_bounds__(1024) segment_scan_kernel(const int *__restrict__ seg_count, int S,
+                                                            int *__restrict__ seg_off, int *__restrict__ cursor,
+                                                            const u32 *__restrict__ pool_count, u32 cap,
+                                                            int *__restrict__ status) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+        if (status) { status[0] = (int)min(*pool_count, 0x7fffffffu); status[1] = (int)cap; }
+    }
+    __syncthreads();
+    for (int base = 0; base < S; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < S ? seg_count[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+        if (i < S) { seg_off[i] = excl; cursor[i] = excl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg_off[S] = s_carry;
+}
+
+// ------------------------------------------------------------------------------------------- K3
+__global__ void __launch_bounds__(256) scatter_kernel(const u64 *__restrict__ pool_key, const u32 *__restrict__ pool_seg,
+                                                      const u32 *__restrict__ pool_count, u32 cap,
+                                                      int *__restrict__ cursor, u64 *__restrict__ sorted_key) {
+    const u32 total = min(*pool_count, cap);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int pos = atomicAdd(cursor + pool_seg[i], 1);
+        sorted_key[pos] = pool_key[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K4
+// Bitonic sort (ascending) of n keys for arbitrary n: every merge runs in the same direction
+// (first step pairs i with i ^ (k-1)), so absent elements behave as +inf padding at the end.
+__device__ void block_bitonic_sort(u64 *keys, int n) {
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int j = i ^ (k - 1);
+            if (j > i && j < n) {
+                const u64 a = keys[i], b = keys[j];
+                if (a > b) { keys[i] = b; keys[j] = a; }
+            }
+        }
+        __syncthreads();
+        for (int d = k >> 2; d > 0; d >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int j = i ^ d;
+                if (j > i && j < n) {
+                    const u64 a = keys[i], b = keys[j];
+                    if (a > b) { keys[i] = b; keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// torchvision nms (CPU kernel) pair test: suppressed iff fl(inter / (area_i + area_j - inter)) > thr.
+__device__ __forceinline__ bool nms_suppresses(const float4 a, float area_a, const float4 b, float area_b, float thr) {
+    const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (!(w > 0.0f && h > 0.0f)) {
+        // inter = 0 -> ovr is 0 (or NaN when both areas are 0): never > thr for thr >= 0
+        if (thr >= 0.0f) return false;
+    }
+    const float inter = __fmul_rn(fmaxf(w, 0.0f), fmaxf(h, 0.0f));
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return ovr > thr;
+}
+__device__ __forceinline__ float nms_area(const float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+struct NmsParams {
+    const float4 *bbox;      // DECODE mode: [N,A,4] activations
+    const float4 *anchors;
+    const int *im_hw;
+    const float4 *boxes;     // RAW mode: [K,4] boxes already sorted per segment
+    unsigned char *keep_flags;  // RAW mode output
+    long long A;
+    long long anchor_stride;
+    int C;
+    float thr;
+    float4 wts;
+    const int *seg_off;
+    u64 *sorted_key;
+    u64 *kept_key;
+    float4 *kept_box;
+    int *kept_count;
+};
+
+template <bool RAW>
+__global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
+    __shared__ u64 s_keys[RAW ? 1 : SORT_SMEM];
+    __shared__ float4 s_box[NMS_CHUNK];
+    __shared__ float s_area[NMS_CHUNK];
+    __shared__ u32 s_mask[NMS_CHUNK][NMS_CHUNK / 32];
+    __shared__ u32 s_removed[NMS_CHUNK / 32];
+    __shared__ int s_wbase[NMS_CHUNK / 32 + 1];
+
+    const int seg = blockIdx.x;
+    const int off = P.seg_off[seg];
+    const int cnt = P.seg_off[seg + 1] - off;
+    if (cnt <= 0) {
+        if (!RAW && threadIdx.x == 0) P.kept_count[seg] = 0;
+        return;
+    }
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    long long img_row = 0, anc_row = 0;
+    float imw = 0.f, imh = 0.f;
+    u64 *keys = nullptr;
+    if (!RAW) {
+        const int n = seg / P.C;
+        img_row = (long long)n * P.A;
+        anc_row = (long long)n * P.anchor_stride;
+        imh = (float)P.im_hw[2 * n];
+        imw = (float)P.im_hw[2 * n + 1];
+        keys = P.sorted_key + off;
+        if (cnt <= SORT_SMEM) {
+            for (int i = t; i < cnt; i += NMS_CHUNK) s_keys[i] = keys[i];
+            __syncthreads();
+            block_bitonic_sort(s_keys, cnt);
+            for (int i = t; i < cnt; i += NMS_CHUNK) keys[i] = s_keys[i];
+        } else {
+            block_bitonic_sort(keys, cnt);
+        }
+        __syncthreads();
+    }
+
+    int K = 0;   // kept so far (block-uniform)
+    for (int c0 = 0; c0 < cnt; c0 += NMS_CHUNK) {
+        const int m = min(NMS_CHUNK, cnt - c0);
+        // (0) load this chunk's boxes
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        u64 key = 0;
+        if (t < m) {
+            if (RAW) {
+                b = P.boxes[off + c0 + t];
+            } else {
+                key = keys[c0 + t];
+                const long long anchor = (long long)(u32)key;
+                b = decode_clip(P.bbox, P.anchors, img_row + anchor, anc_row + anchor, P.wts, imw, imh);
+            }
+        }
+        const float area = nms_area(b);
+        // (a) suppression by boxes kept in earlier chunks (tiles of NMS_CHUNK through shared memory)
+        bool alive = t < m;
+        for (int k0 = 0; k0 < K; k0 += NMS_CHUNK) {
+            const int kn = min(NMS_CHUNK, K - k0);
+            __syncthreads();
+            if (t < kn) {
+                const float4 kb = P.kept_box[off + k0 + t];
+                s_box[t] = kb;
+                s_area[t] = nms_area(kb);
+            }
+            __syncthreads();
+            if (alive) {
+                for (int k = 0; k < kn; ++k)
+                    if (nms_suppresses(s_box[k], s_area[k], b, area, P.thr)) { alive = false; break; }
+            }
+        }
+        __syncthreads();
+        // (b) in-chunk bitmask: row t = boxes j > t suppressed by t
+        s_box[t] = b;
+        s_area[t] = area;
+        {
+            const u32 dead = __ballot_sync(0xffffffffu, !alive);
+            if (lane == 0) s_removed[warp] = dead;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int w = 0; w < NMS_CHUNK / 32; ++w) {
+            u32 bits = 0;
+            if (alive && w * 32 + 31 > t && w * 32 < m) {
+                const int jlo = max(w * 32, t + 1), jhi = min(w * 32 + 32, m);
+                for (int j = jlo; j < jhi; ++j)
+                    if (nms_suppresses(b, area, s_box[j], s_area[j], P.thr)) bits |= 1u << (j & 31);
+            }
+            s_mask[t][w] = bits;
+        }
+        __syncthreads();
+        // (c) warp-cooperative serial resolve: lane w owns the removed-word w
+        if (warp == 0) {
+            u32 rw = lane < NMS_CHUNK / 32 ? s_removed[lane] : 0u;
+            for (int i = 0; i < m; ++i) {
+                const u32 r = __shfl_sync(0xffffffffu, rw, i >> 5);
+                if (!((r >> (i & 31)) & 1u)) {
+                    if (lane < NMS_CHUNK / 32) rw |= s_mask[i][lane];
+                }
+            }
+            if (lane < NMS_CHUNK / 32) s_removed[lane] = rw;
+        }
+        __syncthreads();
+        // (d) compaction of the kept boxes of this chunk
+        const bool kept = t < m && !((s_removed[warp] >> lane) & 1u);
+        const u32 km = __ballot_sync(0xffffffffu, kept);
+        if (lane == 0) s_wbase[warp + 1] = __popc(km);
+        __syncthreads();
+        if (t == 0) {
+            s_wbase[0] = 0;
+            for (int w = 0; w < NMS_CHUNK / 32; ++w) s_wbase[w + 1] += s_wbase[w];
+        }
+        __syncthreads();
+        if (RAW) {
+            if (t < m) P.keep_flags[off + c0 + t] = kept ? 1 : 0;
+        }
+        if (kept) {
+            const int pos = off + K + s_wbase[warp] + __popc(km & ((1u << lane) - 1u));
+            P.kept_box[pos] = b;
+            if (!RAW) P.kept_key[pos] = key;
+        }
+        K += s_wbase[NMS_CHUNK / 32];
+        __syncthreads();
+    }
+    if (!RAW && t == 0) P.kept_count[seg] = K;
+}
+
+// ------------------------------------------------------------------------------------------- K5
+struct TopkParams {
+    const int *seg_off;
+    const int *kept_count;
+    const u64 *kept_key;
+    const float4 *kept_box;
+    int C;
+    int max_det;
+    float *out_boxes;
+    float *out_scores;
+    long long *out_labels;
+    int *out_count;
+};
+
+__global__ void __launch_bounds__(PP_BLOCK) image_topk_kernel(const TopkParams P) {
+    extern __shared__ int s_dyn[];            // [C] per-class tie counts / prefix
+    __shared__ u32 s_hist[256];
+    __shared__ u32 s_prefix, s_mask_bits, s_need;   // radix-select state
+    __shared__ int s_total, s_nsel;
+    __shared__ u64 s_sel_hi[MAX_DET_CAP];     // (inverted score << 32) | class
+    __shared__ u32 s_sel_lo[MAX_DET_CAP];     // anchor
+    __shared__ int s_sel_pos[MAX_DET_CAP];    // index into kept arrays
+
+    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = PP_BLOCK / 32;
+    const int C = P.C, seg0 = n * C;
+    if (t == 0) { s_total = 0; s_nsel = 0; }
+    __syncthreads();
+    {
+        int local = 0;
+        for (int c = t; c < C; c += PP_BLOCK) local += P.kept_count[seg0 + c];
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane == 0) atomicAdd(&s_total, local);
+    }
+    __syncthreads();
+    const int total = s_total;
+    const int want = min(total, P.max_det);
+    if (t == 0) P.out_count[n] = want;
+    if (want == 0) return;
+
+    // ---- radix select of the want-th smallest inverted-score (only when total > max_det) ----
+    u32 thr_hi = 0xffffffffu;     // select everything with hi < thr_hi, plus ranked ties == thr_hi
+    int need_ties = 0;
+    bool select_all = total <= P.max_det;
+    if (!select_all) {
+        if (t == 0) { s_prefix = 0; s_mask_bits = 0; s_need = (u32)want; }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = t; i < 256; i += PP_BLOCK) s_hist[i] = 0;
+            __syncthreads();
+            const u32 prefix = s_prefix, mbits = s_mask_bits;
+            for (int c = warp; c < C; c += nw) {
+                const int off = P.seg_off[seg0 + c], kc = P.kept_count[seg0 + c];
+                for (int k = lane; k < kc; k += 32) {
+                    const u32 hi = (u32)(P.kept_key[off + k] >> 32);
+                    if ((hi & mbits) == prefix) atomicAdd(&s_hist[(hi >> shift) & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            if (t == 0) {
+                u32 need = s_need, acc = 0;
+                int bkt = 0;
+                for (; bkt < 256; ++bkt) {
+                    if (acc + s_hist[bkt] >= need) break;
+                    acc += s_hist[bkt];
+                }
+                s_need = need - acc;
+                s_prefix = prefix | ((u32)bkt << shift);
+                s_mask_bits = mbits | (255u << shift);
+            }
+            __syncthreads();
+        }
+        thr_hi = s_prefix;
+        need_ties = (int)s_need;     // how many entries with hi == thr_hi are taken (>= 1)
+    }
+
+    // ---- per-class tie counts -> exclusive prefix (class asc, then anchor asc inside a class) ----
+    if (!select_all) {
+        for (int c = warp; c < C; c += nw) {
+            const int off = P.seg_off[seg0 + c], kc = P.kept_count[seg0 + c];
+            int cntc = 0;
+            for (int k = lane; k < kc; k += 32) cntc += ((u32)(P.kept_key[off + k] >> 32) == thr_hi);
+            for (int o = 16; o > 0; o >>= 1) cntc += __shfl_xor_sync(0xffffffffu, cntc, o);
+            if (lane == 0) s_dyn[c] = cntc;
+        }
+        __syncthreads();
+        if (t == 0) {
+            int acc = 0;
+            for (int c = 0; c < C; ++c) { const int v = s_dyn[c]; s_dyn[c] = acc; acc += v; }
+        }
+        __syncthreads();
+    }
+
+    // ---- collect the winners ----
+    for (int c = warp; c < C; c += nw) {
+        const int off = P.seg_off[seg0 + c], kc = P.kept_count[seg0 + c];
+        int tie_seen = 0;    // ties of this class seen in previous iterations (kept list is sorted)
+        for (int k0 = 0; k0 < kc; k0 += 32) {
+            const int k = k0 + lane;
+            u64 key = 0;
+            bool is_lt = false, is_tie = false;
+            if (k < kc) {
+                key = P.kept_key[off + k];
+                const u32 hi = (u32)(key >> 32);
+                is_lt = select_all || hi < thr_hi;
+                is_tie = !select_all && hi == thr_hi;
+            }
+            const u32 tm = __ballot_sync(0xffffffffu, is_tie);
+            bool take = is_lt;
+            if (is_tie) {
+                const int rank = s_dyn[c] + tie_seen + __popc(tm & ((1u << lane) - 1u));
+                take = rank < need_ties;
+            }
+            tie_seen += __popc(tm);
+            if (take) {
+                const int slot = atomicAdd(&s_nsel, 1);
+                if (slot < MAX_DET_CAP) {
+                    s_sel_hi[slot] = (key & 0xffffffff00000000ull) | (u64)(u32)c;
+                    s_sel_lo[slot] = (u32)key;
+                    s_sel_pos[slot] = off + k;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int nsel = min(s_nsel, want);
+
+    // ---- order the winners: (score desc, class asc, anchor asc).  Rank by counting (nsel <= 1024). ----
+    for (int i = t; i < nsel; i += PP_BLOCK) {
+        const u64 hi = s_sel_hi[i];
+        const u32 lo = s_sel_lo[i];
+        int rank = 0;
+        for (int j = 0; j < nsel; ++j) {
+            const u64 hj = s_sel_hi[j];
+            rank += (hj < hi) || (hj == hi && s_sel_lo[j] < lo);
+        }
+        const int pos = s_sel_pos[i];
+        const float4 b = P.kept_box[pos];
+        const long long o = (long long)n * P.max_det + rank;
+        ((float4 *)P.out_boxes)[o] = b;
+        P.out_scores[o] = __uint_as_float(~(u32)(hi >> 32));
+        P.out_labels[o] = (long long)(u32)hi + 1;          // models.py:230 labels + 1
+    }
+}
+
+}  // namespace
+
+extern "C" size_t rn_postprocess_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det) {
+    (void)A; (void)max_det;
+    if (N <= 0 || C <= 0 || cand_capacity < 0) return 0;
+    return carve(nullptr, N, C, cand_capacity).total_bytes;
+}
+
+extern "C" int rn_postprocess(const float *logits, const float *bbox, const float *anchors,
+                              int64_t anchor_image_stride, const int32_t *im_hw, int N,
+                              int64_t A, int C, float score_thr, double nms_thr, int max_det,
+                              const float *weights_host, int pre_nms_topk, const int64_t *level_off_host,
+                              int num_levels, int64_t cand_capacity, float *out_boxes, float *out_scores,
+                              int64_t *out_labels, int32_t *out_count, int32_t *out_status, void *workspace,
+                              size_t workspace_bytes, rn_stream_t stream) {
+    (void)level_off_host; (void)num_levels;
+    RN_CHECK_ARG(logits && bbox && anchors && im_hw && weights_host && out_boxes && out_scores && out_labels &&
+                     out_count && out_status && workspace,
+                 RN_E_BADARG, "rn_postprocess: null pointer");
+    RN_CHECK_ARG(N > 0 && A > 0 && C > 0, RN_E_BADARG, "rn_postprocess: N, A, C must be positive");
+    RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_postprocess: N=%d exceeds 65535", N);
+    RN_CHECK_ARG(A < (1LL << 32), RN_E_TOOLARGE, "rn_postprocess: A exceeds 2^32");
+    RN_CHECK_ARG(C <= 8192, RN_E_TOOLARGE, "rn_postprocess: C=%d exceeds 8192", C);
+    RN_CHECK_ARG(max_det >= 1 && max_det <= MAX_DET_CAP, RN_E_TOOLARGE, "rn_postprocess: max_det=%d outside [1,%d]",
+                 max_det, MAX_DET_CAP);
+    RN_CHECK_ARG(cand_capacity >= 1 && cand_capacity < 0x7fffffffLL, RN_E_BADARG, "rn_postprocess: bad cand_capacity");
+    RN_CHECK_ARG(pre_nms_topk == 0, RN_E_BADARG, "rn_postprocess: pre_nms_topk is not implemented in this build");
+    RN_CHECK_ARG((size_t)N * C < 0x7fffffffULL, RN_E_TOOLARGE, "rn_postprocess: N*C too large");
+    PPWorkspace w = carve(workspace, N, C, cand_capacity);
+    RN_CHECK_ARG(workspace_bytes >= w.total_bytes, RN_E_WORKSPACE, "rn_postprocess: workspace too small (%zu < %zu)",
+                 workspace_bytes, w.total_bytes);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, w.zero_bytes, s);
+    if (e != cudaSuccess) { rn_set_error("rn_postprocess: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+
+    // guard logit: every x <= x_lo has sigmoid(x) <= thr with a 1e-3 margin (SFU/libm error is ~1e-7)
+    const float thr = score_thr;
+    float x_lo;
+    if (!(thr > 0.0f)) x_lo = -INFINITY;
+    else if (thr >= 1.0f) x_lo = INFINITY;
+    else {
+        double xt = log((double)thr / (1.0 - (double)thr));
+        x_lo = (float)(xt - 1e-3 * fmax(1.0, fabs(xt)));
+    }
+    FilterParams F;
+    F.logits = logits; F.bbox = (const float4 *)bbox; F.anchors = (const float4 *)anchors; F.im_hw = im_hw;
+    F.A = A; F.anchor_stride = anchor_image_stride; F.C = C; F.x_lo = x_lo; F.thr = thr; F.cap = (u32)cand_capacity; F.w = w;
+    F.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
+    const bool vec4 = (C % 4 == 0) && (((uintptr_t)logits & 15) == 0);
+    const int CV = vec4 ? C / 4 : C;
+    F.magic = CV == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)CV - 1) / (unsigned)CV);
+    dim3 grid((unsigned)((A + PP_SPAN - 1) / PP_SPAN), (unsigned)N);
+    if (vec4) score_filter_kernel<4><<<grid, PP_BLOCK, 0, s>>>(F); else score_filter_kernel<1><<<grid, PP_BLOCK, 0, s>>>(F);
+    RN_CHECK_LAUNCH("rn_postprocess/score_filter");
+
+    const int S = N * C;
+    segment_scan_kernel<<<1, 1024, 0, s>>>(w.seg_count, S, w.seg_off, w.cursor, w.pool_count, (u32)cand_capacity, out_status);
+    RN_CHECK_LAUNCH("rn_postprocess/segment_scan");
+    scatter_kernel<<<RN_SM_COUNT_B200 * 4, 256, 0, s>>>(w.pool_key, w.pool_seg, w.pool_count, (u32)cand_capacity, w.cursor,
+                                                        w.sorted_key);
+    RN_CHECK_LAUNCH("rn_postprocess/scatter");
+
+    // round the double threshold DOWN to fp32: (double)ovr > thr  <=>  ovr > thr_f  for every fp32 ovr
+    float thr_f = (float)nms_thr;
+    if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
+    NmsParams M;
+    M.bbox = (const float4 *)bbox; M.anchors = (const float4 *)anchors; M.im_hw = im_hw; M.boxes = nullptr;
+    M.keep_flags = nullptr; M.A = A; M.anchor_stride = anchor_image_stride; M.C = C; M.thr = thr_f; M.wts = F.wts; M.seg_off = w.seg_off;
+    M.sorted_key = w.sorted_key; M.kept_key = w.kept_key; M.kept_box = w.kept_box; M.kept_count = w.kept_count;
+    nms_kernel<false><<<S, NMS_CHUNK, 0, s>>>(M);
+    RN_CHECK_LAUNCH("rn_postprocess/nms");
+
+    TopkParams T;
+    T.seg_off = w.seg_off; T.kept_count = w.kept_count; T.kept_key = w.kept_key; T.kept_box = w.kept_box;
+    T.C = C; T.max_det = max_det; T.out_boxes = out_boxes; T.out_scores = out_scores;
+    T.out_labels = (long long *)out_labels; T.out_count = out_count;
+    image_topk_kernel<<<N, PP_BLOCK, (size_t)C * sizeof(int), s>>>(T);
+    RN_CHECK_LAUNCH("rn_postprocess/image_topk");
+    return 0;
+}
+
+extern "C" int rn_nms_segments(const float *boxes, const int32_t *seg_off, int num_segments, int64_t total_boxes,
+                               double nms_thr, uint8_t *keep_flags, void *workspace, size_t workspace_bytes,
+                               rn_stream_t stream) {
+    RN_CHECK_ARG(boxes && seg_off && keep_flags && workspace, RN_E_BADARG, "rn_nms_segments: null pointer");
+    RN_CHECK_ARG(num_segments >= 0 && total_boxes >= 0, RN_E_BADARG, "rn_nms_segments: negative size");
+    RN_CHECK_ARG(workspace_bytes >= (size_t)total_boxes * 16, RN_E_WORKSPACE, "rn_nms_segments: workspace too small");
+    if (num_segments == 0 || total_boxes == 0) return 0;
+    float thr_f = (float)nms_thr;
+    if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
+    NmsParams M;
+    M.bbox = nullptr; M.anchors = nullptr; M.im_hw = nullptr; M.boxes = (const float4 *)boxes;
+    M.keep_flags = keep_flags; M.A = 0; M.anchor_stride = 0; M.C = 1; M.thr = thr_f; M.wts = make_float4(1.f, 1.f, 1.f, 1.f);
+    M.seg_off = seg_off; M.sorted_key = nullptr; M.kept_key = nullptr; M.kept_box = (float4 *)workspace;
+    M.kept_count = nullptr;
+    nms_kernel<true><<<num_segments, NMS_CHUNK, 0, (cudaStream_t)stream>>>(M);
+    RN_CHECK_LAUNCH("rn_nms_segments");
+    return 0;
+}
