@@ -1,0 +1,58 @@
+"""Image-sharded multi-GPU loss: one process per GPU, each rank owns a contiguous
+slice of the batch; images are independent in the reference (python loop, per-image normaliser,
+retinanet/losses.py:126-140), so the only exchange is ONE all-reduce (NCCL over NVLink) of four
+floats per step: [sum_i cls_i/max(1,F_i), sum_i reg_i/max(1,F_i), sum_i F_i, N_local].
+Inference post-processing needs no communication at all.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .box_utils import PackedTargets
+from .losses import RetinaNetLosses, _FusedRetinaNetLoss, _shared_anchors
+
+
+def shard_range(num_images: int, rank: int, world: int):
+    """Rank r owns images [r*N/W, (r+1)*N/W) (contiguous, sizes differ by at most one)."""
+    return (num_images * rank) // world, (num_images * (rank + 1)) // world
+
+
+class ShardedRetinaNetLosses(RetinaNetLosses):
+    """``forward`` takes this rank's shard and returns the loss of the GLOBAL batch (identical on
+    every rank and equal to the single-process reference on the full batch up to fp32 summation
+    order).  Gradients w.r.t. the local shard are already scaled by 1/N_global."""
+
+    def __init__(self, num_classes: int, global_batch: Optional[int] = None, group=None) -> None:
+        super().__init__(num_classes)
+        self.global_batch = global_batch
+        self.group = group
+        self.last_stats: Optional[Tensor] = None
+
+    def forward(self, targets: List[Dict[str, Tensor]], head_outputs: Dict[str, Tensor],
+                anchors: List[Tensor]) -> Dict[str, Tensor]:
+        cls, box = head_outputs["cls_preds"], head_outputs["bbox_preds"]
+        n_local = len(targets)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        n_global = self.global_batch
+        if n_global is None:
+            if world > 1:
+                t = torch.tensor([float(n_local)], device=cls.device)
+                dist.all_reduce(t, group=self.group)
+                n_global = int(t.item())
+            else:
+                n_global = n_local
+        an, stride = _shared_anchors(anchors)
+        packed = PackedTargets([t["boxes"] for t in targets], [t["labels"] for t in targets], cls.device)
+        c, r, image = _FusedRetinaNetLoss.apply(cls, box, an, stride, packed, self._hp(n_global))
+        self.last_per_image = image
+        stats = torch.stack([c.detach(), r.detach(), image[:, 2].sum(), image.new_tensor(float(n_local))])
+        if world > 1:
+            dist.all_reduce(stats, group=self.group)          # the ONE collective of the path (16 bytes)
+        self.last_stats = stats                                # [cls, reg, sum F, N] of the global batch
+        # value = global loss; gradient flows only through the local shard (already / N_global)
+        return {"classification_loss": c + (stats[0] - c.detach()),
+                "regression_loss": r + (stats[1] - r.detach())}

@@ -1,0 +1,394 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes), against the oracle
+and the committed golden vectors of the unmodified reference.
+
+Bars (BASELINE.json north_star): bit-exact for matched indices, labels and NMS keep lists; 1e-5
+relative for losses and decoded boxes.  Gradients: 1e-5 relative + a 1e-9 absolute floor (values are
+O(1e-7..1e-3) and fp32 SFU math is used).
+"""
+import numpy as np
+import pytest
+import torch
+
+import synth_data as S
+from helpers import config_image, golden, max_rel, rel_close, to_cuda_targets
+from oracle import c_oracle as CO
+from oracle import torch_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+BOX_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pytorch_retinanet_b200 as pkg
+    from pytorch_retinanet_b200 import _native
+    _native.load()
+    return pkg
+
+
+def gpu_anchors(P, padded_hw, **kw):
+    gen = P.AnchorGenerator(**kw).cuda()
+    return gen.grid_anchors(S.grid_sizes(padded_hw), torch.device("cuda"))
+
+
+# ------------------------------------------------------------------------------------------ anchors
+@pytest.mark.parametrize("cid", [1, 2, 5])
+def test_anchor_grid_bit_exact(P, cid):
+    hw = S.CONFIGS[cid].padded_hw
+    got = torch.cat(gpu_anchors(P, hw)).cpu()
+    want = O.image_anchors(O.fpn_grid_sizes(*hw))
+    assert got.shape == want.shape and torch.equal(got, want)
+
+
+def test_anchor_generator_api(P):
+    g = golden("known_answers.npz")
+    gen = P.AnchorGenerator(offset=0.5).cuda()
+    assert gen.num_anchors == [9] * 5 and gen.num_cell_anchors == [9] * 5
+    assert sorted(gen.state_dict().keys()) == [f"cell_anchors.{i}" for i in range(5)]
+    got = torch.cat(gen.grid_anchors(S.grid_sizes((64, 96)), torch.device("cuda"))).cpu().numpy()
+    assert np.array_equal(got, g["anchors_off05_64x96"])
+    # forward(): ImageList-like object, one entry per image, levels concatenated
+    from types import SimpleNamespace
+    fmaps = [torch.empty((2, 8, h, w), device="cuda") for h, w in S.grid_sizes((64, 96))]
+    out = gen(SimpleNamespace(image_sizes=[(60, 90), (64, 96)]), fmaps)
+    assert len(out) == 2 and np.array_equal(out[1].cpu().numpy(), g["anchors_off05_64x96"])
+    # custom sizes / ratios / strides (3 levels, 2x2 cell anchors)
+    gen2 = P.AnchorGenerator(sizes=[[16.0, 20.0]], aspect_ratios=[0.5, 2.0], strides=[4, 8, 16]).cuda()
+    gs = [(5, 7), (3, 4), (2, 2)]
+    got2 = torch.cat(gen2.grid_anchors(gs, torch.device("cuda"))).cpu()
+    want2 = O.image_anchors(gs, strides=[4, 8, 16], sizes=[[16.0, 20.0]] * 3, ratios=[0.5, 2.0])
+    assert torch.equal(got2, want2)
+
+
+# ------------------------------------------------------------------------------------------ matcher
+def test_matcher_known_answers(P):
+    g = golden("known_answers.npz")
+    anc, gt = torch.from_numpy(g["m_anchors"]).cuda(), torch.from_numpy(g["m_gt"]).cuda()
+    assert P.matcher(anc, gt).cpu().tolist() == [0, -1, -2]
+    assert P.matcher(anc, torch.zeros((0, 4), device="cuda")).cpu().tolist() == [-2, -2, -2]
+    with pytest.raises(AssertionError):
+        P.matcher(anc, gt, match_thr=0.3, back_thr=0.4)
+    m = P.matcher(anc, gt)
+    assert m.dtype == torch.int64 and m.shape == (3,)
+
+
+@pytest.mark.parametrize("cid", [1, 2, 5])
+def test_matcher_full_size_bit_exact(P, cid):
+    b, g = config_image(cid)
+    m = P.matcher(b["anchors"].cuda(), b["targets"][0]["boxes"].cuda()).cpu().numpy()
+    assert np.array_equal(m, g["matches"])
+
+
+def test_matcher_random_small_golden(P):
+    g = golden("random_small.npz")
+    for k in range(int(g["n_cases"])):
+        p = f"c{k}_"
+        m = P.matcher(torch.from_numpy(g[p + "anchors"]).cuda(), torch.from_numpy(g[p + "gt"]).cuda())
+        assert np.array_equal(m.cpu().numpy(), g[p + "matches"]), k
+
+
+def test_matcher_edge_cases_vs_oracle(P):
+    gen = torch.Generator().manual_seed(5)
+    anc = S.default_anchors((256, 320))
+    cases = []
+    gt_big = S._gt_boxes(gen, 1300, (256, 320))                 # > 2 GT tiles of 512
+    cases.append(("g1300", gt_big, None, None))
+    cases.append(("g1", S._gt_boxes(gen, 1, (256, 320)), None, None))
+    dup = anc[torch.randint(0, anc.shape[0], (40,), generator=gen)]
+    cases.append(("exact_copies", torch.cat([dup, dup]), None, None))  # IoU==1 ties -> lowest index
+    bad = S._gt_boxes(gen, 12, (256, 320))
+    bad[3, 0] = float("nan")                                    # NaN propagates -> everything ignore
+    cases.append(("nan_gt", bad, None, None))
+    neg = S._gt_boxes(gen, 12, (256, 320))
+    neg[5] = torch.tensor([200., 200., 100., 120.])             # x2<x1: negative area
+    neg[7] = torch.tensor([50., 60., 50., 60.])                 # degenerate, area 0
+    cases.append(("malformed_gt", neg, None, None))
+    cases.append(("thr_0.7_0.3", S._gt_boxes(gen, 30, (256, 320)), 0.7, 0.3))
+    cases.append(("bg_thr_0", S._gt_boxes(gen, 30, (256, 320)), 0.5, 0.0))      # disables culling
+    cases.append(("neg_thr", S._gt_boxes(gen, 30, (256, 320)), -0.1, -0.5))     # every anchor foreground
+    for name, gt, ft, bt in cases:
+        want = O.match(anc, gt, ft, bt)
+        got = P.matcher(anc.cuda(), gt.cuda(), ft, bt).cpu()
+        assert torch.equal(got, want), name
+    # malformed anchors (zero area / NaN) take the generic path
+    anc2 = anc[:4096].clone()
+    anc2[17] = torch.tensor([10., 10., 10., 30.])
+    anc2[99, 2] = float("nan")
+    gt = S._gt_boxes(gen, 25, (256, 320))
+    assert torch.equal(P.matcher(anc2.cuda(), gt.cuda()).cpu(), O.match(anc2, gt))
+
+
+# ------------------------------------------------------------------------------------------ box coding
+def test_box_coding(P):
+    g = golden("known_answers.npz")
+    dec = P.activ_2_bbox(torch.from_numpy(g["dec_act"]).cuda(), torch.from_numpy(g["dec_anchor"]).cuda())
+    assert rel_close(dec, g["dec_out"], BOX_RTOL)
+    enc = P.bbox_2_activ(torch.from_numpy(g["enc_gt"]).cuda(), torch.from_numpy(g["enc_anchor"]).cuda())
+    assert rel_close(enc, g["enc_out"], BOX_RTOL)
+    gen = torch.Generator().manual_seed(3)
+    anc = S.default_anchors((128, 128))
+    act = torch.randn((anc.shape[0], 4), generator=gen) * 0.5
+    want = O.decode(act, anc)
+    got = P.activ_2_bbox(act.cuda(), anc.cuda()).cpu()
+    assert rel_close(got, want, BOX_RTOL, 1e-4)                  # cancellation near 0: tiny absolute floor
+    # on the same device (CUDA expf) the decode is bit-identical to the eager op sequence
+    assert torch.equal(got, O.decode(act.cuda(), anc.cuda()).cpu())
+    gt = S._gt_boxes(gen, anc.shape[0], (128, 128))
+    assert rel_close(P.bbox_2_activ(gt.cuda(), anc.cuda()), O.encode(gt, anc), BOX_RTOL, 1e-6)
+    xywh = P.convert_xywh(anc.cuda())
+    assert torch.equal(P.convert_x1y1x2y2(xywh).cpu(), O.to_corners(O.to_center_size(anc)))
+
+
+# ------------------------------------------------------------------------------------------ losses
+def run_gpu_loss(P, cls, bb, targets, anchors_list, C, grad=True):
+    L = P.RetinaNetLosses(C)
+    x = cls.cuda().requires_grad_(grad)
+    b = bb.cuda().requires_grad_(grad)
+    out = L(to_cuda_targets(targets), {"cls_preds": x, "bbox_preds": b}, anchors_list)
+    if grad:
+        (out["classification_loss"] + out["regression_loss"]).backward()
+    return out, x, b, L
+
+
+def test_loss_known_answers(P):
+    g = golden("known_answers.npz")
+    anc = torch.from_numpy(g["l3_anchors"]).cuda()
+    tg = [{"boxes": torch.from_numpy(g["l3_gt"]), "labels": torch.from_numpy(g["l3_labels"])}]
+    out, x, b, L = run_gpu_loss(P, torch.from_numpy(g["l3_cls"]), torch.from_numpy(g["l3_bb"]), tg, [anc], 3)
+    assert rel_close(out["classification_loss"], g["l3_closs"], LOSS_RTOL)
+    assert rel_close(out["regression_loss"], g["l3_rloss"], LOSS_RTOL)
+    assert rel_close(x.grad, g["l3_gcls"], 1e-5, 1e-9) and rel_close(b.grad, g["l3_gbb"], 1e-5, 1e-9)
+    assert L.last_per_image.cpu()[0, 2] == 2
+    # empty GT: everything ignored, both losses exactly 0 and zero gradients
+    tg0 = [{"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)}]
+    out0, x0, b0, _ = run_gpu_loss(P, torch.from_numpy(g["l3_cls"]), torch.from_numpy(g["l3_bb"]), tg0, [anc], 3)
+    assert float(out0["classification_loss"]) == 0.0 and float(out0["regression_loss"]) == 0.0
+    assert float(x0.grad.abs().sum()) == 0.0 and float(b0.grad.abs().sum()) == 0.0
+    # calc_loss keeps the reference's (bb_loss, clas_loss) order
+    bl, cl = L.calc_loss(anc, torch.from_numpy(g["l3_cls"][0]).cuda(), torch.from_numpy(g["l3_bb"][0]).cuda(),
+                         tg[0]["labels"].cuda(), tg[0]["boxes"].cuda())
+    assert rel_close(cl, g["l3_closs"], LOSS_RTOL) and rel_close(bl, g["l3_rloss"], LOSS_RTOL)
+
+
+def test_loss_random_small_golden(P):
+    """Ragged/empty GT, ties, C in {1,3,4,5,8,20} (scalar and 128-bit paths) vs the reference's outputs."""
+    g = golden("random_small.npz")
+    for k in range(int(g["n_cases"])):
+        p = f"c{k}_"
+        anc = torch.from_numpy(g[p + "anchors"]).cuda()
+        tg = [{"boxes": torch.from_numpy(g[p + "gt"]), "labels": torch.from_numpy(g[p + "labels"])}]
+        C = g[p + "cls"].shape[-1]
+        out, x, b, _ = run_gpu_loss(P, torch.from_numpy(g[p + "cls"]), torch.from_numpy(g[p + "bb"]), tg, [anc], C)
+        assert rel_close(out["classification_loss"], g[p + "closs"], LOSS_RTOL, 1e-7), (k, float(out["classification_loss"]), g[p + "closs"])
+        assert rel_close(out["regression_loss"], g[p + "rloss"], LOSS_RTOL, 1e-7), k
+        assert rel_close(x.grad, g[p + "gcls"], 2e-5, 1e-8), (k, max_rel(x.grad, g[p + "gcls"], 1e-6))
+        assert rel_close(b.grad, g[p + "gbb"], 2e-5, 1e-8), k
+
+
+@pytest.mark.parametrize("cid", [1, 2, 5])
+def test_loss_full_size_vs_golden(P, cid):
+    b, g = config_image(cid)
+    anc = b["anchors"].cuda()
+    out, x, bb, L = run_gpu_loss(P, b["cls_preds"], b["bbox_preds"], b["targets"], [anc], b["config"].num_classes)
+    assert rel_close(out["classification_loss"], g["closs"], LOSS_RTOL), (float(out["classification_loss"]), g["closs"])
+    assert rel_close(out["regression_loss"], g["rloss"], LOSS_RTOL), (float(out["regression_loss"]), g["rloss"])
+    gx = x.grad.reshape(-1)[torch.from_numpy(g["g_idx"]).cuda()]
+    assert rel_close(gx, g["gcls_at_idx"], 2e-5, 1e-12), max_rel(gx, g["gcls_at_idx"], 1e-9)
+    rows = torch.from_numpy(g["g_fgrows"]).cuda()
+    assert rel_close(x.grad[0, rows], g["gcls_fgrows"], 2e-5, 1e-12)
+    assert rel_close(bb.grad[0, rows], g["gbb_fgrows"], 2e-5, 1e-9)
+    assert rel_close(x.grad.double().abs().sum(), g["gcls_abs_sum"], 1e-5)
+    assert rel_close(bb.grad.double().abs().sum(), g["gbb_abs_sum"], 1e-5)
+    assert int(L.last_per_image[0, 2]) == int((g["matches"] >= 0).sum())
+
+
+def test_loss_batch_precise_mode_and_determinism(P):
+    """Batch of 3 images with different G (incl. one empty), fast vs precise math, bit-reproducibility,
+    per-image anchor tensors (stacked path) and grad_output scaling."""
+    from pytorch_retinanet_b200 import _native
+    cfg = S.CONFIGS[1]
+    b = S.make_batch(cfg, 10, 3, clustered=True)
+    b["targets"][1] = {"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)}
+    anc = b["anchors"]
+    xo = b["cls_preds"].clone().requires_grad_(True)
+    bo = b["bbox_preds"].clone().requires_grad_(True)
+    want = O.batch_loss(b["targets"], xo, bo, [anc] * 3, cfg.num_classes)
+    (2.0 * want["classification_loss"] + 0.5 * want["regression_loss"]).backward()
+    anc_g = anc.cuda()
+    res = {}
+    for mode in (0, 1):
+        _native.load().rn_loss_set_math_mode(mode)
+        L = P.RetinaNetLosses(cfg.num_classes)
+        x = b["cls_preds"].cuda().requires_grad_(True)
+        bb = b["bbox_preds"].cuda().requires_grad_(True)
+        out = L(to_cuda_targets(b["targets"]), {"cls_preds": x, "bbox_preds": bb}, [anc_g] * 3)
+        (2.0 * out["classification_loss"] + 0.5 * out["regression_loss"]).backward()
+        res[mode] = (out, x.grad.clone(), bb.grad.clone())
+        assert rel_close(out["classification_loss"], want["classification_loss"].detach(), LOSS_RTOL), mode
+        assert rel_close(out["regression_loss"], want["regression_loss"].detach(), LOSS_RTOL), mode
+        assert rel_close(x.grad, xo.grad, 2e-5, 1e-12), (mode, max_rel(x.grad, xo.grad, 1e-9))
+        assert rel_close(bb.grad, bo.grad, 2e-5, 1e-9), mode
+    _native.load().rn_loss_set_math_mode(0)
+    # bit-reproducible run to run (fixed-order reductions, no float atomics)
+    L = P.RetinaNetLosses(cfg.num_classes)
+    outs = []
+    for _ in range(3):
+        o = L(to_cuda_targets(b["targets"]), {"cls_preds": b["cls_preds"].cuda(), "bbox_preds": b["bbox_preds"].cuda()},
+              [anc_g] * 3)
+        outs.append((float(o["classification_loss"]), float(o["regression_loss"])))
+    assert outs[0] == outs[1] == outs[2]
+    # distinct per-image anchor tensors -> stacked [N,A,4] path gives the same numbers
+    o2 = L(to_cuda_targets(b["targets"]), {"cls_preds": b["cls_preds"].cuda(), "bbox_preds": b["bbox_preds"].cuda()},
+           [anc_g.clone() for _ in range(3)])
+    assert float(o2["classification_loss"]) == outs[0][0] and float(o2["regression_loss"]) == outs[0][1]
+
+
+def test_loss_generic_gamma_and_l1(P):
+    """gamma != 2 (pow path) and beta < 1e-5 (pure L1) against the oracle."""
+    cfg = S.CONFIGS[1]
+    b = S.make_batch(cfg, 20, 1, clustered=True)
+    anc = b["anchors"]
+    for gamma, beta in ((1.5, 0.1), (2.0, 0.0), (0.0, 0.5)):
+        xo = b["cls_preds"].clone().requires_grad_(True)
+        bo = b["bbox_preds"].clone().requires_grad_(True)
+        want = O.batch_loss(b["targets"], xo, bo, [anc], cfg.num_classes, gamma=gamma, beta=beta)
+        (want["classification_loss"] + want["regression_loss"]).backward()
+        L = P.RetinaNetLosses(cfg.num_classes)
+        L.gamma, L.beta = gamma, beta
+        x = b["cls_preds"].cuda().requires_grad_(True)
+        bb = b["bbox_preds"].cuda().requires_grad_(True)
+        out = L(to_cuda_targets(b["targets"]), {"cls_preds": x, "bbox_preds": bb}, [anc.cuda()])
+        (out["classification_loss"] + out["regression_loss"]).backward()
+        assert rel_close(out["classification_loss"], want["classification_loss"].detach(), 2e-5), (gamma, beta)
+        assert rel_close(out["regression_loss"], want["regression_loss"].detach(), LOSS_RTOL), (gamma, beta)
+        assert rel_close(x.grad, xo.grad, 5e-5, 1e-11), (gamma, beta, max_rel(x.grad, xo.grad, 1e-8))
+        assert rel_close(bb.grad, bo.grad, 2e-5, 1e-9), (gamma, beta)
+
+
+# ------------------------------------------------------------------------------------------ post-processing
+def gpu_detect(P, cls, bb, anchors_list, im_szs, **kw):
+    from types import SimpleNamespace
+    stub = SimpleNamespace(score_thres=kw.get("score", 0.05), nms_thres=kw.get("nms", 0.5),
+                           detections_per_img=kw.get("max_det", 100))
+    outputs = {"cls_preds": cls.cuda(), "bbox_preds": bb.cuda()}
+    dets = P.process_detections(stub, outputs, anchors_list, im_szs)
+    assert outputs == {}                                          # models.py:168-169 pops both keys
+    return dets
+
+
+def assert_dets_equal(got, want, exact=True, ctx=""):
+    assert got["labels"].dtype == torch.int64 and got["boxes"].dtype == torch.float32
+    assert got["boxes"].shape == want["boxes"].shape, (ctx, got["boxes"].shape, want["boxes"].shape)
+    assert torch.equal(got["labels"].cpu(), want["labels"].cpu()), ctx
+    if exact:
+        assert torch.equal(got["scores"].cpu(), want["scores"].cpu()), ctx
+        assert torch.equal(got["boxes"].cpu(), want["boxes"].cpu()), ctx
+    else:
+        assert rel_close(got["scores"], want["scores"], BOX_RTOL), ctx
+        assert rel_close(got["boxes"], want["boxes"], BOX_RTOL, 1e-4), ctx
+
+
+@pytest.mark.parametrize("cid", [1, 2, 5])
+def test_postprocess_full_size(P, cid):
+    """Bit-exact against the eager op sequence on the same device (CUDA oracle: same expf), and
+    against the CPU reference's golden detections: same labels/order, floats within 1e-5."""
+    b, g = config_image(cid)
+    anc = b["anchors"].cuda()
+    got = gpu_detect(P, b["cls_preds"], b["bbox_preds"], [anc], b["im_szs"])[0]
+    want_cuda = O.postprocess(b["cls_preds"].cuda(), b["bbox_preds"].cuda(), [anc], b["im_szs"])[0]
+    assert_dets_equal(got, want_cuda, exact=True, ctx=f"config{cid} vs CUDA oracle")
+    want_cpu = {"boxes": torch.from_numpy(g["det_boxes"]), "scores": torch.from_numpy(g["det_scores"]),
+                "labels": torch.from_numpy(g["det_labels"])}
+    assert_dets_equal(got, want_cpu, exact=False, ctx=f"config{cid} vs CPU reference golden")
+
+
+def test_postprocess_random_small_golden(P):
+    g = golden("random_small.npz")
+    for k in range(int(g["n_cases"])):
+        p = f"c{k}_"
+        anc = torch.from_numpy(g[p + "anchors"]).cuda()
+        cls, bb = torch.from_numpy(g[p + "cls"]), torch.from_numpy(g[p + "bb"])
+        got = gpu_detect(P, cls, bb, [anc], [(90, 120)], max_det=20)[0]
+        want = O.postprocess(cls.cuda(), bb.cuda(), [anc], [(90, 120)], max_det=20)[0]
+        assert_dets_equal(got, want, exact=True, ctx=f"case {k} vs CUDA oracle")
+        ref = {"boxes": torch.from_numpy(g[p + "det_boxes"]), "scores": torch.from_numpy(g[p + "det_scores"]),
+               "labels": torch.from_numpy(g[p + "det_labels"])}
+        if got["boxes"].shape == ref["boxes"].shape and torch.equal(got["labels"].cpu(), ref["labels"]):
+            assert_dets_equal(got, ref, exact=False, ctx=f"case {k} vs reference golden")
+        else:   # a 1-ulp CPU/GPU sigmoid/exp difference flipped a threshold/NMS decision: must be rare
+            pytest.fail(f"case {k}: detections differ from the CPU reference golden")
+
+
+def test_postprocess_batch_edge_cases(P):
+    """Batch of 4 with: an image without any candidate, huge segments (global-memory sort path and
+    multi-chunk NMS), heavy score ties, max_det < kept, C not a multiple of 4, candidate-pool overflow."""
+    gen = torch.Generator().manual_seed(11)
+    anc = S.default_anchors((128, 160))
+    A, C = anc.shape[0], 6
+    cls = torch.randn((4, A, C), generator=gen) * 1.5 - 6.0
+    bb = torch.randn((4, A, 4), generator=gen) * 0.2
+    cls[1] = -20.0                                                  # no candidates at all
+    cls[2, :, 2] = torch.randn(A, generator=gen) * 0.5 + 1.0        # one class fires on every anchor (A > 2048)
+    cls[3, :, 1] = 0.75                                             # thousands of exactly tied scores
+    cls[3, :, 4] = torch.round(torch.randn(A, generator=gen) * 2) / 2  # few distinct values -> many ties
+    sz = [(128, 160), (100, 150), (128, 160), (120, 130)]
+    want = O.postprocess(cls.cuda(), bb.cuda(), [anc.cuda()] * 4, sz, max_det=50)
+    got = gpu_detect(P, cls, bb, [anc.cuda()] * 4, sz, max_det=50)
+    assert got[1]["boxes"].shape == (0, 4) and got[1]["scores"].shape == (0,) and got[1]["labels"].shape == (0,)
+    for i in range(4):
+        assert_dets_equal(got[i], want[i], exact=True, ctx=f"image {i}")
+    # candidate pool overflow -> transparent re-run with the exact capacity
+    from pytorch_retinanet_b200.detections import postprocess_batch
+    ob, os_, ol, counts = postprocess_batch(cls.cuda(), bb.cuda(), anc.cuda(), 0, sz, 0.05, 0.5, 50, cand_capacity=100)
+    for i in range(4):
+        k = counts[i]
+        assert torch.equal(ob[i, :k].cpu(), want[i]["boxes"].cpu()) and torch.equal(ol[i, :k].cpu(), want[i]["labels"].cpu())
+    # other thresholds
+    want2 = O.postprocess(cls.cuda(), bb.cuda(), [anc.cuda()] * 4, sz, score_thr=0.3, nms_thr=0.35, max_det=100)
+    got2 = gpu_detect(P, cls, bb, [anc.cuda()] * 4, sz, score=0.3, nms=0.35, max_det=100)
+    for i in range(4):
+        assert_dets_equal(got2[i], want2[i], exact=True, ctx=f"thr image {i}")
+
+
+def test_nms_segments_vs_torchvision(P):
+    import ctypes
+    import torchvision
+    from pytorch_retinanet_b200 import _native
+    lib = _native.load()
+    gen = torch.Generator().manual_seed(2)
+    segs, offs = [], [0]
+    for n in (0, 1, 5, 300, 1500):
+        ctr = torch.rand((n, 2), generator=gen) * 60
+        wh = torch.rand((n, 2), generator=gen) * 30 + 1
+        bx = torch.cat([ctr, ctr + wh], 1)
+        if n >= 5:
+            bx[1] = bx[0]                                            # duplicates
+        sc = torch.rand(n, generator=gen)
+        order = torch.sort(sc, descending=True, stable=True)[1]
+        segs.append((bx[order], sc[order]))
+        offs.append(offs[-1] + n)
+    boxes = torch.cat([s[0] for s in segs]).cuda().contiguous()
+    off = torch.tensor(offs, dtype=torch.int32).cuda()
+    keep = torch.zeros(boxes.shape[0], dtype=torch.uint8, device="cuda")
+    ws = torch.empty(boxes.shape[0] * 16, dtype=torch.uint8, device="cuda")
+    for thr in (0.5, 0.3, 0.7000000001):
+        rc = lib.rn_nms_segments(boxes.data_ptr(), off.data_ptr(), len(segs), boxes.shape[0], ctypes.c_double(thr),
+                                 keep.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "rn_nms_segments")
+        kf = keep.cpu()
+        for i, (bx, sc) in enumerate(segs):
+            want = torchvision.ops.nms(bx, sc, thr)                  # CPU kernel, input already sorted
+            gotk = torch.nonzero(kf[offs[i]:offs[i + 1]]).squeeze(1)
+            assert torch.equal(gotk, torch.sort(want)[0]), (thr, i)
+            assert CO.nms(bx.numpy(), sc.numpy(), thr).tolist() == want.tolist()
+
+
+def test_no_cpu_fallback(P):
+    from pytorch_retinanet_b200 import _native
+    anc = S.default_anchors((64, 64))
+    with pytest.raises(_native.NativeError):
+        P.matcher(anc, anc[:3])
+    with pytest.raises(_native.NativeError):
+        P.AnchorGenerator().grid_anchors(S.grid_sizes((64, 64)), torch.device("cpu"))
