@@ -267,31 +267,41 @@ __global__ void __launch_bounds__(LOSS_BLOCK) loss_kernel(const LossParams P) {
     }
 }
 
-// Fixed-order final reduction: one warp per image over its chunk partials, then thread 0 over images.
-__global__ void __launch_bounds__(256) loss_finalize_kernel(const double *__restrict__ partials,
-                                                            const int *__restrict__ fg_count, int N, int chunks,
-                                                            float batch_div, float *__restrict__ out_image,
-                                                            float *__restrict__ out_total) {
+// Fixed-order final reduction (one CTA of 1024 threads): warp w reduces images w, w+32, ... over
+// their chunk partials with four independent accumulators per lane (loads in flight), then thread 0
+// sums the images in index order.  The summation order depends only on (N, chunks) => deterministic.
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(const double *__restrict__ partials,
+                                                             const int *__restrict__ fg_count, int N, int chunks,
+                                                             float batch_div, float *__restrict__ out_image,
+                                                             float *__restrict__ out_total) {
     extern __shared__ double s_img[];   // [N][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int n = warp; n < N; n += nw) {
-        double c = 0.0, r = 0.0;
-        for (int k = lane; k < chunks; k += 32) {
-            c += partials[((long long)n * chunks + k) * 2 + 0];
-            r += partials[((long long)n * chunks + k) * 2 + 1];
+        const double2 *p = (const double2 *)partials + (long long)n * chunks;
+        double c[4] = {0.0, 0.0, 0.0, 0.0}, r[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = lane; k < chunks; k += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = k + 32 * u;
+                if (kk < chunks) {
+                    const double2 v = p[kk];
+                    c[u] += v.x;
+                    r[u] += v.y;
+                }
+            }
         }
-        c = rn::warp_sum(c);
-        r = rn::warp_sum(r);
+        double cs = rn::warp_sum((c[0] + c[1]) + (c[2] + c[3]));
+        double rs = rn::warp_sum((r[0] + r[1]) + (r[2] + r[3]));
         if (lane == 0) {
             const int F = fg_count[n];
             const double den = F > 0 ? (double)F : 1.0;     // clamp(F, min=1)  losses.py:108-109
-            c /= den;
-            r /= den;
-            s_img[2 * n] = c;
-            s_img[2 * n + 1] = r;
+            cs /= den;
+            rs /= den;
+            s_img[2 * n] = cs;
+            s_img[2 * n + 1] = rs;
             if (out_image) {
-                out_image[3 * n + 0] = (float)c;
-                out_image[3 * n + 1] = (float)r;
+                out_image[3 * n + 0] = (float)cs;
+                out_image[3 * n + 1] = (float)rs;
                 out_image[3 * n + 2] = (float)F;
             }
         }
@@ -389,7 +399,7 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     RN_CHECK_LAUNCH("rn_loss");
     size_t smem = (size_t)N * 2 * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    loss_finalize_kernel<<<1, 256, smem, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
+    loss_finalize_kernel<<<1, 1024, smem, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
                                               out_total);
     RN_CHECK_LAUNCH("rn_loss_finalize");
     return 0;

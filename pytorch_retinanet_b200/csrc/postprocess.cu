@@ -30,9 +30,9 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 
 constexpr int PP_BLOCK = 256;
-constexpr int PP_SPAN = 256;       // anchors per CTA in K1
-constexpr int PP_U = 4;
-constexpr int PP_STAGE = 1024;     // staged candidates per CTA
+constexpr int PP_WSPAN = 128;      // anchors per warp task in K1
+constexpr int PP_U = 4;            // 128-bit loads in flight per lane
+constexpr int PP_WSTAGE = 96;      // staged candidates per warp
 constexpr int NMS_CHUNK = 256;
 constexpr int SORT_SMEM = 2048;    // keys sorted in shared memory
 constexpr int MAX_DET_CAP = 1024;
@@ -103,86 +103,96 @@ struct FilterParams {
     PPWorkspace w;
 };
 
-template <int VEC>
-__global__ void __launch_bounds__(PP_BLOCK) score_filter_kernel(const FilterParams P) {
-    __shared__ u64 st_key[PP_STAGE];
-    __shared__ u32 st_seg[PP_STAGE];
-    __shared__ int st_n;
-    __shared__ u32 st_base;
+// Rare path, deliberately NOT inlined: the streaming loop stays a few dozen instructions (the
+// v1 kernel inlined 16 copies of sigmoid+decode and stalled on instruction fetch).
+// Evaluates the exact score of the <= 4 logits of one vector, decodes the anchor's box once,
+// applies the small-box filter and stages the survivors in the warp's shared-memory buffer.
+__device__ __noinline__ void emit_candidates(const FilterParams &P, float4 v, int nvals, int n, int c0,
+                                             long long anchor, long long row, float imw, float imh,
+                                             u64 *st_key, u32 *st_seg, int *st_n) {
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+    bool have_box = false, box_ok = false;
+    for (int k = 0; k < nvals; ++k) {
+        if (!(vals[k] > P.x_lo)) continue;
+        const float s = rn::sigmoid_ref(vals[k]);
+        if (!(s > P.thr)) continue;                                // models.py:196 strict >
+        if (!have_box) {
+            const float4 b = decode_clip(P.bbox, P.anchors, row, (long long)n * P.anchor_stride + anchor, P.wts, imw, imh);
+            // remove_small_boxes(min_size=1e-2), models.py:203
+            box_ok = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);
+            have_box = true;
+        }
+        if (!box_ok) return;
+        const u64 key = ((u64)(~__float_as_uint(s)) << 32) | (u64)(u32)anchor;
+        const u32 seg = (u32)(n * P.C + c0 + k);
+        const int pos = atomicAdd(st_n, 1);
+        if (pos < PP_WSTAGE) {
+            st_key[pos] = key;
+            st_seg[pos] = seg;
+        } else {                                                   // staging full: go straight to the pool
+            const u32 gp = atomicAdd(P.w.pool_count, 1u);
+            if (gp < P.cap) {
+                P.w.pool_key[gp] = key;
+                P.w.pool_seg[gp] = seg;
+                atomicAdd(P.w.seg_count + seg, 1);
+            }
+        }
+    }
+}
 
+// Warp-autonomous streaming filter: every warp owns PP_WSPAN consecutive anchors of one image, reads
+// them with 128-bit loads (PP_U in flight per lane), stages its rare survivors in its own slice of
+// shared memory and flushes them with ONE global atomic per warp.  No block-level barrier anywhere.
+template <int VEC>
+__global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_kernel(const __grid_constant__ FilterParams P) {
+    __shared__ u64 s_key[PP_BLOCK / 32][PP_WSTAGE];
+    __shared__ u32 s_seg[PP_BLOCK / 32][PP_WSTAGE];
+    __shared__ int s_n[PP_BLOCK / 32];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.y;
-    const long long a0 = (long long)blockIdx.x * PP_SPAN;
-    const int span = (int)min((long long)PP_SPAN, P.A - a0);
+    const long long a0 = ((long long)blockIdx.x * (PP_BLOCK / 32) + warp) * PP_WSPAN;
+    if (a0 >= P.A) return;
+    const int span = (int)min((long long)PP_WSPAN, P.A - a0);
     const long long row0 = (long long)n * P.A + a0;
     const int CV = P.C / VEC;
     const int nvec = span * CV;
     const float *src = P.logits + row0 * P.C;
     const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
-    if (threadIdx.x == 0) st_n = 0;
-    __syncthreads();
+    u64 *st_key = s_key[warp];
+    u32 *st_seg = s_seg[warp];
+    int *st_n = &s_n[warp];
+    if (lane == 0) *st_n = 0;
+    __syncwarp();
 
-    for (int base = 0; base < nvec; base += PP_BLOCK * PP_U) {
-        float v[PP_U][VEC];
+    for (int base = 0; base < nvec; base += 32 * PP_U) {
+        float4 v[PP_U];
 #pragma unroll
         for (int u = 0; u < PP_U; ++u) {
-            const int f = base + u * PP_BLOCK + threadIdx.x;
-            if (VEC == 4) {
-                float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                if (f < nvec) t = rn::ld_stream_f4((const float4 *)src + f);
-                v[u][0] = t.x; v[u][VEC > 1 ? 1 : 0] = t.y; v[u][VEC > 2 ? 2 : 0] = t.z; v[u][VEC > 3 ? 3 : 0] = t.w;
-            } else {
-                v[u][0] = f < nvec ? __ldg(src + f) : -INFINITY;
+            const int f = base + u * 32 + lane;
+            v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (f < nvec) {
+                if (VEC == 4) v[u] = rn::ld_stream_f4((const float4 *)src + f);
+                else v[u].x = __ldg(src + f);
             }
         }
 #pragma unroll
         for (int u = 0; u < PP_U; ++u) {
-            float vmax = v[u][0];
-#pragma unroll
-            for (int k = 1; k < VEC; ++k) vmax = fmaxf(vmax, v[u][k]);
+            const float vmax = VEC == 4 ? fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)) : v[u].x;
             if (vmax > P.x_lo) {                                   // rare
-                const int f = base + u * PP_BLOCK + threadIdx.x;
+                const int f = base + u * 32 + lane;
                 const int al = P.magic ? (int)__umulhi((unsigned)f, P.magic) : f;
-                const int c0 = (f - al * CV) * VEC;
-                const long long anchor = a0 + al;
-                bool have_box = false, box_ok = false;
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) {
-                    if (!(v[u][k] > P.x_lo)) continue;
-                    const float s = rn::sigmoid_ref(v[u][k]);
-                    if (!(s > P.thr)) continue;                    // models.py:196 strict >
-                    if (!have_box) {
-                        const float4 b = decode_clip(P.bbox, P.anchors, row0 + al, (long long)n * P.anchor_stride + anchor, P.wts,
-                                                       imw, imh);
-                        // remove_small_boxes(min_size=1e-2), models.py:203
-                        box_ok = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);
-                        have_box = true;
-                    }
-                    if (!box_ok) break;
-                    const u64 key = ((u64)(~__float_as_uint(s)) << 32) | (u64)(u32)anchor;
-                    const u32 seg = (u32)(n * P.C + c0 + k);
-                    const int pos = atomicAdd(&st_n, 1);
-                    if (pos < PP_STAGE) {
-                        st_key[pos] = key;
-                        st_seg[pos] = seg;
-                    } else {                                       // staging full: go straight to the pool
-                        const u32 gp = atomicAdd(P.w.pool_count, 1u);
-                        if (gp < P.cap) {
-                            P.w.pool_key[gp] = key;
-                            P.w.pool_seg[gp] = seg;
-                            atomicAdd(P.w.seg_count + seg, 1);
-                        }
-                    }
-                }
+                emit_candidates(P, v[u], VEC, n, (f - al * CV) * VEC, a0 + al, row0 + al, imw, imh, st_key, st_seg, st_n);
             }
         }
     }
-    __syncthreads();
-    const int staged = min(st_n, PP_STAGE);
+    __syncwarp();
+    const int staged = min(*st_n, PP_WSTAGE);
     if (staged == 0) return;
-    if (threadIdx.x == 0) st_base = atomicAdd(P.w.pool_count, (u32)staged);
-    __syncthreads();
-    const u32 gbase = st_base;
-    for (int i = threadIdx.x; i < staged; i += PP_BLOCK) {
+    u32 gbase = 0;
+    if (lane == 0) gbase = atomicAdd(P.w.pool_count, (u32)staged);
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);
+    for (int i = lane; i < staged; i += 32) {
         const u32 gp = gbase + (u32)i;
         if (gp < P.cap) {
             P.w.pool_key[gp] = st_key[i];
@@ -275,11 +285,10 @@ __device__ void block_bitonic_sort(u64 *keys, int n) {
 // torchvision nms (CPU kernel) pair test: suppressed iff fl(inter / (area_i + area_j - inter)) > thr.
 __device__ __forceinline__ bool nms_suppresses(const float4 a, float area_a, const float4 b, float area_b, float thr) {
     const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    // disjoint in x (the common case): inter = 0 -> ovr is 0 (or NaN if both areas are 0), never > thr >= 0
+    if (!(w > 0.0f) && thr >= 0.0f) return false;
     const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
-    if (!(w > 0.0f && h > 0.0f)) {
-        // inter = 0 -> ovr is 0 (or NaN when both areas are 0): never > thr for thr >= 0
-        if (thr >= 0.0f) return false;
-    }
+    if (!(h > 0.0f) && thr >= 0.0f) return false;
     const float inter = __fmul_rn(fmaxf(w, 0.0f), fmaxf(h, 0.0f));
     const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
     return ovr > thr;
@@ -396,13 +405,29 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
             s_mask[t][w] = bits;
         }
         __syncthreads();
-        // (c) warp-cooperative serial resolve: lane w owns the removed-word w
+        // (c) warp-cooperative suppression scan.  Lane w (< 8) owns removed-word w.  The chunk is
+        // resolved 32 rows at a time: the 32x32 diagonal block is resolved serially in registers
+        // (shuffle-broadcast rows, warp-uniform ALU chain), then the kept rows' mask words are OR-ed
+        // into the later removed-words, 8 lanes wide.
         if (warp == 0) {
             u32 rw = lane < NMS_CHUNK / 32 ? s_removed[lane] : 0u;
-            for (int i = 0; i < m; ++i) {
-                const u32 r = __shfl_sync(0xffffffffu, rw, i >> 5);
-                if (!((r >> (i & 31)) & 1u)) {
-                    if (lane < NMS_CHUNK / 32) rw |= s_mask[i][lane];
+            const int groups = (m + 31) >> 5;
+            for (int g = 0; g < groups; ++g) {
+                const int row = g * 32 + lane;
+                const u32 diag = row < m ? s_mask[row][g] : 0u;
+                u32 rg = __shfl_sync(0xffffffffu, rw, g);          // removed bits of this group (uniform)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const u32 di = __shfl_sync(0xffffffffu, diag, i);
+                    rg |= ((rg >> i) & 1u) ? 0u : di;
+                }
+                const int nrows = min(32, m - g * 32);
+                u32 keptm = ~rg & (nrows == 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+                if (lane == g) rw = rg;
+                if (lane > g && lane < NMS_CHUNK / 32) {
+                    u32 acc = 0;
+                    for (u32 km = keptm; km; km &= km - 1) acc |= s_mask[g * 32 + __ffs(km) - 1][lane];
+                    rw |= acc;
                 }
             }
             if (lane < NMS_CHUNK / 32) s_removed[lane] = rw;
@@ -446,120 +471,185 @@ struct TopkParams {
     int *out_count;
 };
 
-__global__ void __launch_bounds__(PP_BLOCK) image_topk_kernel(const TopkParams P) {
-    extern __shared__ int s_dyn[];            // [C] per-class tie counts / prefix
-    __shared__ u32 s_hist[256];
-    __shared__ u32 s_prefix, s_mask_bits, s_need;   // radix-select state
-    __shared__ int s_total, s_nsel;
-    __shared__ u64 s_sel_hi[MAX_DET_CAP];     // (inverted score << 32) | class
-    __shared__ u32 s_sel_lo[MAX_DET_CAP];     // anchor
-    __shared__ int s_sel_pos[MAX_DET_CAP];    // index into kept arrays
+constexpr int TOPK_BLOCK = 1024;
+constexpr int TOPK_CACHE = 16384;     // inverted-score words cached in shared memory
 
-    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = PP_BLOCK / 32;
+// One CTA per image.  The kept list of every class is sorted by (score desc, anchor asc), so only
+// the first max_det entries of each class can reach the image's top max_det: the kernel works on the
+// "flattened" sequence e = 0..total-1 of those heads (class-major), whose order among equal scores
+// is exactly the documented tie rule (class asc, anchor asc).
+__global__ void __launch_bounds__(TOPK_BLOCK) image_topk_kernel(const TopkParams P) {
+    extern __shared__ u32 s_dyn[];                  // [C+1] class prefix | [TOPK_CACHE] cached keys
+    __shared__ u32 s_hist[256];
+    __shared__ u32 s_prefix, s_mask_bits, s_need;
+    __shared__ int s_carry, s_nsel;
+    __shared__ int s_warp[TOPK_BLOCK / 32];
+    __shared__ u64 s_sel_hi[MAX_DET_CAP];           // (inverted score << 32) | class
+    __shared__ u32 s_sel_lo[MAX_DET_CAP];           // anchor
+    __shared__ int s_sel_pos[MAX_DET_CAP];          // index into the kept arrays
+
+    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int C = P.C, seg0 = n * C;
-    if (t == 0) { s_total = 0; s_nsel = 0; }
+    int *s_pref = (int *)s_dyn;
+    u32 *s_hi = s_dyn + (C + 1);
+
+    // ---- exclusive scan of m_c = min(kept_count[c], max_det) over the classes ----
+    if (t == 0) { s_carry = 0; s_nsel = 0; }
     __syncthreads();
-    {
-        int local = 0;
-        for (int c = t; c < C; c += PP_BLOCK) local += P.kept_count[seg0 + c];
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-        if (lane == 0) atomicAdd(&s_total, local);
+    for (int base = 0; base < C; base += TOPK_BLOCK) {
+        const int c = base + t;
+        const int v = c < C ? min(P.kept_count[seg0 + c], P.max_det) : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+        if (c < C) s_pref[c] = excl;
+        __syncthreads();
+        if (t == TOPK_BLOCK - 1) s_carry = excl + v;
+        __syncthreads();
     }
-    __syncthreads();
-    const int total = s_total;
+    const int total = s_carry;
+    if (t == 0) s_pref[C] = total;
     const int want = min(total, P.max_det);
     if (t == 0) P.out_count[n] = want;
     if (want == 0) return;
+    __syncthreads();
 
-    // ---- radix select of the want-th smallest inverted-score (only when total > max_det) ----
-    u32 thr_hi = 0xffffffffu;     // select everything with hi < thr_hi, plus ranked ties == thr_hi
+    // flattened index -> position in the kept arrays (binary search over the class prefix)
+    auto locate = [&](int e, int &c) -> int {
+        int lo = 0, hi = C;                          // largest c with s_pref[c] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_pref[mid] <= e) lo = mid; else hi = mid;
+        }
+        c = lo;
+        return P.seg_off[seg0 + lo] + (e - s_pref[lo]);
+    };
+    const bool cached = total <= TOPK_CACHE;
+    if (cached) {
+        for (int e = t; e < total; e += TOPK_BLOCK) {
+            int c;
+            s_hi[e] = (u32)(P.kept_key[locate(e, c)] >> 32);
+        }
+        __syncthreads();
+    }
+    auto get_hi = [&](int e) -> u32 {
+        if (cached) return s_hi[e];
+        int c;
+        return (u32)(P.kept_key[locate(e, c)] >> 32);
+    };
+
+    // ---- radix select (4 x 8 bits, MSB first) of the want-th smallest inverted score ----
+    const bool select_all = total <= P.max_det;
+    u32 thr_hi = 0xffffffffu;
     int need_ties = 0;
-    bool select_all = total <= P.max_det;
     if (!select_all) {
         if (t == 0) { s_prefix = 0; s_mask_bits = 0; s_need = (u32)want; }
         __syncthreads();
         for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int i = t; i < 256; i += PP_BLOCK) s_hist[i] = 0;
+            if (t < 256) s_hist[t] = 0;
             __syncthreads();
             const u32 prefix = s_prefix, mbits = s_mask_bits;
-            for (int c = warp; c < C; c += nw) {
-                const int off = P.seg_off[seg0 + c], kc = P.kept_count[seg0 + c];
-                for (int k = lane; k < kc; k += 32) {
-                    const u32 hi = (u32)(P.kept_key[off + k] >> 32);
-                    if ((hi & mbits) == prefix) atomicAdd(&s_hist[(hi >> shift) & 255u], 1u);
-                }
+            for (int e = t; e < total; e += TOPK_BLOCK) {
+                const u32 hi = get_hi(e);
+                if ((hi & mbits) == prefix) atomicAdd(&s_hist[(hi >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (t == 0) {
-                u32 need = s_need, acc = 0;
-                int bkt = 0;
-                for (; bkt < 256; ++bkt) {
-                    if (acc + s_hist[bkt] >= need) break;
-                    acc += s_hist[bkt];
+            if (warp == 0) {                          // find the bucket holding the need-th entry
+                u32 cnt[8], sum = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { cnt[i] = s_hist[lane * 8 + i]; sum += cnt[i]; }
+                u32 incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
                 }
-                s_need = need - acc;
-                s_prefix = prefix | ((u32)bkt << shift);
-                s_mask_bits = mbits | (255u << shift);
+                const u32 need = s_need;
+                const u32 excl = incl - sum;
+                if (excl < need && need <= incl) {    // exactly one lane
+                    u32 acc = excl;
+                    int b = 0;
+                    for (; b < 8; ++b) {
+                        if (acc + cnt[b] >= need) break;
+                        acc += cnt[b];
+                    }
+                    s_need = need - acc;
+                    s_prefix = prefix | ((u32)(lane * 8 + b) << shift);
+                    s_mask_bits = mbits | (255u << shift);
+                }
             }
             __syncthreads();
         }
         thr_hi = s_prefix;
-        need_ties = (int)s_need;     // how many entries with hi == thr_hi are taken (>= 1)
+        need_ties = (int)s_need;                      // entries with hi == thr_hi to take, in flattened order
     }
 
-    // ---- per-class tie counts -> exclusive prefix (class asc, then anchor asc inside a class) ----
-    if (!select_all) {
-        for (int c = warp; c < C; c += nw) {
-            const int off = P.seg_off[seg0 + c], kc = P.kept_count[seg0 + c];
-            int cntc = 0;
-            for (int k = lane; k < kc; k += 32) cntc += ((u32)(P.kept_key[off + k] >> 32) == thr_hi);
-            for (int o = 16; o > 0; o >>= 1) cntc += __shfl_xor_sync(0xffffffffu, cntc, o);
-            if (lane == 0) s_dyn[c] = cntc;
+    // ---- collect the winners; ties at the threshold are ranked by flattened order ----
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += TOPK_BLOCK) {
+        const int e = base + t;
+        u32 hi = 0;
+        bool is_lt = false, is_tie = false;
+        if (e < total) {
+            hi = get_hi(e);
+            is_lt = select_all || hi < thr_hi;
+            is_tie = !select_all && hi == thr_hi;
         }
-        __syncthreads();
-        if (t == 0) {
-            int acc = 0;
-            for (int c = 0; c < C; ++c) { const int v = s_dyn[c]; s_dyn[c] = acc; acc += v; }
-        }
-        __syncthreads();
-    }
-
-    // ---- collect the winners ----
-    for (int c = warp; c < C; c += nw) {
-        const int off = P.seg_off[seg0 + c], kc = P.kept_count[seg0 + c];
-        int tie_seen = 0;    // ties of this class seen in previous iterations (kept list is sorted)
-        for (int k0 = 0; k0 < kc; k0 += 32) {
-            const int k = k0 + lane;
-            u64 key = 0;
-            bool is_lt = false, is_tie = false;
-            if (k < kc) {
-                key = P.kept_key[off + k];
-                const u32 hi = (u32)(key >> 32);
-                is_lt = select_all || hi < thr_hi;
-                is_tie = !select_all && hi == thr_hi;
-            }
+        bool take = is_lt;
+        if (!select_all) {
             const u32 tm = __ballot_sync(0xffffffffu, is_tie);
-            bool take = is_lt;
-            if (is_tie) {
-                const int rank = s_dyn[c] + tie_seen + __popc(tm & ((1u << lane) - 1u));
-                take = rank < need_ties;
-            }
-            tie_seen += __popc(tm);
-            if (take) {
-                const int slot = atomicAdd(&s_nsel, 1);
-                if (slot < MAX_DET_CAP) {
-                    s_sel_hi[slot] = (key & 0xffffffff00000000ull) | (u64)(u32)c;
-                    s_sel_lo[slot] = (u32)key;
-                    s_sel_pos[slot] = off + k;
+            if (lane == 0) s_warp[warp] = __popc(tm);
+            __syncthreads();
+            if (warp == 0) {
+                int w = s_warp[lane];
+                const int own = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, w, o);
+                    if (lane >= o) w += y;
                 }
+                s_warp[lane] = w - own;               // exclusive
+                if (lane == 31) s_hist[0] = (u32)w;   // chunk total
+            }
+            __syncthreads();
+            if (is_tie) take = s_carry + s_warp[warp] + __popc(tm & ((1u << lane) - 1u)) < need_ties;
+            __syncthreads();
+            if (t == 0) s_carry += (int)s_hist[0];
+            __syncthreads();
+        }
+        if (take) {
+            int c;
+            const int pos = locate(e, c);
+            const int slot = atomicAdd(&s_nsel, 1);
+            if (slot < MAX_DET_CAP) {
+                s_sel_hi[slot] = ((u64)hi << 32) | (u64)(u32)c;
+                s_sel_lo[slot] = (u32)P.kept_key[pos];
+                s_sel_pos[slot] = pos;
             }
         }
     }
     __syncthreads();
     const int nsel = min(s_nsel, want);
 
-    // ---- order the winners: (score desc, class asc, anchor asc).  Rank by counting (nsel <= 1024). ----
-    for (int i = t; i < nsel; i += PP_BLOCK) {
+    // ---- order the winners (score desc, class asc, anchor asc) by rank counting; nsel <= 1024 ----
+    for (int i = t; i < nsel; i += TOPK_BLOCK) {
         const u64 hi = s_sel_hi[i];
         const u32 lo = s_sel_lo[i];
         int rank = 0;
@@ -567,8 +657,7 @@ __global__ void __launch_bounds__(PP_BLOCK) image_topk_kernel(const TopkParams P
             const u64 hj = s_sel_hi[j];
             rank += (hj < hi) || (hj == hi && s_sel_lo[j] < lo);
         }
-        const int pos = s_sel_pos[i];
-        const float4 b = P.kept_box[pos];
+        const float4 b = P.kept_box[s_sel_pos[i]];
         const long long o = (long long)n * P.max_det + rank;
         ((float4 *)P.out_boxes)[o] = b;
         P.out_scores[o] = __uint_as_float(~(u32)(hi >> 32));
@@ -627,7 +716,8 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
     const bool vec4 = (C % 4 == 0) && (((uintptr_t)logits & 15) == 0);
     const int CV = vec4 ? C / 4 : C;
     F.magic = CV == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)CV - 1) / (unsigned)CV);
-    dim3 grid((unsigned)((A + PP_SPAN - 1) / PP_SPAN), (unsigned)N);
+    const long long warp_tasks = (A + PP_WSPAN - 1) / PP_WSPAN;
+    dim3 grid((unsigned)((warp_tasks + PP_BLOCK / 32 - 1) / (PP_BLOCK / 32)), (unsigned)N);
     if (vec4) score_filter_kernel<4><<<grid, PP_BLOCK, 0, s>>>(F); else score_filter_kernel<1><<<grid, PP_BLOCK, 0, s>>>(F);
     RN_CHECK_LAUNCH("rn_postprocess/score_filter");
 
@@ -652,7 +742,10 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
     T.seg_off = w.seg_off; T.kept_count = w.kept_count; T.kept_key = w.kept_key; T.kept_box = w.kept_box;
     T.C = C; T.max_det = max_det; T.out_boxes = out_boxes; T.out_scores = out_scores;
     T.out_labels = (long long *)out_labels; T.out_count = out_count;
-    image_topk_kernel<<<N, PP_BLOCK, (size_t)C * sizeof(int), s>>>(T);
+    const size_t topk_smem = ((size_t)C + 1 + TOPK_CACHE) * sizeof(u32);
+    if (topk_smem > 48 * 1024)
+        cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem);
+    image_topk_kernel<<<N, TOPK_BLOCK, topk_smem, s>>>(T);
     RN_CHECK_LAUNCH("rn_postprocess/image_topk");
     return 0;
 }
