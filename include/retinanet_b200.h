@@ -37,6 +37,10 @@ extern "C" {
 
 #define RN_MAX_LEVELS 8
 
+/* rn_postprocess algorithms (same results; see the function's comment) */
+#define RN_PP_LAZY    0
+#define RN_PP_GENERAL 1
+
 typedef void *rn_stream_t; /* cudaStream_t */
 
 int rn_abi_version(void);
@@ -108,14 +112,18 @@ int rn_scale_by_device_scalar(float *buf, int64_t n, const float *scale, rn_stre
  * anchor offsets of the levels and is only read when pre_nms_topk > 0.
  *   out_boxes [N,max_det,4] fp32, out_scores [N,max_det] fp32, out_labels [N,max_det] int64,
  *   out_count [N] int32 (number of valid rows per image).
- *   out_status [2] int32: {candidates found, candidate capacity}; found > capacity means the
- *   workspace was too small and the call must be repeated with a larger cand_capacity.
+ *   out_status [4] int32: {candidates found, candidate capacity, fallback flag, 0}.  found > capacity
+ *   means the workspace was too small and the call must be repeated with cand_capacity >= found.
+ *   algo = RN_PP_LAZY (per-image greedy NMS in global score order with early exit; bounded work) sets
+ *   the fallback flag when an image could not be completed within its round budget — the caller
+ *   then repeats the call with algo = RN_PP_GENERAL (per-(image,class) segments, any size).  Both
+ *   algorithms produce identical results.
  * workspace: rn_postprocess_workspace_bytes(N, A, C, cand_capacity, max_det).                      */
 size_t rn_postprocess_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
 int rn_postprocess(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, const float *anchors,
                    int64_t anchor_image_stride, const int32_t *im_hw /*[N,2] (h,w)*/, int N, int64_t A, int C, float score_thr, double nms_thr,
                    int max_det, const float *weights_host /*[4]*/, int pre_nms_topk,
-                   const int64_t *level_off_host /*[L+1] or NULL*/, int num_levels, int64_t cand_capacity,
+                   const int64_t *level_off_host /*[L+1] or NULL*/, int num_levels, int algo, int64_t cand_capacity,
                    float *out_boxes, float *out_scores, int64_t *out_labels, int32_t *out_count,
                    int32_t *out_status, void *workspace, size_t workspace_bytes, rn_stream_t stream);
 

@@ -13,6 +13,8 @@ from . import _native
 from .config import BBOX_REG_WEIGHTS, IOU_THRESHOLDS_BACKGROUND, IOU_THRESHOLDS_FOREGROUND
 from .utilities import ifnone
 
+_REG_WEIGHTS_C = _native.host_floats(BBOX_REG_WEIGHTS)
+
 
 def convert_xywh(boxes: Tensor) -> Tensor:
     """xyxy -> (cx, cy, w, h) (reference: box_utils.py:11-15).  Public helper kept for API parity; the
@@ -39,7 +41,7 @@ def _boxcode(fn_name: str, a: Tensor, anchors: Tensor) -> Tensor:
     out = torch.empty_like(a32)
     with torch.cuda.device(a32.device):
         rc = getattr(lib, fn_name)(_native.ptr(a32, what=fn_name + " input"), _native.ptr(an32, what="anchors"),
-                                   a32.shape[0], _native.host_floats(BBOX_REG_WEIGHTS), _native.ptr(out),
+                                   a32.shape[0], _REG_WEIGHTS_C, _native.ptr(out),
                                    _native.stream_ptr(a32.device))
     _native.check(rc, fn_name)
     return out.reshape(a.shape)
@@ -58,26 +60,42 @@ def activ_2_bbox(activations: Tensor, anchors: Tensor) -> Tensor:
 
 
 class PackedTargets:
-    """Ragged ground truth of a batch packed for the C ABI: boxes [sumG,4], labels [sumG], offsets [N+1]."""
+    """Ragged ground truth of a batch packed for the C ABI: boxes [sumG,4], labels [sumG], offsets [N+1].
+
+    Host cost matters here (the GPU part of a step is < 1 ms): one ``torch.cat`` per field, offsets
+    computed from shapes (no device sync) and shipped through pinned memory."""
 
     def __init__(self, boxes: Sequence[Tensor], labels: Optional[Sequence[Tensor]], device: torch.device):
-        counts = [int(b.shape[0]) if b.numel() else 0 for b in boxes]
+        counts = [b.shape[0] if b.numel() else 0 for b in boxes]       # numel()==0 -> "no targets" (box_utils.py:70)
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + c)
         self.num_images = len(counts)
         self.total = offs[-1]
-        live = [_f32c(b).reshape(-1, 4) for b, c in zip(boxes, counts) if c]
-        self.boxes = torch.cat(live) if live else torch.zeros((1, 4), dtype=torch.float32, device=device)
-        if labels is not None:
-            ll = [l.detach().to(torch.int64).reshape(-1) for l, c in zip(labels, counts) if c]
-            self.labels = torch.cat(ll).contiguous() if ll else torch.zeros((1,), dtype=torch.int64, device=device)
-            if self.labels.shape[0] != max(self.total, 1):
-                raise ValueError("targets: number of labels does not match number of boxes")
-        else:
-            self.labels = None
-        self.offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
         self.counts = counts
+        with torch.no_grad():
+            if self.total:
+                live = [b for b, c in zip(boxes, counts) if c]
+                bx = live[0] if len(live) == 1 else torch.cat(live)
+                if bx.dtype != torch.float32 or bx.device != device:
+                    bx = bx.to(device=device, dtype=torch.float32)
+                self.boxes = bx.reshape(-1, 4).contiguous()
+            else:
+                self.boxes = torch.zeros((1, 4), dtype=torch.float32, device=device)
+            if labels is not None:
+                if self.total:
+                    ll = [l for l, c in zip(labels, counts) if c]
+                    lb = ll[0] if len(ll) == 1 else torch.cat(ll)
+                    if lb.dtype != torch.int64 or lb.device != device:
+                        lb = lb.to(device=device, dtype=torch.int64)
+                    self.labels = lb.reshape(-1).contiguous()
+                    if self.labels.shape[0] != self.total:
+                        raise ValueError("targets: number of labels does not match number of boxes")
+                else:
+                    self.labels = torch.zeros((1,), dtype=torch.int64, device=device)
+            else:
+                self.labels = None
+            self.offsets = torch.tensor(offs, dtype=torch.int32).pin_memory().to(device, non_blocking=True)
 
 
 def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_anchors: int,

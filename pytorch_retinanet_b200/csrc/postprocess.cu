@@ -2,7 +2,17 @@
 // Replaces Retinanet.process_detections (retinanet/models.py:160-243) and the torchvision ops it
 // calls (clip_boxes_to_image, remove_small_boxes, nms).
 //
-// Pipeline (all on one stream, no host synchronisation):
+// Two algorithms share the streaming filter K1:
+//  * LAZY (default): one CTA per image runs greedy class-aware NMS in GLOBAL score order and stops as
+//    soon as max_det boxes are kept.  Kept status of a candidate only depends on higher-ranked
+//    candidates of its own class, so the first max_det kept boxes in global order ARE the
+//    reference's output; the top candidates are obtained with a radix select (8-bit digits, MSB
+//    first, early exit) + a 1024-key bitonic sort, LZ_ROUNDS rounds at most.  If an image still has
+//    unprocessed candidates and fewer than max_det boxes after the last round, a flag is raised and
+//    the host re-runs the batch with the general algorithm.
+//  * GENERAL: per-(image,class) segments, exact for any number of candidates (pipeline below).
+//
+// General pipeline (all on one stream, no host synchronisation):
 //  K1 score_filter   HBM-bound streaming pass over the [N,A,C] logits with 128-bit loads.  The
 //                    strict test sigmoid(x) > thr is decided by ONE float compare against a guard
 //                    logit x_lo (slightly below logit(thr)); only the rare survivors evaluate the
@@ -36,9 +46,15 @@ constexpr int PP_WSTAGE = 96;      // staged candidates per warp
 constexpr int NMS_CHUNK = 256;
 constexpr int SORT_SMEM = 2048;    // keys sorted in shared memory
 constexpr int MAX_DET_CAP = 1024;
+constexpr int LZ_BLOCK = 1024;
+constexpr int LZ_M = 1024;         // candidates taken per round (radix select + sort)
+constexpr int LZ_ROUNDS = 4;
+constexpr int LZ_CACHE = 16384;    // candidate keys cached in shared memory (128 KB)
+constexpr int LZ_CHUNK = 256;
 
 struct PPWorkspace {
     u32 *pool_count;     // [1] candidates found (may exceed capacity)
+    u32 *img_count;      // [N] candidates found per image (LAZY; may exceed cap_n)
     int *seg_count;      // [S]
     int *seg_off;        // [S+1]
     int *cursor;         // [S]
@@ -60,6 +76,7 @@ PPWorkspace carve(void *base, int N, int C, int64_t cap) {
     char *p = (char *)base;
     size_t o = 0;
     w.pool_count = (u32 *)(p + o); o += 256;
+    w.img_count = (u32 *)(p + o); o = align_up(o + (size_t)N * 4, 256);
     w.seg_count = (int *)(p + o); o = align_up(o + S * 4, 256);
     w.zero_bytes = o;
     w.seg_off = (int *)(p + o); o = align_up(o + (S + 1) * 4, 256);
@@ -100,36 +117,36 @@ struct FilterParams {
     float x_lo, thr;
     float4 wts;
     u32 cap;
+    u32 cap_n;           // LAZY: per-image capacity of the candidate lists (cap / N)
     PPWorkspace w;
 };
 
 // Rare path, deliberately NOT inlined: the streaming loop stays a few dozen instructions (the
 // v1 kernel inlined 16 copies of sigmoid+decode and stalled on instruction fetch).
-// Evaluates the exact score of the <= 4 logits of one vector, decodes the anchor's box once,
-// applies the small-box filter and stages the survivors in the warp's shared-memory buffer.
+// Evaluates the exact score of the <= 4 logits of one vector and stages the survivors in the
+// warp's shared-memory buffer.  Box decoding / small-box filtering is deferred to the NMS kernels,
+// where it runs on converged warps instead of one lane at a time.
+// LAZY keys: (~score_bits << 32) | (class*A + anchor)  -> ascending = score desc, class asc, anchor asc
+// GENERAL  : (~score_bits << 32) | anchor, plus the (image,class) segment id
+template <bool LAZY>
 __device__ __noinline__ void emit_candidates(const FilterParams &P, float4 v, int nvals, int n, int c0,
-                                             long long anchor, long long row, float imw, float imh,
-                                             u64 *st_key, u32 *st_seg, int *st_n) {
+                                             long long anchor, u64 *st_key, u32 *st_seg, int *st_n) {
     const float vals[4] = {v.x, v.y, v.z, v.w};
-    bool have_box = false, box_ok = false;
     for (int k = 0; k < nvals; ++k) {
         if (!(vals[k] > P.x_lo)) continue;
         const float s = rn::sigmoid_ref(vals[k]);
         if (!(s > P.thr)) continue;                                // models.py:196 strict >
-        if (!have_box) {
-            const float4 b = decode_clip(P.bbox, P.anchors, row, (long long)n * P.anchor_stride + anchor, P.wts, imw, imh);
-            // remove_small_boxes(min_size=1e-2), models.py:203
-            box_ok = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);
-            have_box = true;
-        }
-        if (!box_ok) return;
-        const u64 key = ((u64)(~__float_as_uint(s)) << 32) | (u64)(u32)anchor;
+        const u32 lo = LAZY ? (u32)((long long)(c0 + k) * P.A + anchor) : (u32)anchor;
+        const u64 key = ((u64)(~__float_as_uint(s)) << 32) | (u64)lo;
         const u32 seg = (u32)(n * P.C + c0 + k);
         const int pos = atomicAdd(st_n, 1);
         if (pos < PP_WSTAGE) {
             st_key[pos] = key;
-            st_seg[pos] = seg;
-        } else {                                                   // staging full: go straight to the pool
+            if (!LAZY) st_seg[pos] = seg;
+        } else if (LAZY) {                                         // staging full: go straight to the list
+            const u32 gp = atomicAdd(P.w.img_count + n, 1u);
+            if (gp < P.cap_n) P.w.pool_key[(size_t)n * P.cap_n + gp] = key;
+        } else {
             const u32 gp = atomicAdd(P.w.pool_count, 1u);
             if (gp < P.cap) {
                 P.w.pool_key[gp] = key;
@@ -143,10 +160,10 @@ __device__ __noinline__ void emit_candidates(const FilterParams &P, float4 v, in
 // Warp-autonomous streaming filter: every warp owns PP_WSPAN consecutive anchors of one image, reads
 // them with 128-bit loads (PP_U in flight per lane), stages its rare survivors in its own slice of
 // shared memory and flushes them with ONE global atomic per warp.  No block-level barrier anywhere.
-template <int VEC>
+template <int VEC, bool LAZY>
 __global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_kernel(const __grid_constant__ FilterParams P) {
     __shared__ u64 s_key[PP_BLOCK / 32][PP_WSTAGE];
-    __shared__ u32 s_seg[PP_BLOCK / 32][PP_WSTAGE];
+    __shared__ u32 s_seg[LAZY ? 1 : PP_BLOCK / 32][LAZY ? 1 : PP_WSTAGE];
     __shared__ int s_n[PP_BLOCK / 32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -158,9 +175,8 @@ __global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_kernel(const __grid_
     const int CV = P.C / VEC;
     const int nvec = span * CV;
     const float *src = P.logits + row0 * P.C;
-    const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
     u64 *st_key = s_key[warp];
-    u32 *st_seg = s_seg[warp];
+    u32 *st_seg = LAZY ? nullptr : s_seg[warp];
     int *st_n = &s_n[warp];
     if (lane == 0) *st_n = 0;
     __syncwarp();
@@ -182,7 +198,7 @@ __global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_kernel(const __grid_
             if (vmax > P.x_lo) {                                   // rare
                 const int f = base + u * 32 + lane;
                 const int al = P.magic ? (int)__umulhi((unsigned)f, P.magic) : f;
-                emit_candidates(P, v[u], VEC, n, (f - al * CV) * VEC, a0 + al, row0 + al, imw, imh, st_key, st_seg, st_n);
+                emit_candidates<LAZY>(P, v[u], VEC, n, (f - al * CV) * VEC, a0 + al, st_key, st_seg, st_n);
             }
         }
     }
@@ -190,11 +206,13 @@ __global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_kernel(const __grid_
     const int staged = min(*st_n, PP_WSTAGE);
     if (staged == 0) return;
     u32 gbase = 0;
-    if (lane == 0) gbase = atomicAdd(P.w.pool_count, (u32)staged);
+    if (lane == 0) gbase = atomicAdd(LAZY ? P.w.img_count + n : P.w.pool_count, (u32)staged);
     gbase = __shfl_sync(0xffffffffu, gbase, 0);
     for (int i = lane; i < staged; i += 32) {
         const u32 gp = gbase + (u32)i;
-        if (gp < P.cap) {
+        if (LAZY) {
+            if (gp < P.cap_n) P.w.pool_key[(size_t)n * P.cap_n + gp] = st_key[i];
+        } else if (gp < P.cap) {
             P.w.pool_key[gp] = st_key[i];
             P.w.pool_seg[gp] = st_seg[i];
             atomicAdd(P.w.seg_count + st_seg[i], 1);
@@ -369,8 +387,10 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
             }
         }
         const float area = nms_area(b);
+        // remove_small_boxes(min_size=1e-2), models.py:203: such candidates are neither kept nor suppress
+        const bool box_ok = RAW || ((__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f));
         // (a) suppression by boxes kept in earlier chunks (tiles of NMS_CHUNK through shared memory)
-        bool alive = t < m;
+        bool alive = t < m && box_ok;
         for (int k0 = 0; k0 < K; k0 += NMS_CHUNK) {
             const int kn = min(NMS_CHUNK, K - k0);
             __syncthreads();
@@ -456,6 +476,250 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
     }
     if (!RAW && t == 0) P.kept_count[seg] = K;
 }
+
+// ------------------------------------------------------------------------------------------- LAZY
+struct LazyParams {
+    const float4 *bbox;
+    const float4 *anchors;
+    const int *im_hw;
+    long long A;
+    long long anchor_stride;
+    int C;
+    int N;
+    float thr;
+    float4 wts;
+    int max_det;
+    const u64 *cand_key;     // [N][cap_n]
+    const u32 *img_count;    // [N]
+    u32 cap_n;
+    float *out_boxes;
+    float *out_scores;
+    long long *out_labels;
+    int *out_count;
+    int *status;             // [0] max candidates/image * N (atomicMax), [2] fallback flag
+};
+
+struct LazySmem {
+    u64 sel[LZ_M];
+    float4 box[LZ_CHUNK];
+    float area[LZ_CHUNK];
+    int cls[LZ_CHUNK];
+    u32 mask[LZ_CHUNK][LZ_CHUNK / 32];
+    float4 kbox[MAX_DET_CAP];
+    float karea[MAX_DET_CAP];
+    int kcls[MAX_DET_CAP];
+    u32 kscore[MAX_DET_CAP];
+    u32 hist[256];
+    u32 removed[LZ_CHUNK / 32];
+    int wbase[LZ_CHUNK / 32 + 1];
+    u64 prefix, mask_bits, thr_key;
+    u32 need;
+    int nsel, done;
+};
+
+__global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_constant__ LazyParams P) {
+    extern __shared__ __align__(16) unsigned char lz_raw[];
+    LazySmem &S = *reinterpret_cast<LazySmem *>(lz_raw);
+    u64 *s_cand = reinterpret_cast<u64 *>(lz_raw + ((sizeof(LazySmem) + 15) & ~(size_t)15));
+
+    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u32 found = P.img_count[n];
+    if (t == 0) {
+        const unsigned long long scaled = (unsigned long long)found * (unsigned long long)P.N;
+        atomicMax(P.status + 0, (int)min(scaled, 0x7fffffffULL));
+    }
+    const int K = (int)min(found, P.cap_n);
+    if (K == 0) {
+        if (t == 0) P.out_count[n] = 0;
+        return;
+    }
+    const u64 *g_cand = P.cand_key + (size_t)n * P.cap_n;
+    const bool cached = K <= LZ_CACHE;
+    if (cached) {
+        for (int i = t; i < K; i += LZ_BLOCK) s_cand[i] = g_cand[i];
+    }
+    __syncthreads();
+    const u64 *cand = cached ? s_cand : g_cand;
+    const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
+    const long long img_row = (long long)n * P.A, anc_row = (long long)n * P.anchor_stride;
+    const u32 A32 = (u32)P.A;
+
+    int kept = 0, processed = 0;
+    u64 last = 0;                                  // keys are > 0 (score <= 1 -> ~bits >= 0xC07FFFFF)
+    for (int round = 0; round < LZ_ROUNDS && processed < K && kept < P.max_det; ++round) {
+        const int remaining = K - processed;
+        const int take = min(remaining, LZ_M);
+        // ---- threshold key T: the take-th smallest key among keys > last (radix select) ----
+        u64 T = ~0ULL;
+        if (remaining > LZ_M) {
+            if (t == 0) { S.prefix = 0; S.mask_bits = 0; S.need = (u32)take; S.done = 0; S.thr_key = ~0ULL; }
+            __syncthreads();
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                if (t < 256) S.hist[t] = 0;
+                __syncthreads();
+                const u64 prefix = S.prefix, mbits = S.mask_bits;
+                for (int i = t; i < K; i += LZ_BLOCK) {
+                    const u64 k = cand[i];
+                    if (k > last && (k & mbits) == prefix) atomicAdd(&S.hist[(u32)(k >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    u32 cnt[8], sum = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { cnt[i] = S.hist[lane * 8 + i]; sum += cnt[i]; }
+                    u32 incl = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    const u32 need = S.need, excl = incl - sum;
+                    if (excl < need && need <= incl) {            // exactly one lane
+                        u32 acc = excl;
+                        int b = 0;
+                        for (; b < 8; ++b) {
+                            if (acc + cnt[b] >= need) break;
+                            acc += cnt[b];
+                        }
+                        const u64 np = prefix | ((u64)(lane * 8 + b) << shift);
+                        S.need = need - acc;
+                        S.prefix = np;
+                        S.mask_bits = mbits | (255ULL << shift);
+                        if (need - acc == cnt[b] || shift == 0) {  // the whole bucket is taken: stop early
+                            S.done = 1;
+                            S.thr_key = np | (shift ? ((1ULL << shift) - 1ULL) : 0ULL);
+                        }
+                    }
+                }
+                __syncthreads();
+                if (S.done) break;
+            }
+            T = S.thr_key;
+        }
+        // ---- gather + sort the selected keys ----
+        if (t == 0) S.nsel = 0;
+        __syncthreads();
+        for (int i = t; i < K; i += LZ_BLOCK) {
+            const u64 k = cand[i];
+            if (k > last && k <= T) {
+                const int slot = atomicAdd(&S.nsel, 1);
+                if (slot < LZ_M) S.sel[slot] = k;
+            }
+        }
+        __syncthreads();
+        const int nsel = min(S.nsel, LZ_M);
+        block_bitonic_sort(S.sel, nsel);
+
+        // ---- greedy class-aware NMS over the sorted keys, LZ_CHUNK at a time ----
+        for (int c0 = 0; c0 < nsel && kept < P.max_det; c0 += LZ_CHUNK) {
+            const int m = min(LZ_CHUNK, nsel - c0);
+            if (t < LZ_CHUNK) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                int cls = -1;
+                bool alive = false;
+                if (t < m) {
+                    const u32 lo = (u32)S.sel[c0 + t];
+                    cls = (int)(lo / A32);
+                    const long long anchor = (long long)(lo - (u32)cls * A32);
+                    b = decode_clip(P.bbox, P.anchors, img_row + anchor, anc_row + anchor, P.wts, imw, imh);
+                    // remove_small_boxes(min_size=1e-2), models.py:203
+                    alive = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);
+                }
+                const float area = nms_area(b);
+                if (alive) {                                   // (a) boxes kept so far, same class only
+                    for (int k = 0; k < kept; ++k)
+                        if (S.kcls[k] == cls && nms_suppresses(S.kbox[k], S.karea[k], b, area, P.thr)) { alive = false; break; }
+                }
+                S.box[t] = b;
+                S.area[t] = area;
+                S.cls[t] = cls;
+                const u32 dead = __ballot_sync(0xffffffffu, !alive);
+                if (lane == 0) S.removed[warp] = dead;
+            }
+            __syncthreads();
+            // (b) bitmask: 256 rows x 8 words = 2048 (row, word) tasks, two per thread, word uniform per warp
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int task = q * LZ_BLOCK + t;
+                const int row = task & (LZ_CHUNK - 1), w = task >> 8;
+                u32 bits = 0;
+                const bool row_alive = row < m && !((S.removed[row >> 5] >> (row & 31)) & 1u);
+                if (row_alive && w * 32 + 31 > row && w * 32 < m) {
+                    const float4 b = S.box[row];
+                    const float area = S.area[row];
+                    const int cls = S.cls[row];
+                    const int jlo = max(w * 32, row + 1), jhi = min(w * 32 + 32, m);
+                    for (int j = jlo; j < jhi; ++j)
+                        if (S.cls[j] == cls && nms_suppresses(b, area, S.box[j], S.area[j], P.thr)) bits |= 1u << (j & 31);
+                }
+                S.mask[row][w] = bits;
+            }
+            __syncthreads();
+            // (c) warp-cooperative suppression scan (see nms_kernel)
+            if (warp == 0) {
+                u32 rw = lane < LZ_CHUNK / 32 ? S.removed[lane] : 0u;
+                const int groups = (m + 31) >> 5;
+                for (int g = 0; g < groups; ++g) {
+                    const int row = g * 32 + lane;
+                    const u32 diag = row < m ? S.mask[row][g] : 0u;
+                    u32 rg = __shfl_sync(0xffffffffu, rw, g);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const u32 di = __shfl_sync(0xffffffffu, diag, i);
+                        rg |= ((rg >> i) & 1u) ? 0u : di;
+                    }
+                    const int nrows = min(32, m - g * 32);
+                    const u32 keptm = ~rg & (nrows == 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+                    if (lane == g) rw = rg;
+                    if (lane > g && lane < LZ_CHUNK / 32) {
+                        u32 acc = 0;
+                        for (u32 km = keptm; km; km &= km - 1) acc |= S.mask[g * 32 + __ffs(km) - 1][lane];
+                        rw |= acc;
+                    }
+                }
+                if (lane < LZ_CHUNK / 32) S.removed[lane] = rw;
+            }
+            __syncthreads();
+            // (d) append the kept boxes, in order, to the image's output list (first max_det only)
+            if (t < LZ_CHUNK) {
+                const bool kp = t < m && !((S.removed[warp] >> lane) & 1u);
+                const u32 km = __ballot_sync(0xffffffffu, kp);
+                if (lane == 0) S.wbase[warp + 1] = __popc(km);
+            }
+            __syncthreads();
+            if (t == 0) {
+                S.wbase[0] = 0;
+                for (int w = 0; w < LZ_CHUNK / 32; ++w) S.wbase[w + 1] += S.wbase[w];
+            }
+            __syncthreads();
+            if (t < LZ_CHUNK) {
+                const bool kp = t < m && !((S.removed[warp] >> lane) & 1u);
+                const u32 km = __ballot_sync(0xffffffffu, kp);
+                const int pos = kept + S.wbase[warp] + __popc(km & ((1u << lane) - 1u));
+                if (kp && pos < P.max_det) {
+                    S.kbox[pos] = S.box[t];
+                    S.karea[pos] = S.area[t];
+                    S.kcls[pos] = S.cls[t];
+                    S.kscore[pos] = ~(u32)(S.sel[c0 + t] >> 32);
+                }
+            }
+            kept = min(P.max_det, kept + S.wbase[LZ_CHUNK / 32]);
+            __syncthreads();
+        }
+        processed += nsel;
+        last = T;
+    }
+    if (kept < P.max_det && processed < K && t == 0) atomicOr(P.status + 2, 1);   // general algorithm needed
+    for (int i = t; i < kept; i += LZ_BLOCK) {
+        const long long o = (long long)n * P.max_det + i;
+        ((float4 *)P.out_boxes)[o] = S.kbox[i];
+        P.out_scores[o] = __uint_as_float(S.kscore[i]);
+        P.out_labels[o] = (long long)S.kcls[i] + 1;            // models.py:230 labels + 1
+    }
+    if (t == 0) P.out_count[n] = kept;
+}
+
+__global__ void set_status_capacity_kernel(int *status, int capacity) { status[1] = capacity; }
 
 // ------------------------------------------------------------------------------------------- K5
 struct TopkParams {
@@ -677,7 +941,7 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
                               int64_t anchor_image_stride, const int32_t *im_hw, int N,
                               int64_t A, int C, float score_thr, double nms_thr, int max_det,
                               const float *weights_host, int pre_nms_topk, const int64_t *level_off_host,
-                              int num_levels, int64_t cand_capacity, float *out_boxes, float *out_scores,
+                              int num_levels, int algo, int64_t cand_capacity, float *out_boxes, float *out_scores,
                               int64_t *out_labels, int32_t *out_count, int32_t *out_status, void *workspace,
                               size_t workspace_bytes, rn_stream_t stream) {
     (void)level_off_host; (void)num_levels;
@@ -693,11 +957,15 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
     RN_CHECK_ARG(cand_capacity >= 1 && cand_capacity < 0x7fffffffLL, RN_E_BADARG, "rn_postprocess: bad cand_capacity");
     RN_CHECK_ARG(pre_nms_topk == 0, RN_E_BADARG, "rn_postprocess: pre_nms_topk is not implemented in this build");
     RN_CHECK_ARG((size_t)N * C < 0x7fffffffULL, RN_E_TOOLARGE, "rn_postprocess: N*C too large");
+    RN_CHECK_ARG(algo == RN_PP_LAZY || algo == RN_PP_GENERAL, RN_E_BADARG, "rn_postprocess: unknown algo %d", algo);
+    RN_CHECK_ARG(algo != RN_PP_LAZY || (unsigned long long)A * (unsigned long long)C < (1ULL << 32), RN_E_TOOLARGE,
+                 "rn_postprocess: the lazy algorithm needs A*C < 2^32 (use RN_PP_GENERAL)");
     PPWorkspace w = carve(workspace, N, C, cand_capacity);
     RN_CHECK_ARG(workspace_bytes >= w.total_bytes, RN_E_WORKSPACE, "rn_postprocess: workspace too small (%zu < %zu)",
                  workspace_bytes, w.total_bytes);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(workspace, 0, w.zero_bytes, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out_status, 0, 4 * sizeof(int32_t), s);
     if (e != cudaSuccess) { rn_set_error("rn_postprocess: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
 
     // guard logit: every x <= x_lo has sigmoid(x) <= thr with a 1e-3 margin (SFU/libm error is ~1e-7)
@@ -709,17 +977,43 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
         double xt = log((double)thr / (1.0 - (double)thr));
         x_lo = (float)(xt - 1e-3 * fmax(1.0, fabs(xt)));
     }
+    const bool lazy = algo == RN_PP_LAZY;
     FilterParams F;
     F.logits = logits; F.bbox = (const float4 *)bbox; F.anchors = (const float4 *)anchors; F.im_hw = im_hw;
-    F.A = A; F.anchor_stride = anchor_image_stride; F.C = C; F.x_lo = x_lo; F.thr = thr; F.cap = (u32)cand_capacity; F.w = w;
+    F.A = A; F.anchor_stride = anchor_image_stride; F.C = C; F.x_lo = x_lo; F.thr = thr; F.cap = (u32)cand_capacity;
+    F.cap_n = (u32)max((int64_t)1, cand_capacity / N); F.w = w;
     F.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
     const bool vec4 = (C % 4 == 0) && (((uintptr_t)logits & 15) == 0);
     const int CV = vec4 ? C / 4 : C;
     F.magic = CV == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)CV - 1) / (unsigned)CV);
     const long long warp_tasks = (A + PP_WSPAN - 1) / PP_WSPAN;
     dim3 grid((unsigned)((warp_tasks + PP_BLOCK / 32 - 1) / (PP_BLOCK / 32)), (unsigned)N);
-    if (vec4) score_filter_kernel<4><<<grid, PP_BLOCK, 0, s>>>(F); else score_filter_kernel<1><<<grid, PP_BLOCK, 0, s>>>(F);
+    if (lazy) {
+        if (vec4) score_filter_kernel<4, true><<<grid, PP_BLOCK, 0, s>>>(F); else score_filter_kernel<1, true><<<grid, PP_BLOCK, 0, s>>>(F);
+    } else {
+        if (vec4) score_filter_kernel<4, false><<<grid, PP_BLOCK, 0, s>>>(F); else score_filter_kernel<1, false><<<grid, PP_BLOCK, 0, s>>>(F);
+    }
     RN_CHECK_LAUNCH("rn_postprocess/score_filter");
+
+    // round the double threshold DOWN to fp32: (double)ovr > thr  <=>  ovr > thr_f  for every fp32 ovr
+    float thr_f = (float)nms_thr;
+    if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
+
+    if (lazy) {
+        LazyParams Z;
+        Z.bbox = (const float4 *)bbox; Z.anchors = (const float4 *)anchors; Z.im_hw = im_hw; Z.A = A;
+        Z.anchor_stride = anchor_image_stride; Z.C = C; Z.N = N; Z.thr = thr_f; Z.wts = F.wts; Z.max_det = max_det;
+        Z.cand_key = w.pool_key; Z.img_count = w.img_count; Z.cap_n = F.cap_n; Z.out_boxes = out_boxes;
+        Z.out_scores = out_scores; Z.out_labels = (long long *)out_labels; Z.out_count = out_count; Z.status = out_status;
+        const size_t smem = ((sizeof(LazySmem) + 15) & ~(size_t)15) + (size_t)LZ_CACHE * sizeof(u64);
+        cudaFuncSetAttribute(lazy_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lazy_nms_kernel<<<N, LZ_BLOCK, smem, s>>>(Z);
+        RN_CHECK_LAUNCH("rn_postprocess/lazy_nms");
+        // status[1] = capacity (N * cap_n) is written by a 1-thread epilogue to keep the call async
+        set_status_capacity_kernel<<<1, 1, 0, s>>>(out_status, (int)min((long long)F.cap_n * N, 0x7fffffffLL));
+        RN_CHECK_LAUNCH("rn_postprocess/status");
+        return 0;
+    }
 
     const int S = N * C;
     segment_scan_kernel<<<1, 1024, 0, s>>>(w.seg_count, S, w.seg_off, w.cursor, w.pool_count, (u32)cand_capacity, out_status);
@@ -728,9 +1022,6 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
                                                         w.sorted_key);
     RN_CHECK_LAUNCH("rn_postprocess/scatter");
 
-    // round the double threshold DOWN to fp32: (double)ovr > thr  <=>  ovr > thr_f  for every fp32 ovr
-    float thr_f = (float)nms_thr;
-    if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
     NmsParams M;
     M.bbox = (const float4 *)bbox; M.anchors = (const float4 *)anchors; M.im_hw = im_hw; M.boxes = nullptr;
     M.keep_flags = nullptr; M.A = A; M.anchor_stride = anchor_image_stride; M.C = C; M.thr = thr_f; M.wts = F.wts; M.seg_off = w.seg_off;

@@ -17,7 +17,22 @@ from torch import Tensor
 
 from . import _native
 from .config import BBOX_REG_WEIGHTS, MAX_DETECTIONS_PER_IMAGE, NMS_THRES, SCORE_THRES
+from .box_utils import _REG_WEIGHTS_C
 from .losses import _shared_anchors
+
+_HW_CACHE: Dict[Tuple, Tensor] = {}
+
+
+def _image_sizes_tensor(im_szs, dev) -> Tensor:
+    """[N,2] int32 (h,w) on the device; cached per (sizes, device) — batches of equal-size images repeat."""
+    key = (tuple((int(h), int(w)) for h, w in im_szs), dev.index)
+    t = _HW_CACHE.get(key)
+    if t is None:
+        if len(_HW_CACHE) > 64:
+            _HW_CACHE.clear()
+        t = torch.tensor(key[0], dtype=torch.int32).reshape(-1, 2).to(dev)
+        _HW_CACHE[key] = t
+    return t
 
 
 def default_candidate_capacity(N: int, A: int, C: int) -> int:
@@ -27,8 +42,12 @@ def default_candidate_capacity(N: int, A: int, C: int) -> int:
 def postprocess_batch(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
                       im_szs: Sequence[Tuple[int, int]], score_thres: float, nms_thres: float, max_det: int,
                       pre_nms_topk: Optional[int] = None, level_offsets: Optional[Sequence[int]] = None,
-                      cand_capacity: Optional[int] = None):
-    """Returns (boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int])."""
+                      cand_capacity: Optional[int] = None, algo: str = "auto"):
+    """Returns (boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int]).
+
+    ``algo``: "auto" = lazy per-image algorithm, transparently repeated with the general
+    per-(image,class) algorithm when the lazy one reports it could not finish an image;
+    "lazy" / "general" force one of them (tests).  Results are identical."""
     lib = _native.load()
     dev = cls_preds.device
     N, A, C = cls_preds.shape
@@ -38,11 +57,12 @@ def postprocess_batch(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, an
     b = b if (b.dtype == torch.float32 and b.is_contiguous()) else b.to(torch.float32).contiguous()
     if len(im_szs) != N:
         raise ValueError(f"{len(im_szs)} image sizes for {N} images")
-    hw = torch.tensor([[int(h), int(w)] for h, w in im_szs], dtype=torch.int32).to(dev, non_blocking=True)
+    hw = _image_sizes_tensor(im_szs, dev)
     out_boxes = torch.empty((N, max_det, 4), dtype=torch.float32, device=dev)
     out_scores = torch.empty((N, max_det), dtype=torch.float32, device=dev)
     out_labels = torch.empty((N, max_det), dtype=torch.int64, device=dev)
-    meta = torch.empty((N + 2,), dtype=torch.int32, device=dev)   # counts [N] + status [2]
+    meta = torch.empty((N + 4,), dtype=torch.int32, device=dev)   # counts [N] + status [4]
+    use_general = algo == "general" or (A * C >= (1 << 32))
     cap = int(cand_capacity) if cand_capacity else default_candidate_capacity(N, A, C)
     topk = int(pre_nms_topk) if pre_nms_topk else 0
     lvl = None
@@ -59,16 +79,22 @@ def postprocess_batch(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, an
             rc = lib.rn_postprocess(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
                                     _native.ptr(anchors, torch.float32, "anchors"), anchor_stride, _native.ptr(hw), N, A, C,
                                     float(score_thres), float(nms_thres), int(max_det),
-                                    _native.host_floats(BBOX_REG_WEIGHTS), topk, lvl, nlev, cap,
+                                    _REG_WEIGHTS_C, topk, lvl, nlev, 1 if use_general else 0, cap,
                                     _native.ptr(out_boxes), _native.ptr(out_scores), _native.ptr(out_labels),
                                     meta.data_ptr(), meta.data_ptr() + 4 * N, _native.ptr(ws), ws_bytes,
                                     _native.stream_ptr(dev))
         _native.check(rc, "rn_postprocess")
         host = meta.tolist()          # the single D2H copy / sync of the path
-        found, capacity = host[N], host[N + 1]
-        if found <= capacity:
-            return out_boxes, out_scores, out_labels, host[:N]
-        cap = found                   # candidate pool overflowed: the exact need is now known
+        found, capacity, fallback = host[N], host[N + 1], host[N + 2]
+        if found > capacity:
+            cap = found               # candidate pool overflowed: the exact need is now known
+            continue
+        if fallback and not use_general:
+            if algo == "lazy":
+                raise _native.NativeError("rn_postprocess: lazy algorithm could not finish (algo='lazy' forced)")
+            use_general = True        # rare: an image needs more rounds than the lazy budget
+            continue
+        return out_boxes, out_scores, out_labels, host[:N]
 
 
 def process_detections(self, outputs: Dict[str, Tensor], anchors: List[Tensor],

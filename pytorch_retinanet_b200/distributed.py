@@ -49,9 +49,11 @@ class ShardedRetinaNetLosses(RetinaNetLosses):
         packed = PackedTargets([t["boxes"] for t in targets], [t["labels"] for t in targets], cls.device)
         c, r, image = _FusedRetinaNetLoss.apply(cls, box, an, stride, packed, self._hp(n_global))
         self.last_per_image = image
+        if world == 1:
+            self.last_stats = None
+            return {"classification_loss": c, "regression_loss": r}
         stats = torch.stack([c.detach(), r.detach(), image[:, 2].sum(), image.new_tensor(float(n_local))])
-        if world > 1:
-            dist.all_reduce(stats, group=self.group)          # the ONE collective of the path (16 bytes)
+        dist.all_reduce(stats, group=self.group)              # the ONE collective of the path (16 bytes)
         self.last_stats = stats                                # [cls, reg, sum F, N] of the global batch
         # value = global loss; gradient flows only through the local shard (already / N_global)
         return {"classification_loss": c + (stats[0] - c.detach()),

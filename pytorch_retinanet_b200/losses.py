@@ -15,7 +15,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _native
-from .box_utils import PackedTargets, match_batch
+from .box_utils import _REG_WEIGHTS_C, PackedTargets, match_batch
 from .config import (BBOX_REG_WEIGHTS, FOCAL_LOSS_ALPHA, FOCAL_LOSS_GAMMA, IOU_THRESHOLDS_BACKGROUND,
                      IOU_THRESHOLDS_FOREGROUND, SMOOTH_L1_LOSS_BETA)
 
@@ -59,7 +59,7 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
         rc = lib.rn_loss(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
                          _native.ptr(anchors, torch.float32, "anchors"), anchor_stride,
                          _native.ptr(packed.boxes), _native.ptr(packed.offsets), _native.ptr(codes), _native.ptr(fg),
-                         N, A, C, float(alpha), float(gamma), float(beta), _native.host_floats(BBOX_REG_WEIGHTS),
+                         N, A, C, float(alpha), float(gamma), float(beta), _REG_WEIGHTS_C,
                          float(batch_div), _native.ptr(out_image), _native.ptr(out_total), _native.ptr(gl),
                          _native.ptr(gb), _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
     _native.check(rc, "rn_loss")

@@ -268,14 +268,25 @@ def test_loss_generic_gamma_and_l1(P):
 
 
 # ------------------------------------------------------------------------------------------ post-processing
-def gpu_detect(P, cls, bb, anchors_list, im_szs, **kw):
+def gpu_detect(P, cls, bb, anchors_list, im_szs, algo="auto", **kw):
+    """algo="auto": through the drop-in process_detections(self, outputs, anchors, im_szs);
+    "lazy"/"general": the same C-ABI call with the algorithm forced."""
     from types import SimpleNamespace
-    stub = SimpleNamespace(score_thres=kw.get("score", 0.05), nms_thres=kw.get("nms", 0.5),
-                           detections_per_img=kw.get("max_det", 100))
-    outputs = {"cls_preds": cls.cuda(), "bbox_preds": bb.cuda()}
-    dets = P.process_detections(stub, outputs, anchors_list, im_szs)
-    assert outputs == {}                                          # models.py:168-169 pops both keys
-    return dets
+    score, nms, max_det = kw.get("score", 0.05), kw.get("nms", 0.5), kw.get("max_det", 100)
+    if algo == "auto":
+        stub = SimpleNamespace(score_thres=score, nms_thres=nms, detections_per_img=max_det)
+        outputs = {"cls_preds": cls.cuda(), "bbox_preds": bb.cuda()}
+        dets = P.process_detections(stub, outputs, anchors_list, im_szs)
+        assert outputs == {}                                      # models.py:168-169 pops both keys
+        return dets
+    from pytorch_retinanet_b200.detections import postprocess_batch
+    from pytorch_retinanet_b200.losses import _shared_anchors
+    an, stride = _shared_anchors(anchors_list)
+    ob, os_, ol, counts = postprocess_batch(cls.cuda(), bb.cuda(), an, stride, im_szs, score, nms, max_det, algo=algo)
+    return [{"boxes": ob[i, :k], "scores": os_[i, :k], "labels": ol[i, :k]} for i, k in enumerate(counts)]
+
+
+ALGOS = ["auto", "lazy", "general"]
 
 
 def assert_dets_equal(got, want, exact=True, ctx=""):
@@ -290,13 +301,14 @@ def assert_dets_equal(got, want, exact=True, ctx=""):
         assert rel_close(got["boxes"], want["boxes"], BOX_RTOL, 1e-4), ctx
 
 
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("cid", [1, 2, 5])
-def test_postprocess_full_size(P, cid):
+def test_postprocess_full_size(P, cid, algo):
     """Bit-exact against the eager op sequence on the same device (CUDA oracle: same expf), and
     against the CPU reference's golden detections: same labels/order, floats within 1e-5."""
     b, g = config_image(cid)
     anc = b["anchors"].cuda()
-    got = gpu_detect(P, b["cls_preds"], b["bbox_preds"], [anc], b["im_szs"])[0]
+    got = gpu_detect(P, b["cls_preds"], b["bbox_preds"], [anc], b["im_szs"], algo=algo)[0]
     want_cuda = O.postprocess(b["cls_preds"].cuda(), b["bbox_preds"].cuda(), [anc], b["im_szs"])[0]
     assert_dets_equal(got, want_cuda, exact=True, ctx=f"config{cid} vs CUDA oracle")
     want_cpu = {"boxes": torch.from_numpy(g["det_boxes"]), "scores": torch.from_numpy(g["det_scores"]),
@@ -304,13 +316,14 @@ def test_postprocess_full_size(P, cid):
     assert_dets_equal(got, want_cpu, exact=False, ctx=f"config{cid} vs CPU reference golden")
 
 
-def test_postprocess_random_small_golden(P):
+@pytest.mark.parametrize("algo", ["auto", "general"])
+def test_postprocess_random_small_golden(P, algo):
     g = golden("random_small.npz")
     for k in range(int(g["n_cases"])):
         p = f"c{k}_"
         anc = torch.from_numpy(g[p + "anchors"]).cuda()
         cls, bb = torch.from_numpy(g[p + "cls"]), torch.from_numpy(g[p + "bb"])
-        got = gpu_detect(P, cls, bb, [anc], [(90, 120)], max_det=20)[0]
+        got = gpu_detect(P, cls, bb, [anc], [(90, 120)], algo=algo, max_det=20)[0]
         want = O.postprocess(cls.cuda(), bb.cuda(), [anc], [(90, 120)], max_det=20)[0]
         assert_dets_equal(got, want, exact=True, ctx=f"case {k} vs CUDA oracle")
         ref = {"boxes": torch.from_numpy(g[p + "det_boxes"]), "scores": torch.from_numpy(g[p + "det_scores"]),
@@ -321,34 +334,47 @@ def test_postprocess_random_small_golden(P):
             pytest.fail(f"case {k}: detections differ from the CPU reference golden")
 
 
-def test_postprocess_batch_edge_cases(P):
-    """Batch of 4 with: an image without any candidate, huge segments (global-memory sort path and
-    multi-chunk NMS), heavy score ties, max_det < kept, C not a multiple of 4, candidate-pool overflow."""
+@pytest.mark.parametrize("algo", ["auto", "general"])
+def test_postprocess_batch_edge_cases(P, algo):
+    """Batch of 5 with: an image without any candidate, huge segments (global-memory sort path and
+    multi-chunk NMS), heavy score ties, max_det < kept, C not a multiple of 4, an image where nearly
+    everything is suppressed (lazy algorithm runs out of rounds -> general fallback), pool overflow."""
     gen = torch.Generator().manual_seed(11)
     anc = S.default_anchors((128, 160))
     A, C = anc.shape[0], 6
-    cls = torch.randn((4, A, C), generator=gen) * 1.5 - 6.0
-    bb = torch.randn((4, A, 4), generator=gen) * 0.2
+    cls = torch.randn((5, A, C), generator=gen) * 1.5 - 6.0
+    bb = torch.randn((5, A, 4), generator=gen) * 0.2
     cls[1] = -20.0                                                  # no candidates at all
     cls[2, :, 2] = torch.randn(A, generator=gen) * 0.5 + 1.0        # one class fires on every anchor (A > 2048)
     cls[3, :, 1] = 0.75                                             # thousands of exactly tied scores
     cls[3, :, 4] = torch.round(torch.randn(A, generator=gen) * 2) / 2  # few distinct values -> many ties
-    sz = [(128, 160), (100, 150), (128, 160), (120, 130)]
-    want = O.postprocess(cls.cuda(), bb.cuda(), [anc.cuda()] * 4, sz, max_det=50)
-    got = gpu_detect(P, cls, bb, [anc.cuda()] * 4, sz, max_det=50)
+    cls[4, :, :3] = torch.randn((A, 3), generator=gen) + 2.0        # ~11k candidates, tiny image: almost all suppressed
+    sz = [(128, 160), (100, 150), (128, 160), (120, 130), (6, 5)]
+    ancs = [anc.cuda()] * 5
+    want = O.postprocess(cls.cuda(), bb.cuda(), ancs, sz, max_det=50)
+    got = gpu_detect(P, cls, bb, ancs, sz, algo=algo, max_det=50)
     assert got[1]["boxes"].shape == (0, 4) and got[1]["scores"].shape == (0,) and got[1]["labels"].shape == (0,)
-    for i in range(4):
+    assert want[4]["boxes"].shape[0] < 50                           # the fallback case really is one
+    for i in range(5):
         assert_dets_equal(got[i], want[i], exact=True, ctx=f"image {i}")
+    if algo == "auto":
+        from pytorch_retinanet_b200 import _native
+        with pytest.raises(_native.NativeError):                    # lazy alone cannot finish image 4
+            gpu_detect(P, cls, bb, ancs, sz, algo="lazy", max_det=50)
+        got_l = gpu_detect(P, cls[:4], bb[:4], ancs[:4], sz[:4], algo="lazy", max_det=50)
+        for i in range(4):
+            assert_dets_equal(got_l[i], want[i], exact=True, ctx=f"lazy image {i}")
     # candidate pool overflow -> transparent re-run with the exact capacity
     from pytorch_retinanet_b200.detections import postprocess_batch
-    ob, os_, ol, counts = postprocess_batch(cls.cuda(), bb.cuda(), anc.cuda(), 0, sz, 0.05, 0.5, 50, cand_capacity=100)
-    for i in range(4):
+    ob, os_, ol, counts = postprocess_batch(cls.cuda(), bb.cuda(), anc.cuda(), 0, sz, 0.05, 0.5, 50, cand_capacity=100,
+                                            algo=algo)
+    for i in range(5):
         k = counts[i]
         assert torch.equal(ob[i, :k].cpu(), want[i]["boxes"].cpu()) and torch.equal(ol[i, :k].cpu(), want[i]["labels"].cpu())
     # other thresholds
-    want2 = O.postprocess(cls.cuda(), bb.cuda(), [anc.cuda()] * 4, sz, score_thr=0.3, nms_thr=0.35, max_det=100)
-    got2 = gpu_detect(P, cls, bb, [anc.cuda()] * 4, sz, score=0.3, nms=0.35, max_det=100)
-    for i in range(4):
+    want2 = O.postprocess(cls.cuda(), bb.cuda(), ancs, sz, score_thr=0.3, nms_thr=0.35, max_det=100)
+    got2 = gpu_detect(P, cls, bb, ancs, sz, algo=algo, score=0.3, nms=0.35, max_det=100)
+    for i in range(5):
         assert_dets_equal(got2[i], want2[i], exact=True, ctx=f"thr image {i}")
 
 
