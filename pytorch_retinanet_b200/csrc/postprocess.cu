@@ -558,9 +558,18 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                 if (t < 256) S.hist[t] = 0;
                 __syncthreads();
                 const u64 prefix = S.prefix, mbits = S.mask_bits;
-                for (int i = t; i < K; i += LZ_BLOCK) {
-                    const u64 k = cand[i];
-                    if (k > last && (k & mbits) == prefix) atomicAdd(&S.hist[(u32)(k >> shift) & 255u], 1u);
+                // warp-aggregated histogram: lanes with the same digit elect one leader (match.any), so a
+                // skewed digit (e.g. the 3 possible top bytes of a score in (0.05,1]) costs 3 shared-memory
+                // atomics per warp instead of 32 serialised ones
+                for (int i0 = warp * 32; i0 < K; i0 += LZ_BLOCK) {
+                    const int i = i0 + lane;
+                    u32 digit = 256u;
+                    if (i < K) {
+                        const u64 k = cand[i];
+                        if (k > last && (k & mbits) == prefix) digit = (u32)(k >> shift) & 255u;
+                    }
+                    const u32 peers = __match_any_sync(0xffffffffu, digit);
+                    if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&S.hist[digit], (u32)__popc(peers));
                 }
                 __syncthreads();
                 if (warp == 0) {
@@ -599,12 +608,16 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
         // ---- gather + sort the selected keys ----
         if (t == 0) S.nsel = 0;
         __syncthreads();
-        for (int i = t; i < K; i += LZ_BLOCK) {
-            const u64 k = cand[i];
-            if (k > last && k <= T) {
-                const int slot = atomicAdd(&S.nsel, 1);
-                if (slot < LZ_M) S.sel[slot] = k;
-            }
+        for (int i0 = warp * 32; i0 < K; i0 += LZ_BLOCK) {            // warp-aggregated append
+            const int i = i0 + lane;
+            const u64 k = i < K ? cand[i] : 0ULL;
+            const bool pick = i < K && k > last && k <= T;
+            const u32 pm = __ballot_sync(0xffffffffu, pick);
+            int base = 0;
+            if (lane == 0 && pm) base = atomicAdd(&S.nsel, __popc(pm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int slot = base + __popc(pm & ((1u << lane) - 1u));
+            if (pick && slot < LZ_M) S.sel[slot] = k;
         }
         __syncthreads();
         const int nsel = min(S.nsel, LZ_M);
@@ -829,9 +842,15 @@ __global__ void __launch_bounds__(TOPK_BLOCK) image_topk_kernel(const TopkParams
             if (t < 256) s_hist[t] = 0;
             __syncthreads();
             const u32 prefix = s_prefix, mbits = s_mask_bits;
-            for (int e = t; e < total; e += TOPK_BLOCK) {
-                const u32 hi = get_hi(e);
-                if ((hi & mbits) == prefix) atomicAdd(&s_hist[(hi >> shift) & 255u], 1u);
+            for (int e0 = warp * 32; e0 < total; e0 += TOPK_BLOCK) {     // warp-aggregated (see lazy_nms_kernel)
+                const int e = e0 + lane;
+                u32 digit = 256u;
+                if (e < total) {
+                    const u32 hi = get_hi(e);
+                    if ((hi & mbits) == prefix) digit = (hi >> shift) & 255u;
+                }
+                const u32 peers = __match_any_sync(0xffffffffu, digit);
+                if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (u32)__popc(peers));
             }
             __syncthreads();
             if (warp == 0) {                          // find the bucket holding the need-th entry

