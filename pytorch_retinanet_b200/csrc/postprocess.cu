@@ -93,7 +93,7 @@ PPWorkspace carve(void *base, int N, int C, int64_t cap) {
 
 // decode + clip of one anchor: activ_2_bbox (box_utils.py:37-48) then clip_boxes_to_image
 // (tv:ops/boxes.py:149-182: x in [0,w], y in [0,h]).
-__device__ __forceinline__ float4 decode_clip(const float4 *__restrict__ bbox, const float4 *__restrict__ anchors,
+__device__ __noinline__ float4 decode_clip(const float4 *__restrict__ bbox, const float4 *__restrict__ anchors,
                                               long long row, long long anchor_row, float4 wts, float imw,
                                               float imh) {
     float4 b = rn::decode_box(__ldg(bbox + row), __ldg(anchors + anchor_row), wts);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const u64 *__restrict__ po
 // ------------------------------------------------------------------------------------------- K4
 // Bitonic sort (ascending) of n keys for arbitrary n: every merge runs in the same direction
 // (first step pairs i with i ^ (k-1)), so absent elements behave as +inf padding at the end.
-__device__ void block_bitonic_sort(u64 *keys, int n) {
+__device__ __noinline__ void block_bitonic_sort(u64 *keys, int n) {
     for (int k = 2; (k >> 1) < n; k <<= 1) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int j = i ^ (k - 1);
@@ -536,6 +536,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     const u64 *g_cand = P.cand_key + (size_t)n * P.cap_n;
     const bool cached = K <= LZ_CACHE;
     if (cached) {
+#pragma unroll 4
         for (int i = t; i < K; i += LZ_BLOCK) s_cand[i] = g_cand[i];
     }
     __syncthreads();
@@ -546,6 +547,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
 
     int kept = 0, processed = 0;
     u64 last = 0;                                  // keys are > 0 (score <= 1 -> ~bits >= 0xC07FFFFF)
+#pragma unroll 1
     for (int round = 0; round < LZ_ROUNDS && processed < K && kept < P.max_det; ++round) {
         const int remaining = K - processed;
         const int take = min(remaining, LZ_M);
@@ -554,6 +556,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
         if (remaining > LZ_M) {
             if (t == 0) { S.prefix = 0; S.mask_bits = 0; S.need = (u32)take; S.done = 0; S.thr_key = ~0ULL; }
             __syncthreads();
+#pragma unroll 1
             for (int shift = 56; shift >= 0; shift -= 8) {
                 if (t < 256) S.hist[t] = 0;
                 __syncthreads();
@@ -561,6 +564,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                 // warp-aggregated histogram: lanes with the same digit elect one leader (match.any), so a
                 // skewed digit (e.g. the 3 possible top bytes of a score in (0.05,1]) costs 3 shared-memory
                 // atomics per warp instead of 32 serialised ones
+#pragma unroll 1
                 for (int i0 = warp * 32; i0 < K; i0 += LZ_BLOCK) {
                     const int i = i0 + lane;
                     u32 digit = 256u;
@@ -608,6 +612,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
         // ---- gather + sort the selected keys ----
         if (t == 0) S.nsel = 0;
         __syncthreads();
+#pragma unroll 1
         for (int i0 = warp * 32; i0 < K; i0 += LZ_BLOCK) {            // warp-aggregated append
             const int i = i0 + lane;
             const u64 k = i < K ? cand[i] : 0ULL;
@@ -624,6 +629,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
         block_bitonic_sort(S.sel, nsel);
 
         // ---- greedy class-aware NMS over the sorted keys, LZ_CHUNK at a time ----
+#pragma unroll 1
         for (int c0 = 0; c0 < nsel && kept < P.max_det; c0 += LZ_CHUNK) {
             const int m = min(LZ_CHUNK, nsel - c0);
             if (t < LZ_CHUNK) {
@@ -640,6 +646,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                 }
                 const float area = nms_area(b);
                 if (alive) {                                   // (a) boxes kept so far, same class only
+#pragma unroll 1
                     for (int k = 0; k < kept; ++k)
                         if (S.kcls[k] == cls && nms_suppresses(S.kbox[k], S.karea[k], b, area, P.thr)) { alive = false; break; }
                 }
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
             }
             __syncthreads();
             // (b) bitmask: 256 rows x 8 words = 2048 (row, word) tasks, two per thread, word uniform per warp
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 2; ++q) {
                 const int task = q * LZ_BLOCK + t;
                 const int row = task & (LZ_CHUNK - 1), w = task >> 8;
@@ -662,6 +669,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                     const float area = S.area[row];
                     const int cls = S.cls[row];
                     const int jlo = max(w * 32, row + 1), jhi = min(w * 32 + 32, m);
+#pragma unroll 1
                     for (int j = jlo; j < jhi; ++j)
                         if (S.cls[j] == cls && nms_suppresses(b, area, S.box[j], S.area[j], P.thr)) bits |= 1u << (j & 31);
                 }
