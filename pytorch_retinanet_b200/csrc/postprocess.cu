@@ -48,7 +48,7 @@ constexpr int SORT_SMEM = 2048;    // keys sorted in shared memory
 constexpr int MAX_DET_CAP = 1024;
 constexpr int LZ_BLOCK = 1024;
 constexpr int LZ_M = 1024;         // candidates taken per round (radix select + sort)
-constexpr int LZ_ROUNDS = 4;
+constexpr int LZ_ROUNDS = 5;
 constexpr int LZ_CACHE = 16384;    // candidate keys cached in shared memory (128 KB)
 constexpr int LZ_CHUNK = 256;
 
@@ -444,11 +444,12 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
                 const int nrows = min(32, m - g * 32);
                 u32 keptm = ~rg & (nrows == 32 ? 0xffffffffu : ((1u << nrows) - 1u));
                 if (lane == g) rw = rg;
-                if (lane > g && lane < NMS_CHUNK / 32) {
-                    u32 acc = 0;
-                    for (u32 km = keptm; km; km &= km - 1) acc |= s_mask[g * 32 + __ffs(km) - 1][lane];
-                    rw |= acc;
-                }
+                u32 acc = 0;                                       // 4 row subsets x 8 words, all 32 lanes
+                for (u32 km = keptm & (0x11111111u << (lane >> 3)); km; km &= km - 1)
+                    acc |= s_mask[g * 32 + __ffs(km) - 1][lane & 7];
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 8);
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 16);
+                if (lane > g && lane < NMS_CHUNK / 32) rw |= acc;
             }
             if (lane < NMS_CHUNK / 32) s_removed[lane] = rw;
         }
@@ -550,10 +551,11 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
 #pragma unroll 1
     for (int round = 0; round < LZ_ROUNDS && processed < K && kept < P.max_det; ++round) {
         const int remaining = K - processed;
-        const int take = min(remaining, LZ_M);
+        const int cap_r = round == 0 ? LZ_CHUNK : LZ_M;      // first round: one chunk is usually enough
+        const int take = min(remaining, cap_r);
         // ---- threshold key T: the take-th smallest key among keys > last (radix select) ----
         u64 T = ~0ULL;
-        if (remaining > LZ_M) {
+        if (remaining > cap_r) {
             if (t == 0) { S.prefix = 0; S.mask_bits = 0; S.need = (u32)take; S.done = 0; S.thr_key = ~0ULL; }
             __syncthreads();
 #pragma unroll 1
@@ -676,11 +678,21 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                 S.mask[row][w] = bits;
             }
             __syncthreads();
-            // (c) warp-cooperative suppression scan (see nms_kernel)
+            // (c) warp-cooperative suppression scan, 32 rows at a time: the 32x32 diagonal block is
+            // resolved in registers (shuffle-broadcast rows, warp-uniform ALU chain); the kept rows' mask
+            // words are then OR-ed into the later removed-words by all 32 lanes (4 row subsets x 8 words).
+            // Stops as soon as the image's max_det boxes are found: later rows are simply dropped.
             if (warp == 0) {
                 u32 rw = lane < LZ_CHUNK / 32 ? S.removed[lane] : 0u;
                 const int groups = (m + 31) >> 5;
+                const int sub = lane >> 3, wl = lane & 7;
+                int room = P.max_det - kept;
+#pragma unroll 1
                 for (int g = 0; g < groups; ++g) {
+                    if (room <= 0) {                               // the cut is behind us: drop the rest
+                        if (lane >= g && lane < LZ_CHUNK / 32) rw = 0xffffffffu;
+                        break;
+                    }
                     const int row = g * 32 + lane;
                     const u32 diag = row < m ? S.mask[row][g] : 0u;
                     u32 rg = __shfl_sync(0xffffffffu, rw, g);
@@ -691,12 +703,13 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                     }
                     const int nrows = min(32, m - g * 32);
                     const u32 keptm = ~rg & (nrows == 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+                    room -= __popc(keptm);
                     if (lane == g) rw = rg;
-                    if (lane > g && lane < LZ_CHUNK / 32) {
-                        u32 acc = 0;
-                        for (u32 km = keptm; km; km &= km - 1) acc |= S.mask[g * 32 + __ffs(km) - 1][lane];
-                        rw |= acc;
-                    }
+                    u32 acc = 0;
+                    for (u32 km = keptm & (0x11111111u << sub); km; km &= km - 1) acc |= S.mask[g * 32 + __ffs(km) - 1][wl];
+                    acc |= __shfl_xor_sync(0xffffffffu, acc, 8);
+                    acc |= __shfl_xor_sync(0xffffffffu, acc, 16);
+                    if (lane > g && lane < LZ_CHUNK / 32) rw |= acc;
                 }
                 if (lane < LZ_CHUNK / 32) S.removed[lane] = rw;
             }
