@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
 #pragma unroll 1
     for (int round = 0; round < LZ_ROUNDS && processed < K && kept < P.max_det; ++round) {
         const int remaining = K - processed;
-        const int cap_r = round == 0 ? LZ_CHUNK : LZ_M;      // first round: one chunk is usually enough
+        const int cap_r = LZ_M;
         const int take = min(remaining, cap_r);
         // ---- threshold key T: the take-th smallest key among keys > last (radix select) ----
         u64 T = ~0ULL;
