@@ -95,7 +95,8 @@ class PackedTargets:
                     self.labels = torch.zeros((1,), dtype=torch.int64, device=device)
             else:
                 self.labels = None
-            self.offsets = torch.tensor(offs, dtype=torch.int32).pin_memory().to(device, non_blocking=True)
+            off = torch.tensor(offs, dtype=torch.int32)
+            self.offsets = off.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else off
 
 
 def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_anchors: int,

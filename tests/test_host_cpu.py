@@ -1,0 +1,136 @@
+"""CPU tests (-m "not gpu") of the host-side logic: C-ABI symbol coverage, argument checking that
+needs no GPU, packing of ragged targets, the integration swap, and the 2-rank (gloo) logic of the
+image-sharded loss with the CUDA kernel replaced by the oracle."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from pytorch_retinanet_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "retinanet_b200.h")).read()
+    declared = set(re.findall(r"\b(rn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    lib = _native.load()                                   # loads without a GPU
+    raw = ctypes.CDLL(_native.lib_path())
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert lib.rn_abi_version() == 1
+    # argument errors are reported through return codes + rn_last_error (no GPU touched)
+    assert lib.rn_match(None, 10, 0, None, None, None, 1, 0.5, 0.4, None, None, None, None) == -1
+    assert b"null" in lib.rn_last_error()
+    assert lib.rn_postprocess_workspace_bytes(16, 201600, 80, 1 << 20, 100) > (1 << 20) * 8
+    assert lib.rn_loss_workspace_bytes(16, 201600, 80) == 16 * 788 * 16
+
+
+def test_no_cpu_fallback_and_loud_failure():
+    import pytorch_retinanet_b200 as P
+    from pytorch_retinanet_b200 import _native
+    a = torch.rand(8, 4)
+    with pytest.raises(_native.NativeError):
+        P.matcher(a, a[:2])
+    with pytest.raises(_native.NativeError):
+        P.AnchorGenerator().grid_anchors([(4, 4)] * 5, torch.device("cpu"))
+    with pytest.raises(AssertionError):
+        P.matcher(a, a[:2], match_thr=0.3, back_thr=0.4)   # box_utils.py:66
+    src = "".join(open(os.path.join(ROOT, "pytorch_retinanet_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "pytorch_retinanet_b200")) if f.endswith(".py"))
+    assert "oracle" not in src                              # the product never imports the oracle
+
+
+def test_packed_targets_and_anchor_generator_host_side():
+    from pytorch_retinanet_b200.box_utils import PackedTargets
+    from pytorch_retinanet_b200 import AnchorGenerator
+    from oracle import torch_oracle as O
+    dev = torch.device("cpu")
+    boxes = [torch.rand(3, 4), torch.zeros(0, 4), torch.rand(5, 4).double()]
+    labels = [torch.tensor([1, 2, 3]), torch.zeros(0, dtype=torch.int64), torch.tensor([4, 5, 6, 7, 8], dtype=torch.int32)]
+    p = PackedTargets(boxes, labels, dev)
+    assert p.offsets.tolist() == [0, 3, 3, 8] and p.boxes.shape == (8, 4) and p.boxes.dtype == torch.float32
+    assert p.labels.dtype == torch.int64 and p.labels.tolist() == [1, 2, 3, 4, 5, 6, 7, 8]
+    g = AnchorGenerator()
+    assert g.num_anchors == [9] * 5 and list(g.state_dict().keys()) == [f"cell_anchors.{i}" for i in range(5)]
+    for i, c in enumerate(g.cell_anchors):
+        assert torch.equal(c, O.cell_anchor_table(O.SIZES[i], O.RATIOS))
+    with pytest.raises(AssertionError):
+        AnchorGenerator(sizes=[[32.0], [64.0]], strides=[8, 16, 32])
+
+
+def test_patch_retinanet_on_the_real_reference():
+    from oracle.ref_shim import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    ref = load_reference()
+    import pytorch_retinanet_b200 as P
+    model = ref.Retinanet(num_classes=7, backbone_kind="resnet18", pretrained=False)
+    keys_before = list(model.state_dict().keys())
+    cells_before = [c.clone() for c in model.anchor_generator.cell_anchors]
+    P.patch_retinanet(model)
+    assert isinstance(model.anchor_generator, P.AnchorGenerator)
+    assert isinstance(model.retinanet_head.losses, P.RetinaNetLosses) and model.retinanet_head.losses.n_c == 7
+    assert model.process_detections.__func__ is P.process_detections
+    assert list(model.state_dict().keys()) == keys_before
+    assert all(torch.equal(a, b) for a, b in zip(model.anchor_generator.cell_anchors, cells_before))
+
+
+# ---- 2-rank gloo test of the sharded loss: the CUDA call is replaced by the oracle -------------------
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth_data as S
+    from oracle import torch_oracle as O
+    import pytorch_retinanet_b200.distributed as D
+
+    class FakeFused:                                         # same contract as _FusedRetinaNetLoss.apply
+        @staticmethod
+        def apply(cls, box, anchors, stride, packed, hp):
+            rows = []
+            off = packed.offsets.tolist()
+            for i in range(cls.shape[0]):
+                gt, lab = packed.boxes[off[i]:off[i + 1]], packed.labels[off[i]:off[i + 1]]
+                r, c, _, f = O.image_loss(anchors, cls[i], box[i], lab, gt if off[i + 1] > off[i] else gt[:0], cls.shape[-1])
+                rows.append(torch.stack([c, r, f.float()]))
+            image = torch.stack(rows)
+            return image[:, 0].sum() / hp["batch_div"], image[:, 1].sum() / hp["batch_div"], image.detach()
+
+    D._FusedRetinaNetLoss = FakeFused
+    cfg = S.CONFIGS[1]
+    n_total = 5                                              # uneven shards: 2 + 3
+    b = S.make_batch(cfg, 0, n_total, clustered=True)
+    b["targets"][1] = {"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)}
+    lo, hi = D.shard_range(n_total, rank, world)
+    L = D.ShardedRetinaNetLosses(cfg.num_classes)           # global batch discovered by all-reduce
+    x = b["cls_preds"][lo:hi].clone().requires_grad_(True)
+    out = L(b["targets"][lo:hi], {"cls_preds": x, "bbox_preds": b["bbox_preds"][lo:hi]}, [b["anchors"]] * (hi - lo))
+    (out["classification_loss"] + out["regression_loss"]).backward()
+    full = O.batch_loss(b["targets"], b["cls_preds"], b["bbox_preds"], [b["anchors"]] * n_total, cfg.num_classes)
+    xf = b["cls_preds"].clone().requires_grad_(True)
+    ff = O.batch_loss(b["targets"], xf, b["bbox_preds"], [b["anchors"]] * n_total, cfg.num_classes)
+    (ff["classification_loss"] + ff["regression_loss"]).backward()
+    ok = (abs(float(out["classification_loss"]) - float(full["classification_loss"])) <= 1e-5 * float(full["classification_loss"])
+          and abs(float(out["regression_loss"]) - float(full["regression_loss"])) <= 1e-5 * float(full["regression_loss"])
+          and torch.allclose(x.grad, xf.grad[lo:hi], rtol=1e-5, atol=1e-12)
+          and int(L.last_stats[3]) == n_total)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_loss_two_ranks_gloo():
+    from pytorch_retinanet_b200.distributed import shard_range
+    assert [shard_range(5, r, 2) for r in range(2)] == [(0, 2), (2, 5)]
+    assert [shard_range(128, r, 8) for r in range(8)] == [(16 * r, 16 * r + 16) for r in range(8)]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}
