@@ -85,7 +85,8 @@ int rn_decode(const float *activations, const float *anchors, int64_t n, const f
  * both divided by max(1, F_n) per image, then averaged over `batch_div` images (losses.py:108-109,
  * 138-140).
  *   out_image [N,3]  = {cls_n / max(1,F_n), reg_n / max(1,F_n), F_n}   (fp32)
- *   out_total [2]    = {sum_n cls_n/max(1,F_n), sum_n reg_n/max(1,F_n)} / batch_div
+ *   out_total [4]    = {sum_n cls_n/max(1,F_n) / batch_div, sum_n reg_n/max(1,F_n) / batch_div, sum_n F_n, N}
+ *                      (the 16-byte vector that image-sharded multi-GPU runs all-reduce)
  *   grad_logits / grad_bbox (optional, both or neither): d out_total[0] / d logits and
  *   d out_total[1] / d bbox_preds, written for EVERY element (zeros where no gradient flows).
  * Reductions are two-stage and order-fixed, so results are bit-reproducible run to run.
@@ -95,7 +96,7 @@ int rn_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, cons
             int64_t anchor_image_stride, const float *gt_boxes /*[sumG,4]*/, const int32_t *gt_off /*[N+1]*/, const int32_t *codes /*[N,A]*/,
             const int32_t *fg_count /*[N]*/, int N, int64_t A, int C, float alpha, float gamma, float beta,
             const float *weights_host /*[4]*/, float batch_div, float *out_image /*[N,3]*/,
-            float *out_total /*[2]*/, float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/,
+            float *out_total /*[4]*/, float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/,
             void *workspace, size_t workspace_bytes, rn_stream_t stream);
 
 /* In-place scale of a gradient buffer by a DEVICE scalar (autograd's grad_output); every block

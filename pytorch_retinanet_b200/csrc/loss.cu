@@ -309,9 +309,12 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const double *__res
     __syncthreads();
     if (threadIdx.x == 0) {
         double c = 0.0, r = 0.0;
-        for (int n = 0; n < N; ++n) { c += s_img[2 * n]; r += s_img[2 * n + 1]; }
+        long long fsum = 0;
+        for (int n = 0; n < N; ++n) { c += s_img[2 * n]; r += s_img[2 * n + 1]; fsum += fg_count[n]; }
         out_total[0] = (float)(c / (double)batch_div);      // losses.py:138-140
         out_total[1] = (float)(r / (double)batch_div);
+        out_total[2] = (float)fsum;                         // sum_n F_n   } carried for the image-sharded
+        out_total[3] = (float)N;                            // local images } all-reduce
     }
 }
 

@@ -47,14 +47,10 @@ class ShardedRetinaNetLosses(RetinaNetLosses):
                 n_global = n_local
         an, stride = _shared_anchors(anchors)
         packed = PackedTargets([t["boxes"] for t in targets], [t["labels"] for t in targets], cls.device)
-        c, r, image = _FusedRetinaNetLoss.apply(cls, box, an, stride, packed, self._hp(n_global))
+        hp = self._hp(n_global)
+        if world > 1:
+            hp["all_reduce_group"] = self.group                # the all-reduce happens inside the autograd function
+        c, r, image, total = _FusedRetinaNetLoss.apply(cls, box, an, stride, packed, hp)
         self.last_per_image = image
-        if world == 1:
-            self.last_stats = None
-            return {"classification_loss": c, "regression_loss": r}
-        stats = torch.stack([c.detach(), r.detach(), image[:, 2].sum(), image.new_tensor(float(n_local))])
-        dist.all_reduce(stats, group=self.group)              # the ONE collective of the path (16 bytes)
-        self.last_stats = stats                                # [cls, reg, sum F, N] of the global batch
-        # value = global loss; gradient flows only through the local shard (already / N_global)
-        return {"classification_loss": c + (stats[0] - c.detach()),
-                "regression_loss": r + (stats[1] - r.detach())}
+        self.last_stats = total                                # [cls, reg, sum F, N] of the GLOBAL batch (device tensor)
+        return {"classification_loss": c, "regression_loss": r}

@@ -36,7 +36,7 @@ def _shared_anchors(anchors: Sequence[Tensor]) -> Tuple[Tensor, int]:
 def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
                        packed: PackedTargets, alpha: float, gamma: float, beta: float, match_thr: float,
                        back_thr: float, batch_div: float, want_grad: bool):
-    """Launches rn_match + rn_loss.  Returns (out_total [2], out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
+    """Launches rn_match + rn_loss.  Returns (out_total [4], out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
     lib = _native.load()
     dev = cls_preds.device
     N, A, C = cls_preds.shape
@@ -49,7 +49,7 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
     x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
     b = b if (b.dtype == torch.float32 and b.is_contiguous()) else b.to(torch.float32).contiguous()
     _, codes, fg = match_batch(anchors, anchor_stride, packed, A, match_thr, back_thr, False, True)
-    out_total = torch.empty((2,), dtype=torch.float32, device=dev)
+    out_total = torch.empty((4,), dtype=torch.float32, device=dev)
     out_image = torch.empty((N, 3), dtype=torch.float32, device=dev)
     gl = torch.empty_like(x) if want_grad else None
     gb = torch.empty_like(b) if want_grad else None
@@ -73,13 +73,19 @@ class _FusedRetinaNetLoss(torch.autograd.Function):
         total, image, gl, gb, _ = fused_loss_forward(cls_preds, bbox_preds, anchors, anchor_stride, packed,
                                                      hp["alpha"], hp["gamma"], hp["beta"], hp["match_thr"],
                                                      hp["back_thr"], hp["batch_div"], want)
+        group = hp.get("all_reduce_group", False)
+        if group is not False:
+            # image-sharded batch: the ONE collective of the path — 16 bytes over NCCL/NVLink.  The local
+            # gradients are already scaled by 1/N_global, so backward needs no communication.
+            import torch.distributed as dist
+            dist.all_reduce(total, group=group)
         ctx.grads = (gl, gb)
         ctx.in_dtypes = (cls_preds.dtype, bbox_preds.dtype)
-        ctx.mark_non_differentiable(image)
-        return total[0], total[1], image
+        ctx.mark_non_differentiable(image, total)
+        return total[0], total[1], image, total
 
     @staticmethod
-    def backward(ctx, g_cls, g_reg, _g_image):
+    def backward(ctx, g_cls, g_reg, _g_image, _g_total):
         gl, gb = ctx.grads
         ctx.grads = (None, None)
         if gl is None:
@@ -121,7 +127,7 @@ class RetinaNetLosses(nn.Module):
             raise ValueError(f"clas_pred has {clas_pred.shape[-1]} classes, expected {self.n_c}")
         an = anchors.detach().to(torch.float32).contiguous()
         packed = PackedTargets([bbox_tgt], [clas_tgt], clas_pred.device)
-        c, r, _ = _FusedRetinaNetLoss.apply(clas_pred[None], bbox_pred[None], an, 0, packed, self._hp(1.0))
+        c, r, _, _ = _FusedRetinaNetLoss.apply(clas_pred[None], bbox_pred[None], an, 0, packed, self._hp(1.0))
         return r, c
 
     def forward(self, targets: List[Dict[str, Tensor]], head_outputs: Dict[str, Tensor],
@@ -131,6 +137,6 @@ class RetinaNetLosses(nn.Module):
             raise ValueError(f"cls_preds has {clas_preds.shape[-1]} classes, expected {self.n_c}")
         an, stride = _shared_anchors(anchors)
         packed = PackedTargets([t["boxes"] for t in targets], [t["labels"] for t in targets], clas_preds.device)
-        c, r, image = _FusedRetinaNetLoss.apply(clas_preds, bbox_preds, an, stride, packed, self._hp(len(targets)))
+        c, r, image, _ = _FusedRetinaNetLoss.apply(clas_preds, bbox_preds, an, stride, packed, self._hp(len(targets)))
         self.last_per_image = image   # [N,3]: cls_i, reg_i, F_i (device tensor, no sync)
         return {"classification_loss": c, "regression_loss": r}

@@ -101,7 +101,12 @@ def _worker(rank, world, port, ret):
                 r, c, _, f = O.image_loss(anchors, cls[i], box[i], lab, gt if off[i + 1] > off[i] else gt[:0], cls.shape[-1])
                 rows.append(torch.stack([c, r, f.float()]))
             image = torch.stack(rows)
-            return image[:, 0].sum() / hp["batch_div"], image[:, 1].sum() / hp["batch_div"], image.detach()
+            c, r = image[:, 0].sum() / hp["batch_div"], image[:, 1].sum() / hp["batch_div"]
+            total = torch.stack([c.detach(), r.detach(), image[:, 2].sum().detach(), torch.tensor(float(cls.shape[0]))])
+            if hp.get("all_reduce_group", False) is not False:
+                dist.all_reduce(total, group=hp["all_reduce_group"])
+            # value of the global batch, gradient of the local shard (what the CUDA autograd function does)
+            return c + (total[0] - c.detach()), r + (total[1] - r.detach()), image.detach(), total
 
     D._FusedRetinaNetLoss = FakeFused
     cfg = S.CONFIGS[1]
