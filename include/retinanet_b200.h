@@ -63,7 +63,7 @@ int rn_anchor_grid(const float *cells, const int32_t *level_desc_host /*[L][4]*/
  * Optional outputs (may be NULL):
  *   codes   [N,A] int32 — packed per-anchor target used by rn_loss: -2 / -1 / (g | (label-1) << 20)
  *                         (requires gt_labels; G per image < 2^20, classes < 2^11)
- *   fg_count[N]   int32 — number of foreground anchors per image (must be zeroed by the caller). */
+ *   fg_count[N]   int32 — number of foreground anchors per image (zeroed by the call itself).       */
 int rn_match(const float *anchors /*[A,4] or [N,A,4]*/, int64_t A, int64_t anchor_image_stride,
              const float *gt_boxes /*[sumG,4]*/,
              const int64_t *gt_labels /*[sumG] or NULL*/, const int32_t *gt_off /*[N+1]*/, int N,
@@ -98,6 +98,17 @@ int rn_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, cons
             const float *weights_host /*[4]*/, float batch_div, float *out_image /*[N,3]*/,
             float *out_total /*[4]*/, float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/,
             void *workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* Dense element-wise losses, API parity with RetinaNetLosses.focal_loss (losses.py:29-47, arbitrary
+ * float targets of the logits' shape, NO +1 shift) and RetinaNetLosses.smooth_l1_loss (losses.py:19-27).
+ * out_sum [1] = sum over the n elements; grad (optional, [n]) = d out_sum / d input.
+ * workspace: rn_dense_loss_workspace_bytes().                                                      */
+size_t rn_dense_loss_workspace_bytes(void);
+int rn_focal_loss_dense(const float *logits, const float *targets, int64_t n, float alpha, float gamma,
+                        float *out_sum, float *grad /*[n] or NULL*/, void *workspace, size_t workspace_bytes,
+                        rn_stream_t stream);
+int rn_smooth_l1_dense(const float *input, const float *target, int64_t n, float beta, float *out_sum,
+                       float *grad /*[n] or NULL*/, void *workspace, size_t workspace_bytes, rn_stream_t stream);
 
 /* In-place scale of a gradient buffer by a DEVICE scalar (autograd's grad_output); every block
  * returns immediately when *scale == 1.0f, so the common case costs one launch and no traffic.    */

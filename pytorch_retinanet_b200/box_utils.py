@@ -108,7 +108,7 @@ def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_
     N, A = packed.num_images, num_anchors
     matches = torch.empty((N, A), dtype=torch.int64, device=dev) if want_matches else None
     codes = torch.empty((N, A), dtype=torch.int32, device=dev) if want_codes else None
-    fg = torch.zeros((N,), dtype=torch.int32, device=dev) if want_codes else None
+    fg = torch.empty((N,), dtype=torch.int32, device=dev) if want_codes else None   # zeroed by rn_match
     with torch.cuda.device(dev):
         rc = lib.rn_match(_native.ptr(anchors, torch.float32, "anchors"), A, anchor_stride,
                           _native.ptr(packed.boxes, torch.float32, "target boxes"),

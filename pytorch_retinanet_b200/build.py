@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "librn_b200.so")
+LIB_PATH = os.path.join(LIB_DIR, "librn_b200%s.so" % os.environ.get("RN_LIB_SUFFIX", "_dbg" if os.environ.get("RN_LAZY_TIMING") else ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH] + sources()
+    extra = (["-DRN_LAZY_TIMING=1"] if os.environ.get("RN_LAZY_TIMING") else []) + os.environ.get("RN_EXTRA_DEFS", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(LIB_DIR, "build.log")
     with open(log, "w") as f:

@@ -22,6 +22,8 @@
 // PRECISE uses expf/log1pf/IEEE division (test reference for the approximation error).
 // Reductions: fp32 per thread (<= a few hundred terms), fp64 from the warp level on, per-CTA
 // partials to the workspace and a fixed-order final kernel => bit-reproducible.
+#include <algorithm>
+
 #include "rn_common.cuh"
 
 namespace {
@@ -406,6 +408,96 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
                                               out_total);
     RN_CHECK_LAUNCH("rn_loss_finalize");
     return 0;
+}
+
+// ---- dense element-wise losses (API parity with RetinaNetLosses.focal_loss / smooth_l1_loss) ----------
+// focal_loss(clas_pred, clas_tgt), retinanet/losses.py:29-47, for arbitrary float targets:
+//   p = sigmoid(x) (detached); w = (t(1-p) + (1-t)p)^gamma * ((1-t)alpha + t(1-alpha));
+//   loss = sum w * ((1-t) x - log_sigmoid(x));  dloss/dx = w * (p - t)
+// smooth_l1_loss(input, target), retinanet/losses.py:19-27.
+// HBM-bound streaming reductions: grid-stride 128-bit loads, per-CTA fp64 partials, one-block finish.
+namespace {
+constexpr int DENSE_BLOCK = 256;
+constexpr int DENSE_GRID = RN_SM_COUNT_B200 * 8;
+
+template <bool FOCAL>
+__global__ void __launch_bounds__(DENSE_BLOCK) dense_loss_kernel(const float *__restrict__ x, const float *__restrict__ t,
+                                                                 long long n, float p0, float p1, float *__restrict__ grad,
+                                                                 double *__restrict__ partials) {
+    float acc = 0.0f;
+    const long long stride = (long long)gridDim.x * DENSE_BLOCK;
+    for (long long i = (long long)blockIdx.x * DENSE_BLOCK + threadIdx.x; i < n; i += stride) {
+        const float xv = __ldg(x + i), tv = __ldg(t + i);
+        float l, g;
+        if (FOCAL) {
+            const float alpha = p0, gamma = p1;
+            const float e = expf(-fabsf(xv));
+            const float r = __fdiv_rn(1.0f, 1.0f + e);
+            const float p = xv >= 0.0f ? r : e * r;
+            float w = tv * (1.0f - p) + (1.0f - tv) * p;
+            w = (gamma == 2.0f ? w * w : (w > 0.0f ? powf(w, gamma) : (gamma == 0.0f ? 1.0f : 0.0f)));
+            w *= (1.0f - tv) * alpha + tv * (1.0f - alpha);
+            const float logsig = fminf(xv, 0.0f) - log1pf(e);
+            l = w * ((1.0f - tv) * xv - logsig);
+            g = w * (p - tv);
+        } else {
+            const float beta = p0;
+            const float d = xv - tv, a = fabsf(d);
+            if (beta < 1e-5f) { l = a; g = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f); }
+            else if (a < beta) { l = 0.5f * a * a / beta; g = d / beta; }
+            else { l = a - 0.5f * beta; g = d > 0.0f ? 1.0f : -1.0f; }
+        }
+        acc += l;
+        if (grad) grad[i] = g;
+    }
+    double a = acc, b = 0.0, c = 0.0;
+    block_sum3(a, b, c);
+    if (threadIdx.x == 0) partials[blockIdx.x] = a;
+}
+
+__global__ void __launch_bounds__(256) dense_finish_kernel(const double *__restrict__ partials, int n, float *__restrict__ out) {
+    __shared__ double s[8];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) a += partials[i];
+    a = rn::warp_sum(a);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int i = 0; i < 8; ++i) r += s[i];
+        out[0] = (float)r;
+    }
+}
+
+int dense_launch(bool focal, const float *x, const float *t, int64_t n, float p0, float p1, float *out, float *grad,
+                 void *workspace, size_t workspace_bytes, rn_stream_t stream, const char *name) {
+    RN_CHECK_ARG(n >= 0 && out, RN_E_BADARG, "%s: bad argument", name);
+    RN_CHECK_ARG(n == 0 || (x && t), RN_E_BADARG, "%s: null input", name);
+    RN_CHECK_ARG(workspace && workspace_bytes >= DENSE_GRID * sizeof(double), RN_E_WORKSPACE, "%s: workspace too small", name);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(DENSE_GRID, (n + DENSE_BLOCK - 1) / DENSE_BLOCK));
+    if (focal) dense_loss_kernel<true><<<grid, DENSE_BLOCK, 0, s>>>(x, t, n, p0, p1, grad, (double *)workspace);
+    else dense_loss_kernel<false><<<grid, DENSE_BLOCK, 0, s>>>(x, t, n, p0, p1, grad, (double *)workspace);
+    RN_CHECK_LAUNCH(name);
+    dense_finish_kernel<<<1, 256, 0, s>>>((const double *)workspace, grid, out);
+    RN_CHECK_LAUNCH(name);
+    return 0;
+}
+}  // namespace
+
+extern "C" size_t rn_dense_loss_workspace_bytes(void) { return DENSE_GRID * sizeof(double); }
+
+extern "C" int rn_focal_loss_dense(const float *logits, const float *targets, int64_t n, float alpha, float gamma,
+                                   float *out_sum, float *grad, void *workspace, size_t workspace_bytes,
+                                   rn_stream_t stream) {
+    return dense_launch(true, logits, targets, n, alpha, gamma, out_sum, grad, workspace, workspace_bytes, stream,
+                        "rn_focal_loss_dense");
+}
+
+extern "C" int rn_smooth_l1_dense(const float *input, const float *target, int64_t n, float beta, float *out_sum,
+                                  float *grad, void *workspace, size_t workspace_bytes, rn_stream_t stream) {
+    return dense_launch(false, input, target, n, beta, 0.0f, out_sum, grad, workspace, workspace_bytes, stream,
+                        "rn_smooth_l1_dense");
 }
 
 extern "C" int rn_scale_by_device_scalar(float *buf, int64_t n, const float *scale, rn_stream_t stream) {

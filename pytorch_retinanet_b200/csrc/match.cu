@@ -178,8 +178,12 @@ extern "C" int rn_match(const float *anchors, int64_t A, int64_t anchor_image_st
     RN_CHECK_ARG(!codes || gt_labels, RN_E_BADARG, "rn_match: codes requested without gt_labels");
     RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_match: N=%d exceeds 65535 images per call", N);
     if (A == 0 || N == 0) return 0;
-    dim3 grid((unsigned)((A + MATCH_BLOCK - 1) / MATCH_BLOCK), (unsigned)N);
     cudaStream_t s = (cudaStream_t)stream;
+    if (fg_count) {   // the per-image counters are accumulated with integer atomics: start from zero
+        cudaError_t e = cudaMemsetAsync(fg_count, 0, (size_t)N * sizeof(int32_t), s);
+        if (e != cudaSuccess) { rn_set_error("rn_match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    dim3 grid((unsigned)((A + MATCH_BLOCK - 1) / MATCH_BLOCK), (unsigned)N);
     const bool fast = bg_thr > 0.0f;  // then fg_thr > bg_thr > 0: culling and pruning are exact
     if (fast) {
         // inter < uni*bg*(1-2^-20)  =>  fl(inter/uni) < bg   (rounding slack is 2^-23 per op)

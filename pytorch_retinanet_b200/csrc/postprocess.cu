@@ -425,31 +425,36 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
             s_mask[t][w] = bits;
         }
         __syncthreads();
-        // (c) warp-cooperative suppression scan.  Lane w (< 8) owns removed-word w.  The chunk is
-        // resolved 32 rows at a time: the 32x32 diagonal block is resolved serially in registers
-        // (shuffle-broadcast rows, warp-uniform ALU chain), then the kept rows' mask words are OR-ed
-        // into the later removed-words, 8 lanes wide.
+        // (c) warp-cooperative suppression scan (parallel form of the greedy scan, see lazy_nms_kernel):
+        // per 32-row group, K <- alive & no kept j<i with M[j][i], iterated to the fixed point with one
+        // warp-wide OR reduction (REDUX) per sweep; kept rows are OR-reduced into the later words.
         if (warp == 0) {
             u32 rw = lane < NMS_CHUNK / 32 ? s_removed[lane] : 0u;
             const int groups = (m + 31) >> 5;
+#pragma unroll 1
             for (int g = 0; g < groups; ++g) {
                 const int row = g * 32 + lane;
-                const u32 diag = row < m ? s_mask[row][g] : 0u;
-                u32 rg = __shfl_sync(0xffffffffu, rw, g);          // removed bits of this group (uniform)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const u32 di = __shfl_sync(0xffffffffu, diag, i);
-                    rg |= ((rg >> i) & 1u) ? 0u : di;
+                const u32 rem0 = __shfl_sync(0xffffffffu, rw, g);
+                const bool valid = row < m && !((rem0 >> lane) & 1u);
+                const u32 diag = valid ? s_mask[row][g] : 0u;
+                bool kp = valid;
+#pragma unroll 1
+                for (int sweep = 0; sweep < 32; ++sweep) {
+                    const u32 rem = __reduce_or_sync(0xffffffffu, kp ? diag : 0u);
+                    const bool nk = valid && !((rem >> lane) & 1u);
+                    const bool changed = nk != kp;
+                    kp = nk;
+                    if (!__any_sync(0xffffffffu, changed)) break;
                 }
-                const int nrows = min(32, m - g * 32);
-                u32 keptm = ~rg & (nrows == 32 ? 0xffffffffu : ((1u << nrows) - 1u));
-                if (lane == g) rw = rg;
-                u32 acc = 0;                                       // 4 row subsets x 8 words, all 32 lanes
-                for (u32 km = keptm & (0x11111111u << (lane >> 3)); km; km &= km - 1)
-                    acc |= s_mask[g * 32 + __ffs(km) - 1][lane & 7];
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 8);
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 16);
-                if (lane > g && lane < NMS_CHUNK / 32) rw |= acc;
+                const u32 keptm = __ballot_sync(0xffffffffu, kp);
+                if (lane == g) rw = ~keptm;
+#pragma unroll
+                for (int w = 0; w < NMS_CHUNK / 32; ++w) {
+                    if (w > g) {
+                        const u32 acc = __reduce_or_sync(0xffffffffu, kp ? s_mask[row][w] : 0u);
+                        if (lane == w) rw |= acc;
+                    }
+                }
             }
             if (lane < NMS_CHUNK / 32) s_removed[lane] = rw;
         }
@@ -524,6 +529,13 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     u64 *s_cand = reinterpret_cast<u64 *>(lz_raw + ((sizeof(LazySmem) + 15) & ~(size_t)15));
 
     const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#ifdef RN_LAZY_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    int n_rounds = 0, n_chunks = 0;
+#define LZ_TICK(id) do { if (t == 0) { long long now_ = clock64(); tacc[id] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define LZ_TICK(id) do { } while (0)
+#endif
     const u32 found = P.img_count[n];
     if (t == 0) {
         const unsigned long long scaled = (unsigned long long)found * (unsigned long long)P.N;
@@ -542,6 +554,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     }
     __syncthreads();
     const u64 *cand = cached ? s_cand : g_cand;
+    LZ_TICK(0);
     const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
     const long long img_row = (long long)n * P.A, anc_row = (long long)n * P.anchor_stride;
     const u32 A32 = (u32)P.A;
@@ -611,6 +624,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
             }
             T = S.thr_key;
         }
+        LZ_TICK(1);
         // ---- gather + sort the selected keys ----
         if (t == 0) S.nsel = 0;
         __syncthreads();
@@ -628,7 +642,9 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
         }
         __syncthreads();
         const int nsel = min(S.nsel, LZ_M);
+        LZ_TICK(2);
         block_bitonic_sort(S.sel, nsel);
+        LZ_TICK(3);
 
         // ---- greedy class-aware NMS over the sorted keys, LZ_CHUNK at a time ----
 #pragma unroll 1
@@ -659,6 +675,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                 if (lane == 0) S.removed[warp] = dead;
             }
             __syncthreads();
+            LZ_TICK(4);
             // (b) bitmask: 256 rows x 8 words = 2048 (row, word) tasks, two per thread, word uniform per warp
 #pragma unroll 1
             for (int q = 0; q < 2; ++q) {
@@ -678,14 +695,19 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                 S.mask[row][w] = bits;
             }
             __syncthreads();
+            LZ_TICK(5);
             // (c) warp-cooperative suppression scan, 32 rows at a time: the 32x32 diagonal block is
             // resolved in registers (shuffle-broadcast rows, warp-uniform ALU chain); the kept rows' mask
             // words are then OR-ed into the later removed-words by all 32 lanes (4 row subsets x 8 words).
             // Stops as soon as the image's max_det boxes are found: later rows are simply dropped.
             if (warp == 0) {
+                // Parallel form of the greedy scan.  Within a 32-row group, K[i] = alive[i] & no kept j<i with
+                // M[j][i]; iterating K <- f(K) from K = alive converges to the greedy answer (row i is final
+                // after at most i sweeps; chains are short in practice).  Each sweep is one warp-wide OR
+                // reduction (REDUX) of the kept rows' diagonal words; the kept rows are then OR-reduced into
+                // the later removed-words the same way.  No serial 32-step chain, no divergent loops.
                 u32 rw = lane < LZ_CHUNK / 32 ? S.removed[lane] : 0u;
                 const int groups = (m + 31) >> 5;
-                const int sub = lane >> 3, wl = lane & 7;
                 int room = P.max_det - kept;
 #pragma unroll 1
                 for (int g = 0; g < groups; ++g) {
@@ -694,26 +716,33 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                         break;
                     }
                     const int row = g * 32 + lane;
-                    const u32 diag = row < m ? S.mask[row][g] : 0u;
-                    u32 rg = __shfl_sync(0xffffffffu, rw, g);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const u32 di = __shfl_sync(0xffffffffu, diag, i);
-                        rg |= ((rg >> i) & 1u) ? 0u : di;
+                    const u32 rem0 = __shfl_sync(0xffffffffu, rw, g);           // removed by earlier groups / dead
+                    const bool valid = row < m && !((rem0 >> lane) & 1u);
+                    const u32 diag = valid ? S.mask[row][g] : 0u;
+                    bool kp = valid;
+#pragma unroll 1
+                    for (int sweep = 0; sweep < 32; ++sweep) {
+                        const u32 rem = __reduce_or_sync(0xffffffffu, kp ? diag : 0u);
+                        const bool nk = valid && !((rem >> lane) & 1u);
+                        const bool changed = nk != kp;
+                        kp = nk;
+                        if (!__any_sync(0xffffffffu, changed)) break;
                     }
-                    const int nrows = min(32, m - g * 32);
-                    const u32 keptm = ~rg & (nrows == 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+                    const u32 keptm = __ballot_sync(0xffffffffu, kp);
                     room -= __popc(keptm);
-                    if (lane == g) rw = rg;
-                    u32 acc = 0;
-                    for (u32 km = keptm & (0x11111111u << sub); km; km &= km - 1) acc |= S.mask[g * 32 + __ffs(km) - 1][wl];
-                    acc |= __shfl_xor_sync(0xffffffffu, acc, 8);
-                    acc |= __shfl_xor_sync(0xffffffffu, acc, 16);
-                    if (lane > g && lane < LZ_CHUNK / 32) rw |= acc;
+                    if (lane == g) rw = ~keptm;                    // everything not kept in this group counts as removed
+#pragma unroll
+                    for (int w = 0; w < LZ_CHUNK / 32; ++w) {
+                        if (w > g) {                               // warp-uniform
+                            const u32 acc = __reduce_or_sync(0xffffffffu, kp ? S.mask[row][w] : 0u);
+                            if (lane == w) rw |= acc;
+                        }
+                    }
                 }
                 if (lane < LZ_CHUNK / 32) S.removed[lane] = rw;
             }
             __syncthreads();
+            LZ_TICK(6);
             // (d) append the kept boxes, in order, to the image's output list (first max_det only)
             if (t < LZ_CHUNK) {
                 const bool kp = t < m && !((S.removed[warp] >> lane) & 1u);
@@ -739,9 +768,16 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
             }
             kept = min(P.max_det, kept + S.wbase[LZ_CHUNK / 32]);
             __syncthreads();
+            LZ_TICK(7);
+#ifdef RN_LAZY_TIMING
+            ++n_chunks;
+#endif
         }
         processed += nsel;
         last = T;
+#ifdef RN_LAZY_TIMING
+        ++n_rounds;
+#endif
     }
     if (kept < P.max_det && processed < K && t == 0) atomicOr(P.status + 2, 1);   // general algorithm needed
     for (int i = t; i < kept; i += LZ_BLOCK) {
@@ -751,6 +787,12 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
         P.out_labels[o] = (long long)S.kcls[i] + 1;            // models.py:230 labels + 1
     }
     if (t == 0) P.out_count[n] = kept;
+#ifdef RN_LAZY_TIMING
+    if (t == 0)
+        printf("lazy img %d K %d rounds %d chunks %d kept %d | load %lld radix %lld gather %lld sort %lld decode+a %lld mask %lld resolve %lld append %lld\n",
+               n, K, n_rounds, n_chunks, kept, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
+#endif
+#undef LZ_TICK
 }
 
 __global__ void set_status_capacity_kernel(int *status, int capacity) { status[1] = capacity; }

@@ -21,6 +21,18 @@ from .box_utils import _REG_WEIGHTS_C
 from .losses import _shared_anchors
 
 _HW_CACHE: Dict[Tuple, Tensor] = {}
+_WS_CACHE: Dict[Tuple, Tensor] = {}
+
+
+def _workspace(nbytes: int, dev) -> Tensor:
+    """Scratch buffer reused across calls on the same (device, stream): the pipeline is stream-ordered,
+    so the next call may overwrite it.  Grows monotonically."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _WS_CACHE.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = t
+    return t
 
 
 def _image_sizes_tensor(im_szs, dev) -> Tensor:
@@ -39,16 +51,75 @@ def default_candidate_capacity(N: int, A: int, C: int) -> int:
     return int(min(N * A * C, max(1 << 20, N * (1 << 16))))
 
 
-def postprocess_batch(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
-                      im_szs: Sequence[Tuple[int, int]], score_thres: float, nms_thres: float, max_det: int,
-                      pre_nms_topk: Optional[int] = None, level_offsets: Optional[Sequence[int]] = None,
-                      cand_capacity: Optional[int] = None, algo: str = "auto"):
-    """Returns (boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int]).
+class PendingDetections:
+    """Handle of an enqueued post-processing call.  All kernels and the (pinned, asynchronous) copy of
+    the detection counts are already on the stream; ``result()`` waits for that copy only, handles the
+    rare re-runs (candidate pool overflow / lazy -> general fallback) and slices the ragged outputs.
+    Lets a caller enqueue the next batch before looking at this one (no GPU idle gap at the sync)."""
+
+    def __init__(self, args: dict):
+        self._a = args
+        self._done = None
+        self._launch()
+
+    def _launch(self):
+        a = self._a
+        lib = _native.load()
+        dev, N, A, C = a["dev"], a["N"], a["A"], a["C"]
+        ws_bytes = lib.rn_postprocess_workspace_bytes(N, A, C, a["cap"], a["max_det"])
+        ws = _workspace(ws_bytes, dev)
+        meta = torch.empty((N + 4,), dtype=torch.int32, device=dev)   # counts [N] + status [4]
+        with torch.cuda.device(dev):
+            rc = lib.rn_postprocess(_native.ptr(a["x"], torch.float32, "cls_preds"), _native.ptr(a["b"], torch.float32, "bbox_preds"),
+                                    _native.ptr(a["anchors"], torch.float32, "anchors"), a["anchor_stride"], _native.ptr(a["hw"]),
+                                    N, A, C, a["score_thres"], a["nms_thres"], a["max_det"], _REG_WEIGHTS_C, a["topk"],
+                                    a["lvl"], a["nlev"], 1 if a["use_general"] else 0, a["cap"],
+                                    _native.ptr(a["out_boxes"]), _native.ptr(a["out_scores"]), _native.ptr(a["out_labels"]),
+                                    meta.data_ptr(), meta.data_ptr() + 4 * N, _native.ptr(ws), ws_bytes,
+                                    _native.stream_ptr(dev))
+        _native.check(rc, "rn_postprocess")
+        self._host = torch.empty((N + 4,), dtype=torch.int32, pin_memory=True)
+        self._host.copy_(meta, non_blocking=True)       # the single D2H copy of the path
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(dev))
+
+    def result(self):
+        """(boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int])."""
+        if self._done is not None:
+            return self._done
+        a = self._a
+        N = a["N"]
+        while True:
+            self._event.synchronize()
+            host = self._host.tolist()
+            found, capacity, fallback = host[N], host[N + 1], host[N + 2]
+            if found > capacity:
+                a["cap"] = found          # candidate pool overflowed: the exact need is now known
+            elif fallback and not a["use_general"]:
+                if a["algo"] == "lazy":
+                    raise _native.NativeError("rn_postprocess: lazy algorithm could not finish (algo='lazy' forced)")
+                a["use_general"] = True   # rare: an image needs more rounds than the lazy budget
+            else:
+                self._done = (a["out_boxes"], a["out_scores"], a["out_labels"], host[:N])
+                return self._done
+            self._launch()
+
+    def detections(self) -> List[Dict[str, Tensor]]:
+        ob, os_, ol, counts = self.result()
+        # one unbind per tensor + one slice per field (half the view ops of ob[i, :k])
+        return [{"boxes": b[:k], "scores": s[:k], "labels": l[:k]}
+                for b, s, l, k in zip(ob.unbind(0), os_.unbind(0), ol.unbind(0), counts)]
+
+
+def postprocess_batch_async(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
+                            im_szs: Sequence[Tuple[int, int]], score_thres: float, nms_thres: float, max_det: int,
+                            pre_nms_topk: Optional[int] = None, level_offsets: Optional[Sequence[int]] = None,
+                            cand_capacity: Optional[int] = None, algo: str = "auto") -> PendingDetections:
+    """Enqueues the whole post-processing of a batch and returns without synchronising.
 
     ``algo``: "auto" = lazy per-image algorithm, transparently repeated with the general
     per-(image,class) algorithm when the lazy one reports it could not finish an image;
     "lazy" / "general" force one of them (tests).  Results are identical."""
-    lib = _native.load()
     dev = cls_preds.device
     N, A, C = cls_preds.shape
     x = cls_preds.detach()
@@ -57,56 +128,43 @@ def postprocess_batch(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, an
     b = b if (b.dtype == torch.float32 and b.is_contiguous()) else b.to(torch.float32).contiguous()
     if len(im_szs) != N:
         raise ValueError(f"{len(im_szs)} image sizes for {N} images")
-    hw = _image_sizes_tensor(im_szs, dev)
-    out_boxes = torch.empty((N, max_det, 4), dtype=torch.float32, device=dev)
-    out_scores = torch.empty((N, max_det), dtype=torch.float32, device=dev)
-    out_labels = torch.empty((N, max_det), dtype=torch.int64, device=dev)
-    meta = torch.empty((N + 4,), dtype=torch.int32, device=dev)   # counts [N] + status [4]
-    use_general = algo == "general" or (A * C >= (1 << 32))
-    cap = int(cand_capacity) if cand_capacity else default_candidate_capacity(N, A, C)
     topk = int(pre_nms_topk) if pre_nms_topk else 0
-    lvl = None
-    nlev = 0
+    lvl, nlev = None, 0
     if topk:
         if level_offsets is None:
             raise ValueError("pre_nms_topk requires level_offsets")
         nlev = len(level_offsets) - 1
         lvl = (ctypes.c_int64 * len(level_offsets))(*[int(v) for v in level_offsets])
-    while True:
-        ws_bytes = lib.rn_postprocess_workspace_bytes(N, A, C, cap, max_det)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            rc = lib.rn_postprocess(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
-                                    _native.ptr(anchors, torch.float32, "anchors"), anchor_stride, _native.ptr(hw), N, A, C,
-                                    float(score_thres), float(nms_thres), int(max_det),
-                                    _REG_WEIGHTS_C, topk, lvl, nlev, 1 if use_general else 0, cap,
-                                    _native.ptr(out_boxes), _native.ptr(out_scores), _native.ptr(out_labels),
-                                    meta.data_ptr(), meta.data_ptr() + 4 * N, _native.ptr(ws), ws_bytes,
-                                    _native.stream_ptr(dev))
-        _native.check(rc, "rn_postprocess")
-        host = meta.tolist()          # the single D2H copy / sync of the path
-        found, capacity, fallback = host[N], host[N + 1], host[N + 2]
-        if found > capacity:
-            cap = found               # candidate pool overflowed: the exact need is now known
-            continue
-        if fallback and not use_general:
-            if algo == "lazy":
-                raise _native.NativeError("rn_postprocess: lazy algorithm could not finish (algo='lazy' forced)")
-            use_general = True        # rare: an image needs more rounds than the lazy budget
-            continue
-        return out_boxes, out_scores, out_labels, host[:N]
+    args = dict(dev=dev, N=N, A=A, C=C, x=x, b=b, anchors=anchors, anchor_stride=anchor_stride,
+                hw=_image_sizes_tensor(im_szs, dev), score_thres=float(score_thres), nms_thres=float(nms_thres),
+                max_det=int(max_det), topk=topk, lvl=lvl, nlev=nlev, algo=algo,
+                use_general=(algo == "general" or (A * C >= (1 << 32))),
+                cap=int(cand_capacity) if cand_capacity else default_candidate_capacity(N, A, C),
+                out_boxes=torch.empty((N, max_det, 4), dtype=torch.float32, device=dev),
+                out_scores=torch.empty((N, max_det), dtype=torch.float32, device=dev),
+                out_labels=torch.empty((N, max_det), dtype=torch.int64, device=dev))
+    return PendingDetections(args)
+
+
+def postprocess_batch(*args, **kw):
+    """Synchronous form of :func:`postprocess_batch_async`: returns
+    (boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int])."""
+    return postprocess_batch_async(*args, **kw).result()
+
+
+def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Tensor],
+                             im_szs: List[Tuple[int, int]]) -> PendingDetections:
+    """Same arguments and side effects as :func:`process_detections`; returns a handle whose
+    ``.detections()`` yields the reference's ``List[Dict]``."""
+    class_logits = outputs.pop("cls_preds")
+    bboxes = outputs.pop("bbox_preds")
+    an, stride = _shared_anchors(anchors)
+    return postprocess_batch_async(class_logits, bboxes, an, stride, im_szs,
+                                   getattr(self, "score_thres", SCORE_THRES), getattr(self, "nms_thres", NMS_THRES),
+                                   getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE),
+                                   getattr(self, "pre_nms_topk", None), getattr(self, "anchor_level_offsets", None))
 
 
 def process_detections(self, outputs: Dict[str, Tensor], anchors: List[Tensor],
                        im_szs: List[Tuple[int, int]]) -> List[Dict[str, Tensor]]:
-    class_logits = outputs.pop("cls_preds")
-    bboxes = outputs.pop("bbox_preds")
-    an, stride = _shared_anchors(anchors)
-    score_thres = getattr(self, "score_thres", SCORE_THRES)
-    nms_thres = getattr(self, "nms_thres", NMS_THRES)
-    max_det = getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE)
-    topk = getattr(self, "pre_nms_topk", None)
-    lvl = getattr(self, "anchor_level_offsets", None)
-    ob, os_, ol, counts = postprocess_batch(class_logits, bboxes, an, stride, im_szs, score_thres, nms_thres,
-                                            max_det, topk, lvl)
-    return [{"boxes": ob[i, :k], "scores": os_[i, :k], "labels": ol[i, :k]} for i, k in enumerate(counts)]
+    return process_detections_async(self, outputs, anchors, im_szs).detections()

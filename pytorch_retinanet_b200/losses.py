@@ -105,6 +105,43 @@ class _FusedRetinaNetLoss(torch.autograd.Function):
         return outs[0], outs[1], None, None, None, None
 
 
+class _DenseLoss(torch.autograd.Function):
+    """sum-reduced element-wise loss with its gradient produced in the same pass (focal or smooth-L1)."""
+
+    @staticmethod
+    def forward(ctx, kind, x, t, p0, p1):
+        lib = _native.load()
+        xc = x.detach().to(torch.float32).contiguous()
+        tc = t.detach().to(torch.float32).contiguous()
+        if xc.shape != tc.shape:
+            raise ValueError(f"{kind}: input {tuple(x.shape)} and target {tuple(t.shape)} differ in shape")
+        dev = xc.device
+        out = torch.empty((1,), dtype=torch.float32, device=dev)
+        grad = torch.empty_like(xc) if x.requires_grad else None
+        nb = lib.rn_dense_loss_workspace_bytes()
+        ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            if kind == "focal":
+                rc = lib.rn_focal_loss_dense(_native.ptr(xc, what="clas_pred"), _native.ptr(tc, what="clas_tgt"), xc.numel(),
+                                             float(p0), float(p1), _native.ptr(out), _native.ptr(grad), _native.ptr(ws), nb,
+                                             _native.stream_ptr(dev))
+            else:
+                rc = lib.rn_smooth_l1_dense(_native.ptr(xc, what="input"), _native.ptr(tc, what="target"), xc.numel(),
+                                            float(p0), _native.ptr(out), _native.ptr(grad), _native.ptr(ws), nb,
+                                            _native.stream_ptr(dev))
+        _native.check(rc, kind)
+        ctx.grad = grad
+        ctx.in_dtype = x.dtype
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grad is None:
+            return None, None, None, None, None
+        gx = ctx.grad * g                      # tiny API-parity path; the fused path never comes here
+        return None, gx.to(ctx.in_dtype), None, None, None
+
+
 class RetinaNetLosses(nn.Module):
     """Reference: retinanet/losses.py:11-145 (hyper-parameters read from config at construction)."""
 
@@ -119,6 +156,15 @@ class RetinaNetLosses(nn.Module):
         return {"alpha": self.alpha, "gamma": self.gamma, "beta": self.beta,
                 "match_thr": IOU_THRESHOLDS_FOREGROUND, "back_thr": IOU_THRESHOLDS_BACKGROUND,
                 "batch_div": float(batch_div)}
+
+    def smooth_l1_loss(self, input: Tensor, target: Tensor) -> Tensor:
+        """Sum-reduced smooth-L1 (reference: losses.py:19-27); differentiable w.r.t. ``input``."""
+        return _DenseLoss.apply("smooth_l1", input, target, self.beta, 0.0)
+
+    def focal_loss(self, clas_pred: Tensor, clas_tgt: Tensor) -> Tensor:
+        """Sum-reduced sigmoid focal loss on dense float targets (reference: losses.py:29-47, weights from
+        detached probabilities, alpha applied inverted, NO +1 shift — that lives in calc_loss)."""
+        return _DenseLoss.apply("focal", clas_pred, clas_tgt, self.alpha, self.gamma)
 
     def calc_loss(self, anchors: Tensor, clas_pred: Tensor, bbox_pred: Tensor, clas_tgt: Tensor,
                   bbox_tgt: Tensor) -> Tuple[Tensor, Tensor]:

@@ -267,6 +267,36 @@ def test_loss_generic_gamma_and_l1(P):
         assert rel_close(bb.grad, bo.grad, 2e-5, 1e-9), (gamma, beta)
 
 
+def test_dense_focal_and_smooth_l1_methods(P):
+    """RetinaNetLosses.focal_loss / smooth_l1_loss (losses.py:19-47) on dense targets, with gradients."""
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn((3001, 7), generator=gen) * 3
+    t = (torch.rand((3001, 7), generator=gen) < 0.1).float()
+    t[5] = torch.rand(7, generator=gen)                            # soft targets are legal inputs too
+    for gamma, alpha in ((2.0, 0.25), (1.5, 0.4)):
+        xo = x.clone().requires_grad_(True)
+        want = O.focal_sum(xo, t, alpha, gamma)
+        want.backward()
+        L = P.RetinaNetLosses(7)
+        L.gamma, L.alpha = gamma, alpha
+        xg = x.cuda().requires_grad_(True)
+        got = L.focal_loss(xg, t.cuda())
+        (got * 2.0).backward()
+        assert rel_close(got, want.detach(), LOSS_RTOL), (gamma, float(got), float(want))
+        assert rel_close(xg.grad, 2.0 * xo.grad, 2e-5, 1e-9)
+    a, b = torch.randn((513, 4), generator=gen), torch.randn((513, 4), generator=gen) * 0.2
+    for beta in (0.1, 0.0):
+        ao = a.clone().requires_grad_(True)
+        want = O.smooth_l1_sum(ao, b, beta)
+        want.backward()
+        L = P.RetinaNetLosses(3)
+        L.beta = beta
+        ag = a.cuda().requires_grad_(True)
+        got = L.smooth_l1_loss(ag, b.cuda())
+        got.backward()
+        assert rel_close(got, want.detach(), LOSS_RTOL) and rel_close(ag.grad, ao.grad, 1e-5, 1e-9), beta
+
+
 # ------------------------------------------------------------------------------------------ post-processing
 def gpu_detect(P, cls, bb, anchors_list, im_szs, algo="auto", **kw):
     """algo="auto": through the drop-in process_detections(self, outputs, anchors, im_szs);

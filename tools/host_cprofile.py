@@ -1,0 +1,39 @@
+"""cProfile of the bench step's host side (top functions by self time)."""
+import cProfile, os, pstats, sys, io
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import synth_data as S
+import pytorch_retinanet_b200 as P
+from types import SimpleNamespace
+
+dev = torch.device("cuda", 0)
+cfg = S.CONFIGS[2]
+n_img = 16
+batch = S.make_batch(cfg, 0, n_img)
+d_cls, d_box = batch["cls_preds"].to(dev), batch["bbox_preds"].to(dev)
+targets = [{k: v.to(dev) for k, v in t.items()} for t in batch["targets"]]
+gen = P.AnchorGenerator().to(dev)
+fmaps = [torch.empty((n_img, 1, h, w), device=dev) for h, w in S.grid_sizes(cfg.padded_hw)]
+images = SimpleNamespace(image_sizes=batch["im_szs"])
+L = P.RetinaNetLosses(cfg.num_classes)
+stub = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
+
+def step():
+    anchors = gen(images, fmaps)
+    x, b = d_cls.detach().requires_grad_(True), d_box.detach().requires_grad_(True)
+    out = L(targets, {"cls_preds": x, "bbox_preds": b}, anchors)
+    (out["classification_loss"] + out["regression_loss"]).backward()
+    return P.process_detections(stub, {"cls_preds": d_cls, "bbox_preds": d_box}, anchors, batch["im_szs"])
+
+for _ in range(10):
+    step()
+torch.cuda.synchronize()
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(200):
+    step()
+torch.cuda.synchronize()
+pr.disable()
+s = io.StringIO()
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28)
+print(s.getvalue()[:6000])
