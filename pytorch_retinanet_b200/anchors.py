@@ -66,6 +66,7 @@ class AnchorGenerator(nn.Module):
         self.offset = offset
         self.cell_anchors = self._calculate_cell_anchors(self.sizes, self.aspect_ratios)
         self._cache: Dict[Tuple, Tensor] = {}
+        self.last_level_offsets: List[int] = []   # anchor offsets of the pyramid levels of the last grid
 
     def _calculate_cell_anchors(self, sizes, ratios):
         return self._calculate_anchors(sizes, ratios)
@@ -104,6 +105,10 @@ class AnchorGenerator(nn.Module):
         if device.type != "cuda":
             raise _native.NativeError("retinanet_b200.AnchorGenerator: feature maps must live on a CUDA device")
         grid_sizes = [(int(h), int(w)) for h, w in grid_sizes]
+        offs = [0]
+        for (h, w), n in zip(grid_sizes, self.num_anchors):
+            offs.append(offs[-1] + h * w * n)
+        self.last_level_offsets = offs
         key = (tuple(grid_sizes), device.index if device.index is not None else torch.cuda.current_device())
         hit = self._cache.get(key)
         if hit is not None:

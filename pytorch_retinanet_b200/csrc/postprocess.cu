@@ -503,6 +503,9 @@ struct LazyParams {
     long long *out_labels;
     int *out_count;
     int *status;             // [0] max candidates/image * N (atomicMax), [2] fallback flag
+    int topk;                // pre_nms_topk per (image, pyramid level); 0 = off (reference behaviour)
+    int nlev;
+    long long lvl_off[RN_MAX_LEVELS + 1];   // anchor offsets of the pyramid levels
 };
 
 struct LazySmem {
@@ -517,6 +520,8 @@ struct LazySmem {
     u32 kscore[MAX_DET_CAP];
     u32 hist[256];
     u32 removed[LZ_CHUNK / 32];
+    int lvl_cnt[RN_MAX_LEVELS];                       // candidates seen so far per level (pre_nms_topk)
+    int lvl_wcnt[LZ_CHUNK / 32][RN_MAX_LEVELS];
     int wbase[LZ_CHUNK / 32 + 1];
     u64 prefix, mask_bits, thr_key;
     u32 need;
@@ -546,6 +551,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
         if (t == 0) P.out_count[n] = 0;
         return;
     }
+    if (t < RN_MAX_LEVELS) S.lvl_cnt[t] = 0;
     const u64 *g_cand = P.cand_key + (size_t)n * P.cap_n;
     const bool cached = K <= LZ_CACHE;
     if (cached) {
@@ -562,7 +568,13 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     int kept = 0, processed = 0;
     u64 last = 0;                                  // keys are > 0 (score <= 1 -> ~bits >= 0xC07FFFFF)
 #pragma unroll 1
-    for (int round = 0; round < LZ_ROUNDS && processed < K && kept < P.max_det; ++round) {
+    // with pre_nms_topk the walk continues until every level has seen its k candidates (no round budget)
+    for (int round = 0; (round < LZ_ROUNDS || P.topk > 0) && processed < K && kept < P.max_det; ++round) {
+        if (P.topk > 0) {
+            bool full = true;
+            for (int l = 0; l < P.nlev; ++l) full = full && S.lvl_cnt[l] >= P.topk;
+            if (full) { processed = K; break; }               // nothing below this rank is eligible any more
+        }
         const int remaining = K - processed;
         const int cap_r = LZ_M;
         const int take = min(remaining, cap_r);
@@ -650,10 +662,10 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
 #pragma unroll 1
         for (int c0 = 0; c0 < nsel && kept < P.max_det; c0 += LZ_CHUNK) {
             const int m = min(LZ_CHUNK, nsel - c0);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            int cls = -1, lvl = -1, lrank = 0;
+            bool alive = false;
             if (t < LZ_CHUNK) {
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                int cls = -1;
-                bool alive = false;
                 if (t < m) {
                     const u32 lo = (u32)S.sel[c0 + t];
                     cls = (int)(lo / A32);
@@ -661,7 +673,34 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                     b = decode_clip(P.bbox, P.anchors, img_row + anchor, anc_row + anchor, P.wts, imw, imh);
                     // remove_small_boxes(min_size=1e-2), models.py:203
                     alive = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);
+                    if (P.topk > 0) {
+                        lvl = 0;
+                        for (int l = 1; l < P.nlev; ++l) lvl += anchor >= P.lvl_off[l];
+                    }
                 }
+                if (P.topk > 0) {                              // rank of this candidate inside its level (global order)
+                    for (int l = 0; l < P.nlev; ++l) {
+                        const u32 bl = __ballot_sync(0xffffffffu, lvl == l);
+                        if (lane == 0) S.lvl_wcnt[warp][l] = __popc(bl);
+                        if (lvl == l) lrank = __popc(bl & ((1u << lane) - 1u));
+                    }
+                }
+            }
+            if (P.topk > 0) {
+                __syncthreads();
+                if (t < LZ_CHUNK && lvl >= 0) {
+                    int before = S.lvl_cnt[lvl] + lrank;
+                    for (int w = 0; w < warp; ++w) before += S.lvl_wcnt[w][lvl];
+                    alive = alive && before < P.topk;          // only the top-k scores of a level survive
+                }
+                __syncthreads();
+                if (t < P.nlev) {
+                    int add = 0;
+                    for (int w = 0; w < LZ_CHUNK / 32; ++w) add += S.lvl_wcnt[w][t];
+                    S.lvl_cnt[t] += add;
+                }
+            }
+            if (t < LZ_CHUNK) {
                 const float area = nms_area(b);
                 if (alive) {                                   // (a) boxes kept so far, same class only
 #pragma unroll 1
@@ -1026,7 +1065,6 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
                               int num_levels, int algo, int64_t cand_capacity, float *out_boxes, float *out_scores,
                               int64_t *out_labels, int32_t *out_count, int32_t *out_status, void *workspace,
                               size_t workspace_bytes, rn_stream_t stream) {
-    (void)level_off_host; (void)num_levels;
     RN_CHECK_ARG(logits && bbox && anchors && im_hw && weights_host && out_boxes && out_scores && out_labels &&
                      out_count && out_status && workspace,
                  RN_E_BADARG, "rn_postprocess: null pointer");
@@ -1037,7 +1075,9 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
     RN_CHECK_ARG(max_det >= 1 && max_det <= MAX_DET_CAP, RN_E_TOOLARGE, "rn_postprocess: max_det=%d outside [1,%d]",
                  max_det, MAX_DET_CAP);
     RN_CHECK_ARG(cand_capacity >= 1 && cand_capacity < 0x7fffffffLL, RN_E_BADARG, "rn_postprocess: bad cand_capacity");
-    RN_CHECK_ARG(pre_nms_topk == 0, RN_E_BADARG, "rn_postprocess: pre_nms_topk is not implemented in this build");
+    RN_CHECK_ARG(pre_nms_topk >= 0, RN_E_BADARG, "rn_postprocess: negative pre_nms_topk");
+    RN_CHECK_ARG(pre_nms_topk == 0 || (algo == RN_PP_LAZY && level_off_host && num_levels >= 1 && num_levels <= RN_MAX_LEVELS),
+                 RN_E_BADARG, "rn_postprocess: pre_nms_topk needs algo = RN_PP_LAZY and 1..%d level offsets", RN_MAX_LEVELS);
     RN_CHECK_ARG((size_t)N * C < 0x7fffffffULL, RN_E_TOOLARGE, "rn_postprocess: N*C too large");
     RN_CHECK_ARG(algo == RN_PP_LAZY || algo == RN_PP_GENERAL, RN_E_BADARG, "rn_postprocess: unknown algo %d", algo);
     RN_CHECK_ARG(algo != RN_PP_LAZY || (unsigned long long)A * (unsigned long long)C < (1ULL << 32), RN_E_TOOLARGE,
@@ -1087,6 +1127,9 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
         Z.anchor_stride = anchor_image_stride; Z.C = C; Z.N = N; Z.thr = thr_f; Z.wts = F.wts; Z.max_det = max_det;
         Z.cand_key = w.pool_key; Z.img_count = w.img_count; Z.cap_n = F.cap_n; Z.out_boxes = out_boxes;
         Z.out_scores = out_scores; Z.out_labels = (long long *)out_labels; Z.out_count = out_count; Z.status = out_status;
+        Z.topk = pre_nms_topk; Z.nlev = pre_nms_topk ? num_levels : 0;
+        for (int l = 0; l <= RN_MAX_LEVELS; ++l)
+            Z.lvl_off[l] = (pre_nms_topk && l <= num_levels) ? (long long)level_off_host[l] : (long long)A;
         const size_t smem = ((sizeof(LazySmem) + 15) & ~(size_t)15) + (size_t)LZ_CACHE * sizeof(u64);
         cudaFuncSetAttribute(lazy_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         lazy_nms_kernel<<<N, LZ_BLOCK, smem, s>>>(Z);

@@ -135,6 +135,8 @@ def postprocess_batch_async(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tens
             raise ValueError("pre_nms_topk requires level_offsets")
         nlev = len(level_offsets) - 1
         lvl = (ctypes.c_int64 * len(level_offsets))(*[int(v) for v in level_offsets])
+    if topk and (algo == "general" or A * C >= (1 << 32)):
+        raise ValueError("pre_nms_topk is implemented by the lazy algorithm only (needs A*C < 2^32)")
     args = dict(dev=dev, N=N, A=A, C=C, x=x, b=b, anchors=anchors, anchor_stride=anchor_stride,
                 hw=_image_sizes_tensor(im_szs, dev), score_thres=float(score_thres), nms_thres=float(nms_thres),
                 max_det=int(max_det), topk=topk, lvl=lvl, nlev=nlev, algo=algo,
@@ -152,6 +154,17 @@ def postprocess_batch(*args, **kw):
     return postprocess_batch_async(*args, **kw).result()
 
 
+def _level_offsets(self):
+    """Anchor offsets of the pyramid levels, needed only when ``self.pre_nms_topk`` is set: an explicit
+    ``self.anchor_level_offsets`` wins, else the ones recorded by our AnchorGenerator's last forward."""
+    if not getattr(self, "pre_nms_topk", None):
+        return None
+    offs = getattr(self, "anchor_level_offsets", None)
+    if offs is None:
+        offs = getattr(getattr(self, "anchor_generator", None), "last_level_offsets", None)
+    return offs
+
+
 def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Tensor],
                              im_szs: List[Tuple[int, int]]) -> PendingDetections:
     """Same arguments and side effects as :func:`process_detections`; returns a handle whose
@@ -162,7 +175,7 @@ def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Ten
     return postprocess_batch_async(class_logits, bboxes, an, stride, im_szs,
                                    getattr(self, "score_thres", SCORE_THRES), getattr(self, "nms_thres", NMS_THRES),
                                    getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE),
-                                   getattr(self, "pre_nms_topk", None), getattr(self, "anchor_level_offsets", None))
+                                   getattr(self, "pre_nms_topk", None), _level_offsets(self))
 
 
 def process_detections(self, outputs: Dict[str, Tensor], anchors: List[Tensor],

@@ -427,6 +427,34 @@ def test_postprocess_lazy_fallback(P):
             assert_dets_equal(got[i], want[i], exact=True, ctx=f"{algo} image {i}")
 
 
+@pytest.mark.parametrize("cid,topk", [(1, 50), (1, 1000), (2, 1000), (2, 7)])
+def test_postprocess_pre_nms_topk_extension(P, cid, topk):
+    """`pre_nms_topk` per (image, pyramid level) — BASELINE.json configs[3] lists top-k 1000/level; the
+    reference has no such stage, so the oracle is the reference code + the documented filter
+    (SURVEY.md §8 'Reconciling north_star with A19')."""
+    from types import SimpleNamespace
+    b, _ = config_image(cid)
+    dev = torch.device("cuda")
+    gen = P.AnchorGenerator().cuda()
+    fmaps = [torch.empty((1, 1, h, w), device=dev) for h, w in S.grid_sizes(b["config"].padded_hw)]
+    anchors = gen(SimpleNamespace(image_sizes=b["im_szs"]), fmaps)
+    offs = gen.last_level_offsets
+    assert offs[-1] == b["anchors"].shape[0] and len(offs) == 6
+    model = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100, pre_nms_topk=topk,
+                            anchor_generator=gen)
+    got = P.process_detections(model, {"cls_preds": b["cls_preds"].cuda(), "bbox_preds": b["bbox_preds"].cuda()},
+                               anchors, b["im_szs"])[0]
+    want = O.postprocess(b["cls_preds"].cuda(), b["bbox_preds"].cuda(), anchors, b["im_szs"],
+                         pre_nms_topk=topk, level_offsets=offs)[0]
+    assert_dets_equal(got, want, exact=True, ctx=f"config{cid} topk={topk}")
+    # a top-k that no level reaches is a no-op
+    if topk >= 1000 and cid == 1:
+        plain = P.process_detections(SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100),
+                                     {"cls_preds": b["cls_preds"].cuda(), "bbox_preds": b["bbox_preds"].cuda()},
+                                     anchors, b["im_szs"])[0]
+        assert_dets_equal(got, plain, exact=True, ctx="no-op topk")
+
+
 def test_nms_segments_vs_torchvision(P):
     import ctypes
     import torchvision
