@@ -145,6 +145,7 @@ def time_cpu_reference(batch, n_images, repeats=1):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)              # every host thread the box has
     cfg = S.CONFIGS[WORKLOAD_CFG]
     sample = 2
     batch = S.make_batch(cfg, 0, sample)

@@ -139,6 +139,31 @@ int rn_postprocess(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*
                    float *out_boxes, float *out_scores, int64_t *out_labels, int32_t *out_count,
                    int32_t *out_status, void *workspace, size_t workspace_bytes, rn_stream_t stream);
 
+/* ---- per-level NCHW entry points -------------------------------------------
+ * Same semantics and outputs as rn_loss / rn_postprocess, but the class and box activations are the
+ * RAW per-level conv outputs of the reference's head, before its view/permute/contiguous/cat
+ * (retinanet/layers.py:189-195, 253-259): cls level l is [N, na_l*C, H_l, W_l], box level l is
+ * [N, na_l*4, H_l, W_l] (channel = a*C + c resp. a*4 + k), contiguous.  level_desc_host[l] =
+ * {H_l, W_l, na_l}; *_levels_host are HOST arrays of num_levels DEVICE pointers.  Gradients (optional)
+ * are written in the same per-level layout.  The anchor of element (a, y, x) of level l is
+ * off_l + (y*W_l + x)*na_l + a, i.e. exactly the reference's order, so rn_match's codes apply unchanged. */
+size_t rn_loss_levels_workspace_bytes(int N, const int32_t *level_desc_host, int num_levels);
+int rn_loss_levels(const float *const *cls_levels_host, const float *const *bbox_levels_host,
+                   const int32_t *level_desc_host /*[L][3]*/, int num_levels, const float *anchors,
+                   int64_t anchor_image_stride, const float *gt_boxes, const int32_t *gt_off, const int32_t *codes,
+                   const int32_t *fg_count, int N, int64_t A, int C, float alpha, float gamma, float beta,
+                   const float *weights_host, float batch_div, float *out_image /*[N,3]*/, float *out_total /*[4]*/,
+                   float *const *grad_cls_levels_host /*or NULL*/, float *const *grad_bbox_levels_host /*or NULL*/,
+                   void *workspace, size_t workspace_bytes, rn_stream_t stream);
+size_t rn_postprocess_levels_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
+int rn_postprocess_levels(const float *const *cls_levels_host, const float *const *bbox_levels_host,
+                          const int32_t *level_desc_host /*[L][3]*/, int num_levels, const float *anchors,
+                          int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A, int C, float score_thr,
+                          double nms_thr, int max_det, const float *weights_host, int pre_nms_topk, int algo,
+                          int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
+                          int32_t *out_count, int32_t *out_status, void *workspace, size_t workspace_bytes,
+                          rn_stream_t stream);
+
 /* Stand-alone batched greedy NMS (torchvision `nms` semantics, tv:ops/boxes.py:20-48) over
  * segments whose boxes are ALREADY sorted by score descending (ties: original order): boxes [K,4],
  * seg_off [S+1] int32, keep_flags [K] uint8 out (1 = kept).  workspace >= 16*K bytes.            */

@@ -24,6 +24,7 @@
 // partials to the workspace and a fixed-order final kernel => bit-reproducible.
 #include <algorithm>
 
+#include "loss_math.cuh"
 #include "rn_common.cuh"
 
 namespace {
@@ -54,65 +55,7 @@ struct LossParams {
     float4 wts;
 };
 
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kSmallE = 0.0625f;               // series path valid for e <= 1/16
-constexpr float kSmallX = -2.7725887f;           // x <= ln(1/16)
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// log1p(e) for 0 <= e <= 1/16: alternating series, truncation error e^6/7 < 1e-8
-__device__ __forceinline__ float log1p_small(float e) {
-    float s = fmaf(e, -1.0f / 6.0f, 0.2f);
-    s = fmaf(e, s, -0.25f);
-    s = fmaf(e, s, 1.0f / 3.0f);
-    s = fmaf(e, s, -0.5f);
-    s = fmaf(e, s, 1.0f);
-    return e * s;
-}
-
-// p = sigmoid(x), sp = softplus(x) = log(1 + exp(x))
-template <bool PRECISE>
-__device__ __forceinline__ void sigmoid_softplus(float x, float &p, float &sp) {
-    if (PRECISE) {
-        float e = expf(-fabsf(x));
-        float r = __fdiv_rn(1.0f, 1.0f + e);
-        p = x >= 0.0f ? r : e * r;
-        sp = fmaxf(x, 0.0f) + log1pf(e);
-    } else {
-        float e = ex2_approx(-fabsf(x) * kLog2e);
-        float d = 1.0f + e;
-        float r = rcp_approx(d);
-        p = x >= 0.0f ? r : e * r;
-        float l = e <= kSmallE ? log1p_small(e) : lg2_approx(d) * kLn2;
-        sp = fmaxf(x, 0.0f) + l;
-    }
-}
-// warp-uniform small-x path (x <= -2.77): e = exp(x) <= 1/16
-__device__ __forceinline__ void sigmoid_softplus_small(float v, float &p, float &sp) {
-    float e = ex2_approx(fmaf(v, kLog2e, kLog2e));   // exp(v + 1)
-    p = e * rcp_approx(1.0f + e);
-    sp = log1p_small(e);
-}
-
-template <bool GAMMA2>
-__device__ __forceinline__ float pow_gamma(float b, float gamma) {
-    if (GAMMA2) return b * b;
-    return b > 0.0f ? ex2_approx(gamma * lg2_approx(b)) : (gamma == 0.0f ? 1.0f : 0.0f);
-}
+using namespace rnloss;
 
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
     __shared__ double s[3][LOSS_BLOCK / 32];
@@ -407,6 +350,252 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     loss_finalize_kernel<<<1, 1024, smem, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
                                               out_total);
     RN_CHECK_LAUNCH("rn_loss_finalize");
+    return 0;
+}
+
+// ---- per-level NCHW layout -----------------------------------------------------------
+// The reference's head permutes every level's conv output [N, na*C, H, W] to [N, H*W*na, C] and
+// concatenates the levels (retinanet/layers.py:189-195, 253-259): a full extra read+write of the logits
+// right before this path.  loss_levels_kernel consumes the conv outputs directly (index math only) and
+// writes the gradients back in NCHW, so that pass disappears.  Element (n, a, c, y, x) of a level lives
+// at ((n*na + a)*C + c)*H*W + y*W + x and belongs to anchor lvl_off + (y*W + x)*na + a.
+// One CTA = 128 consecutive positions of one level x all na*C channel planes; the tile's packed codes
+// are staged in shared memory as [a][position]; each warp walks channel planes (4 in flight), each lane
+// owning 4 positions (one 128-bit load when H*W % 4 == 0, else 4 coalesced scalar loads).
+namespace {
+constexpr int LV_TILE = 128;
+constexpr int LV_BLOCK = 256;
+constexpr int LV_MAX_NA = 16;
+constexpr int LV_U = 4;
+
+struct LvlLossParams {
+    const float *cls;
+    const float *box;
+    float *gcls;
+    float *gbox;
+    const float4 *anchors;
+    const float4 *gt;
+    const int *gt_off;
+    const int *codes;
+    const int *fg_count;
+    double *partials;
+    long long A, anchor_stride, lvl_off;
+    int HW, na, C, chunks_total, chunk_base;
+    unsigned magicC;
+    float alpha, gamma, beta, batch_div;
+    float4 wts;
+};
+
+template <int VEC, bool WANT_GRAD, bool GAMMA2>
+__global__ void __launch_bounds__(LV_BLOCK) loss_levels_kernel(const LvlLossParams P) {
+    __shared__ int s_codes[LV_MAX_NA][LV_TILE];
+    const int n = blockIdx.y, tile = blockIdx.x;
+    const int p0 = tile * LV_TILE;
+    const int np = min(LV_TILE, P.HW - p0);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int F = P.fg_count[n];
+    const float inv = 1.0f / (fmaxf((float)F, 1.0f) * P.batch_div);
+    const float neg_gscale = P.alpha * inv;
+    const int *codes = P.codes + (long long)n * P.A + P.lvl_off + (long long)p0 * P.na;
+    for (int idx = t; idx < LV_TILE * P.na; idx += LV_BLOCK) {      // idx = p*na + a: coalesced read, transposed store
+        const int p = idx / P.na, a = idx - p * P.na;
+        s_codes[a][p] = p < np ? __ldg(codes + idx) : -2;
+    }
+    __syncthreads();
+
+    float acc_neg = 0.0f, acc_pos = 0.0f;
+    const int nch = P.na * P.C;
+    const long long img_base = (long long)n * nch * P.HW;
+    for (int ch0 = warp; ch0 < nch; ch0 += (LV_BLOCK / 32) * LV_U) {
+        float v[LV_U][4];
+        int ch[LV_U];
+#pragma unroll
+        for (int u = 0; u < LV_U; ++u) {
+            ch[u] = ch0 + u * (LV_BLOCK / 32);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = -30.0f;
+            if (ch[u] < nch) {
+                const float *plane = P.cls + img_base + (long long)ch[u] * P.HW + p0;
+                if (VEC == 4) {
+                    if (lane * 4 < np) {
+                        const float4 q = rn::ld_stream_f4((const float4 *)plane + lane);
+                        v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (lane + 32 * k < np) v[u][k] = __ldg(plane + lane + 32 * k);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < LV_U; ++u) {
+            if (ch[u] >= nch) continue;                              // warp-uniform
+            const int a = P.magicC ? (int)__umulhi((unsigned)ch[u], P.magicC) : ch[u];  // ch / C
+            const int c = ch[u] - a * P.C;
+            int code[4];
+            bool use[4];
+            float g[4];
+            float vmax = -30.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = VEC == 4 ? lane * 4 + k : lane + 32 * k;
+                code[k] = s_codes[a][p];
+                use[k] = code[k] != -2;
+                vmax = fmaxf(vmax, use[k] ? v[u][k] : -30.0f);
+            }
+            const bool small = __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
+            float local = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float pk, spk;
+                if (small) sigmoid_softplus_small(v[u][k], pk, spk);
+                else sigmoid_softplus<false>(v[u][k] + 1.0f, pk, spk);
+                const float w = pow_gamma<GAMMA2>(pk, P.gamma);
+                local = fmaf(use[k] ? w : 0.0f, spk, local);
+                g[k] = use[k] ? w * pk * neg_gscale : 0.0f;
+                if (code[k] >= 0 && (code[k] >> 20) == c) {          // this element is its anchor's positive
+                    const float x = v[u][k] + 1.0f;
+                    float p, sp;
+                    sigmoid_softplus<false>(x, p, sp);
+                    const float wn = pow_gamma<GAMMA2>(p, P.gamma);
+                    const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
+                    acc_pos += wp * (sp - x) - P.alpha * wn * sp;
+                    g[k] = wp * (p - 1.0f) * inv;
+                }
+            }
+            acc_neg += local;
+            if (WANT_GRAD) {
+                float *gplane = P.gcls + img_base + (long long)ch[u] * P.HW + p0;
+                if (VEC == 4) {
+                    if (lane * 4 < np) rn::st_stream_f4((float4 *)gplane + lane, make_float4(g[0], g[1], g[2], g[3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (lane + 32 * k < np) gplane[lane + 32 * k] = g[k];
+                }
+            }
+        }
+    }
+
+    // ---- regression: (anchor a, position p) pairs of the tile; box channel (a*4 + k) plane, stride HW ----
+    float reg = 0.0f;
+    for (int idx = t; idx < LV_TILE * P.na; idx += LV_BLOCK) {
+        const int a = idx / LV_TILE, p = idx - a * LV_TILE;
+        if (p >= np) continue;
+        const int code = s_codes[a][p];
+        const long long b0 = ((long long)(n * P.na + a) * 4) * P.HW + p0 + p;
+        float gr[4] = {0.f, 0.f, 0.f, 0.f};
+        if (code >= 0) {
+            const long long anchor = P.lvl_off + (long long)(p0 + p) * P.na + a;
+            const float4 gtb = P.gt[P.gt_off[n] + (code & 0xFFFFF)];
+            const float4 an = P.anchors[(long long)n * P.anchor_stride + anchor];
+            const float4 tt = rn::encode_box(gtb, an, P.wts);
+            const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float d = __ldg(P.box + b0 + (long long)k * P.HW) - tv[k];
+                const float nabs = fabsf(d);
+                if (P.beta < 1e-5f) {
+                    reg += nabs;
+                    gr[k] = d > 0.0f ? inv : (d < 0.0f ? -inv : 0.0f);
+                } else if (nabs < P.beta) {
+                    reg += 0.5f * nabs * nabs / P.beta;
+                    gr[k] = d / P.beta * inv;
+                } else {
+                    reg += nabs - 0.5f * P.beta;
+                    gr[k] = d > 0.0f ? inv : -inv;
+                }
+            }
+        }
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) P.gbox[b0 + (long long)k * P.HW] = gr[k];
+        }
+    }
+
+    double s_neg = acc_neg, s_pos = acc_pos, s_reg = reg;
+    block_sum3(s_neg, s_pos, s_reg);
+    if (t == 0) {
+        double *o = P.partials + ((long long)n * P.chunks_total + P.chunk_base + tile) * 2;
+        o[0] = (double)P.alpha * s_neg + s_pos;
+        o[1] = s_reg;
+    }
+}
+
+inline int lv_tiles(int HW) { return (HW + LV_TILE - 1) / LV_TILE; }
+}  // namespace
+
+extern "C" size_t rn_loss_levels_workspace_bytes(int N, const int32_t *level_desc_host, int num_levels) {
+    if (N <= 0 || !level_desc_host || num_levels <= 0) return 16;
+    size_t chunks = 0;
+    for (int l = 0; l < num_levels; ++l) chunks += (size_t)lv_tiles(level_desc_host[3 * l] * level_desc_host[3 * l + 1]);
+    return (size_t)N * chunks * 2 * sizeof(double);
+}
+
+extern "C" int rn_loss_levels(const float *const *cls_levels_host, const float *const *bbox_levels_host,
+                              const int32_t *level_desc_host, int num_levels, const float *anchors,
+                              int64_t anchor_image_stride, const float *gt_boxes, const int32_t *gt_off,
+                              const int32_t *codes, const int32_t *fg_count, int N, int64_t A, int C, float alpha,
+                              float gamma, float beta, const float *weights_host, float batch_div, float *out_image,
+                              float *out_total, float *const *grad_cls_levels_host, float *const *grad_bbox_levels_host,
+                              void *workspace, size_t workspace_bytes, rn_stream_t stream) {
+    RN_CHECK_ARG(cls_levels_host && bbox_levels_host && level_desc_host && anchors && gt_off && codes && fg_count &&
+                     out_total && weights_host, RN_E_BADARG, "rn_loss_levels: null pointer");
+    RN_CHECK_ARG(num_levels >= 1 && num_levels <= RN_MAX_LEVELS, RN_E_TOOLARGE, "rn_loss_levels: bad num_levels %d", num_levels);
+    RN_CHECK_ARG(N > 0 && A > 0 && C > 0 && N <= 65535 && C <= 2048, RN_E_BADARG, "rn_loss_levels: bad N/A/C");
+    RN_CHECK_ARG((grad_cls_levels_host == nullptr) == (grad_bbox_levels_host == nullptr), RN_E_BADARG,
+                 "rn_loss_levels: gradient level arrays must be given together");
+    RN_CHECK_ARG(batch_div > 0.0f, RN_E_BADARG, "rn_loss_levels: batch_div must be positive");
+    RN_CHECK_ARG(workspace && workspace_bytes >= rn_loss_levels_workspace_bytes(N, level_desc_host, num_levels),
+                 RN_E_WORKSPACE, "rn_loss_levels: workspace too small");
+    RN_CHECK_ARG((size_t)N * 2 * sizeof(double) <= 96 * 1024, RN_E_TOOLARGE, "rn_loss_levels: N too large for finalize");
+    cudaStream_t s = (cudaStream_t)stream;
+    int chunks_total = 0;
+    long long total_anchors = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const int32_t *d = level_desc_host + 3 * l;
+        RN_CHECK_ARG(d[0] >= 0 && d[1] >= 0 && d[2] >= 1 && d[2] <= LV_MAX_NA, RN_E_BADARG,
+                     "rn_loss_levels: bad level %d descriptor {%d,%d,%d} (na <= %d)", l, d[0], d[1], d[2], LV_MAX_NA);
+        chunks_total += lv_tiles(d[0] * d[1]);
+        total_anchors += (long long)d[0] * d[1] * d[2];
+    }
+    RN_CHECK_ARG(total_anchors == A, RN_E_BADARG, "rn_loss_levels: levels hold %lld anchors, A = %lld", total_anchors, (long long)A);
+    const bool want = grad_cls_levels_host != nullptr;
+    int chunk_base = 0;
+    long long lvl_off = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const int32_t *d = level_desc_host + 3 * l;
+        const int HW = d[0] * d[1];
+        if (HW > 0) {
+            RN_CHECK_ARG(cls_levels_host[l] && bbox_levels_host[l], RN_E_BADARG, "rn_loss_levels: null level %d", l);
+            LvlLossParams P;
+            P.cls = cls_levels_host[l]; P.box = bbox_levels_host[l];
+            P.gcls = want ? grad_cls_levels_host[l] : nullptr; P.gbox = want ? grad_bbox_levels_host[l] : nullptr;
+            P.anchors = (const float4 *)anchors; P.gt = (const float4 *)gt_boxes; P.gt_off = gt_off; P.codes = codes;
+            P.fg_count = fg_count; P.partials = (double *)workspace; P.A = A; P.anchor_stride = anchor_image_stride;
+            P.lvl_off = lvl_off; P.HW = HW; P.na = d[2]; P.C = C; P.chunks_total = chunks_total; P.chunk_base = chunk_base;
+            P.magicC = C == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)C - 1) / (unsigned)C);
+            P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
+            P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
+            const bool vec4 = (HW % 4 == 0) && (((uintptr_t)P.cls & 15) == 0) && (!want || ((uintptr_t)P.gcls & 15) == 0);
+            dim3 grid((unsigned)lv_tiles(HW), (unsigned)N);
+            const bool g2 = gamma == 2.0f;
+#define RN_LV_LAUNCH(V, W, G) loss_levels_kernel<V, W, G><<<grid, LV_BLOCK, 0, s>>>(P)
+            if (vec4) { if (want) { if (g2) RN_LV_LAUNCH(4, true, true); else RN_LV_LAUNCH(4, true, false); }
+                        else      { if (g2) RN_LV_LAUNCH(4, false, true); else RN_LV_LAUNCH(4, false, false); } }
+            else      { if (want) { if (g2) RN_LV_LAUNCH(1, true, true); else RN_LV_LAUNCH(1, true, false); }
+                        else      { if (g2) RN_LV_LAUNCH(1, false, true); else RN_LV_LAUNCH(1, false, false); } }
+#undef RN_LV_LAUNCH
+            RN_CHECK_LAUNCH("rn_loss_levels");
+        }
+        chunk_base += lv_tiles(HW);
+        lvl_off += (long long)HW * d[2];
+    }
+    size_t smem = (size_t)N * 2 * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    loss_finalize_kernel<<<1, 1024, smem, s>>>((const double *)workspace, fg_count, N, chunks_total, batch_div, out_image, out_total);
+    RN_CHECK_LAUNCH("rn_loss_levels/finalize");
     return 0;
 }
 

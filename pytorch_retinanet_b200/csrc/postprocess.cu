@@ -1058,6 +1058,61 @@ extern "C" size_t rn_postprocess_workspace_bytes(int N, int64_t A, int C, int64_
     return carve(nullptr, N, C, cand_capacity).total_bytes;
 }
 
+// Everything after the streaming filter (shared by the [N,A,C] and the per-level entry points).
+static int pp_tail(const PPWorkspace &w, const FilterParams &F, const float *bbox, const float *anchors,
+                   int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A, int C, double nms_thr,
+                   int max_det, int pre_nms_topk, const int64_t *level_off_host, int num_levels, bool lazy,
+                   int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
+                   int32_t *out_count, int32_t *out_status, cudaStream_t s) {
+    // round the double threshold DOWN to fp32: (double)ovr > thr  <=>  ovr > thr_f  for every fp32 ovr
+    float thr_f = (float)nms_thr;
+    if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
+
+    if (lazy) {
+        LazyParams Z;
+        Z.bbox = (const float4 *)bbox; Z.anchors = (const float4 *)anchors; Z.im_hw = im_hw; Z.A = A;
+        Z.anchor_stride = anchor_image_stride; Z.C = C; Z.N = N; Z.thr = thr_f; Z.wts = F.wts; Z.max_det = max_det;
+        Z.cand_key = w.pool_key; Z.img_count = w.img_count; Z.cap_n = F.cap_n; Z.out_boxes = out_boxes;
+        Z.out_scores = out_scores; Z.out_labels = (long long *)out_labels; Z.out_count = out_count; Z.status = out_status;
+        Z.topk = pre_nms_topk; Z.nlev = pre_nms_topk ? num_levels : 0;
+        for (int l = 0; l <= RN_MAX_LEVELS; ++l)
+            Z.lvl_off[l] = (pre_nms_topk && l <= num_levels) ? (long long)level_off_host[l] : (long long)A;
+        const size_t smem = ((sizeof(LazySmem) + 15) & ~(size_t)15) + (size_t)LZ_CACHE * sizeof(u64);
+        cudaFuncSetAttribute(lazy_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lazy_nms_kernel<<<N, LZ_BLOCK, smem, s>>>(Z);
+        RN_CHECK_LAUNCH("rn_postprocess/lazy_nms");
+        // status[1] = capacity (N * cap_n) is written by a 1-thread epilogue to keep the call async
+        set_status_capacity_kernel<<<1, 1, 0, s>>>(out_status, (int)min((long long)F.cap_n * N, 0x7fffffffLL));
+        RN_CHECK_LAUNCH("rn_postprocess/status");
+        return 0;
+    }
+
+    const int S = N * C;
+    segment_scan_kernel<<<1, 1024, 0, s>>>(w.seg_count, S, w.seg_off, w.cursor, w.pool_count, (u32)cand_capacity, out_status);
+    RN_CHECK_LAUNCH("rn_postprocess/segment_scan");
+    scatter_kernel<<<RN_SM_COUNT_B200 * 4, 256, 0, s>>>(w.pool_key, w.pool_seg, w.pool_count, (u32)cand_capacity, w.cursor,
+                                                        w.sorted_key);
+    RN_CHECK_LAUNCH("rn_postprocess/scatter");
+
+    NmsParams M;
+    M.bbox = (const float4 *)bbox; M.anchors = (const float4 *)anchors; M.im_hw = im_hw; M.boxes = nullptr;
+    M.keep_flags = nullptr; M.A = A; M.anchor_stride = anchor_image_stride; M.C = C; M.thr = thr_f; M.wts = F.wts; M.seg_off = w.seg_off;
+    M.sorted_key = w.sorted_key; M.kept_key = w.kept_key; M.kept_box = w.kept_box; M.kept_count = w.kept_count;
+    nms_kernel<false><<<S, NMS_CHUNK, 0, s>>>(M);
+    RN_CHECK_LAUNCH("rn_postprocess/nms");
+
+    TopkParams T;
+    T.seg_off = w.seg_off; T.kept_count = w.kept_count; T.kept_key = w.kept_key; T.kept_box = w.kept_box;
+    T.C = C; T.max_det = max_det; T.out_boxes = out_boxes; T.out_scores = out_scores;
+    T.out_labels = (long long *)out_labels; T.out_count = out_count;
+    const size_t topk_smem = ((size_t)C + 1 + TOPK_CACHE) * sizeof(u32);
+    if (topk_smem > 48 * 1024)
+        cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem);
+    image_topk_kernel<<<N, TOPK_BLOCK, topk_smem, s>>>(T);
+    RN_CHECK_LAUNCH("rn_postprocess/image_topk");
+    return 0;
+}
+
 extern "C" int rn_postprocess(const float *logits, const float *bbox, const float *anchors,
                               int64_t anchor_image_stride, const int32_t *im_hw, int N,
                               int64_t A, int C, float score_thr, double nms_thr, int max_det,
@@ -1117,53 +1172,205 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
     }
     RN_CHECK_LAUNCH("rn_postprocess/score_filter");
 
-    // round the double threshold DOWN to fp32: (double)ovr > thr  <=>  ovr > thr_f  for every fp32 ovr
-    float thr_f = (float)nms_thr;
-    if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
+    return pp_tail(w, F, bbox, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
+                   level_off_host, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count,
+                   out_status, s);
+}
 
-    if (lazy) {
-        LazyParams Z;
-        Z.bbox = (const float4 *)bbox; Z.anchors = (const float4 *)anchors; Z.im_hw = im_hw; Z.A = A;
-        Z.anchor_stride = anchor_image_stride; Z.C = C; Z.N = N; Z.thr = thr_f; Z.wts = F.wts; Z.max_det = max_det;
-        Z.cand_key = w.pool_key; Z.img_count = w.img_count; Z.cap_n = F.cap_n; Z.out_boxes = out_boxes;
-        Z.out_scores = out_scores; Z.out_labels = (long long *)out_labels; Z.out_count = out_count; Z.status = out_status;
-        Z.topk = pre_nms_topk; Z.nlev = pre_nms_topk ? num_levels : 0;
-        for (int l = 0; l <= RN_MAX_LEVELS; ++l)
-            Z.lvl_off[l] = (pre_nms_topk && l <= num_levels) ? (long long)level_off_host[l] : (long long)A;
-        const size_t smem = ((sizeof(LazySmem) + 15) & ~(size_t)15) + (size_t)LZ_CACHE * sizeof(u64);
-        cudaFuncSetAttribute(lazy_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lazy_nms_kernel<<<N, LZ_BLOCK, smem, s>>>(Z);
-        RN_CHECK_LAUNCH("rn_postprocess/lazy_nms");
-        // status[1] = capacity (N * cap_n) is written by a 1-thread epilogue to keep the call async
-        set_status_capacity_kernel<<<1, 1, 0, s>>>(out_status, (int)min((long long)F.cap_n * N, 0x7fffffffLL));
-        RN_CHECK_LAUNCH("rn_postprocess/status");
-        return 0;
+// ---- per-level NCHW inputs ------------------------------------------------------------
+// The filter streams each level's conv output [N, na*C, H, W] as the flat array it is (a 128-bit load
+// may straddle two channel planes: only the rare survivors decompose their flat index into
+// (anchor, class)); the box activations (1/20 of the bytes) are gathered once into [N,A,4] for the
+// NMS kernels' random access.
+struct LevelFilterParams {
+    const float *cls;        // one level, [N, na*C*HW] flat
+    long long len;           // na*C*HW
+    int HW, na, C;
+    long long lvl_off;
+};
+
+template <bool LAZY>
+__device__ __noinline__ void emit_candidates_level(const FilterParams &P, const LevelFilterParams &Q, float4 v, int nvals,
+                                                   int n, long long e0, u64 *st_key, u32 *st_seg, int *st_n) {
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < nvals; ++k) {
+        if (!(vals[k] > P.x_lo)) continue;
+        const float s = rn::sigmoid_ref(vals[k]);
+        if (!(s > P.thr)) continue;
+        const long long e = e0 + k;
+        const int ch = (int)(e / Q.HW), pos = (int)(e - (long long)ch * Q.HW);
+        const int a = ch / Q.C, c = ch - a * Q.C;
+        const long long anchor = Q.lvl_off + (long long)pos * Q.na + a;
+        const u32 lo = LAZY ? (u32)((long long)c * P.A + anchor) : (u32)anchor;
+        const u64 key = ((u64)(~__float_as_uint(s)) << 32) | (u64)lo;
+        const u32 seg = (u32)(n * P.C + c);
+        const int slot = atomicAdd(st_n, 1);
+        if (slot < PP_WSTAGE) {
+            st_key[slot] = key;
+            if (!LAZY) st_seg[slot] = seg;
+        } else if (LAZY) {
+            const u32 gp = atomicAdd(P.w.img_count + n, 1u);
+            if (gp < P.cap_n) P.w.pool_key[(size_t)n * P.cap_n + gp] = key;
+        } else {
+            const u32 gp = atomicAdd(P.w.pool_count, 1u);
+            if (gp < P.cap) {
+                P.w.pool_key[gp] = key;
+                P.w.pool_seg[gp] = seg;
+                atomicAdd(P.w.seg_count + seg, 1);
+            }
+        }
     }
+}
 
-    const int S = N * C;
-    segment_scan_kernel<<<1, 1024, 0, s>>>(w.seg_count, S, w.seg_off, w.cursor, w.pool_count, (u32)cand_capacity, out_status);
-    RN_CHECK_LAUNCH("rn_postprocess/segment_scan");
-    scatter_kernel<<<RN_SM_COUNT_B200 * 4, 256, 0, s>>>(w.pool_key, w.pool_seg, w.pool_count, (u32)cand_capacity, w.cursor,
-                                                        w.sorted_key);
-    RN_CHECK_LAUNCH("rn_postprocess/scatter");
+constexpr int LVF_SPAN = 8192;     // floats per warp task
 
-    NmsParams M;
-    M.bbox = (const float4 *)bbox; M.anchors = (const float4 *)anchors; M.im_hw = im_hw; M.boxes = nullptr;
-    M.keep_flags = nullptr; M.A = A; M.anchor_stride = anchor_image_stride; M.C = C; M.thr = thr_f; M.wts = F.wts; M.seg_off = w.seg_off;
-    M.sorted_key = w.sorted_key; M.kept_key = w.kept_key; M.kept_box = w.kept_box; M.kept_count = w.kept_count;
-    nms_kernel<false><<<S, NMS_CHUNK, 0, s>>>(M);
-    RN_CHECK_LAUNCH("rn_postprocess/nms");
+template <int VEC, bool LAZY>
+__global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_levels_kernel(const __grid_constant__ FilterParams P,
+                                                                          const __grid_constant__ LevelFilterParams Q) {
+    __shared__ u64 s_key[PP_BLOCK / 32][PP_WSTAGE];
+    __shared__ u32 s_seg[LAZY ? 1 : PP_BLOCK / 32][LAZY ? 1 : PP_WSTAGE];
+    __shared__ int s_n[PP_BLOCK / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.y;
+    const long long e_begin = ((long long)blockIdx.x * (PP_BLOCK / 32) + warp) * LVF_SPAN;
+    if (e_begin >= Q.len) return;
+    const int span = (int)min((long long)LVF_SPAN, Q.len - e_begin);
+    const float *src = Q.cls + (long long)n * Q.len + e_begin;
+    u64 *st_key = s_key[warp];
+    u32 *st_seg = LAZY ? nullptr : s_seg[warp];
+    int *st_n = &s_n[warp];
+    if (lane == 0) *st_n = 0;
+    __syncwarp();
+    const int nvec = span / VEC;
+    for (int base = 0; base < nvec; base += 32 * PP_U) {
+        float4 v[PP_U];
+#pragma unroll
+        for (int u = 0; u < PP_U; ++u) {
+            const int f = base + u * 32 + lane;
+            v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (f < nvec) {
+                if (VEC == 4) v[u] = rn::ld_stream_f4((const float4 *)src + f);
+                else v[u].x = __ldg(src + f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PP_U; ++u) {
+            const float vmax = VEC == 4 ? fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)) : v[u].x;
+            if (vmax > P.x_lo)
+                emit_candidates_level<LAZY>(P, Q, v[u], VEC, n, e_begin + (long long)(base + u * 32 + lane) * VEC, st_key,
+                                            st_seg, st_n);
+        }
+    }
+    __syncwarp();
+    const int staged = min(*st_n, PP_WSTAGE);
+    if (staged == 0) return;
+    u32 gbase = 0;
+    if (lane == 0) gbase = atomicAdd(LAZY ? P.w.img_count + n : P.w.pool_count, (u32)staged);
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);
+    for (int i = lane; i < staged; i += 32) {
+        const u32 gp = gbase + (u32)i;
+        if (LAZY) {
+            if (gp < P.cap_n) P.w.pool_key[(size_t)n * P.cap_n + gp] = st_key[i];
+        } else if (gp < P.cap) {
+            P.w.pool_key[gp] = st_key[i];
+            P.w.pool_seg[gp] = st_seg[i];
+            atomicAdd(P.w.seg_count + st_seg[i], 1);
+        }
+    }
+}
 
-    TopkParams T;
-    T.seg_off = w.seg_off; T.kept_count = w.kept_count; T.kept_key = w.kept_key; T.kept_box = w.kept_box;
-    T.C = C; T.max_det = max_det; T.out_boxes = out_boxes; T.out_scores = out_scores;
-    T.out_labels = (long long *)out_labels; T.out_count = out_count;
-    const size_t topk_smem = ((size_t)C + 1 + TOPK_CACHE) * sizeof(u32);
-    if (topk_smem > 48 * 1024)
-        cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem);
-    image_topk_kernel<<<N, TOPK_BLOCK, topk_smem, s>>>(T);
-    RN_CHECK_LAUNCH("rn_postprocess/image_topk");
-    return 0;
+// box level [N, na*4, H, W] -> rows lvl_off.. of [N, A, 4]
+__global__ void __launch_bounds__(256) gather_bbox_level_kernel(const float *__restrict__ box, int HW, int na, long long A,
+                                                                long long lvl_off, float4 *__restrict__ out) {
+    const int n = blockIdx.y;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;     // idx = a*HW + pos (pos fastest: coalesced reads)
+    if (idx >= (long long)na * HW) return;
+    const int a = (int)(idx / HW), pos = (int)(idx - (long long)a * HW);
+    const float *b0 = box + ((long long)(n * na + a) * 4) * HW + pos;
+    out[(long long)n * A + lvl_off + (long long)pos * na + a] =
+        make_float4(__ldg(b0), __ldg(b0 + HW), __ldg(b0 + 2LL * HW), __ldg(b0 + 3LL * HW));
+}
+
+extern "C" size_t rn_postprocess_levels_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det) {
+    const size_t base = rn_postprocess_workspace_bytes(N, A, C, cand_capacity, max_det);
+    return base ? align_up(base, 256) + (size_t)N * (size_t)A * 16 : 0;
+}
+
+extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const float *const *bbox_levels_host,
+                                     const int32_t *level_desc_host, int num_levels, const float *anchors,
+                                     int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A, int C,
+                                     float score_thr, double nms_thr, int max_det, const float *weights_host,
+                                     int pre_nms_topk, int algo, int64_t cand_capacity, float *out_boxes,
+                                     float *out_scores, int64_t *out_labels, int32_t *out_count, int32_t *out_status,
+                                     void *workspace, size_t workspace_bytes, rn_stream_t stream) {
+    RN_CHECK_ARG(cls_levels_host && bbox_levels_host && level_desc_host && anchors && im_hw && weights_host && out_boxes &&
+                     out_scores && out_labels && out_count && out_status && workspace,
+                 RN_E_BADARG, "rn_postprocess_levels: null pointer");
+    RN_CHECK_ARG(num_levels >= 1 && num_levels <= RN_MAX_LEVELS, RN_E_TOOLARGE, "rn_postprocess_levels: bad num_levels");
+    RN_CHECK_ARG(N > 0 && A > 0 && C > 0 && N <= 65535 && C <= 8192 && A < (1LL << 32), RN_E_BADARG, "rn_postprocess_levels: bad N/A/C");
+    RN_CHECK_ARG(max_det >= 1 && max_det <= MAX_DET_CAP, RN_E_TOOLARGE, "rn_postprocess_levels: bad max_det");
+    RN_CHECK_ARG(cand_capacity >= 1 && cand_capacity < 0x7fffffffLL, RN_E_BADARG, "rn_postprocess_levels: bad cand_capacity");
+    RN_CHECK_ARG((size_t)N * C < 0x7fffffffULL, RN_E_TOOLARGE, "rn_postprocess_levels: N*C too large");
+    RN_CHECK_ARG(algo == RN_PP_LAZY || algo == RN_PP_GENERAL, RN_E_BADARG, "rn_postprocess_levels: unknown algo %d", algo);
+    RN_CHECK_ARG(algo != RN_PP_LAZY || (unsigned long long)A * (unsigned long long)C < (1ULL << 32), RN_E_TOOLARGE,
+                 "rn_postprocess_levels: the lazy algorithm needs A*C < 2^32");
+    RN_CHECK_ARG(pre_nms_topk >= 0 && (pre_nms_topk == 0 || algo == RN_PP_LAZY), RN_E_BADARG,
+                 "rn_postprocess_levels: pre_nms_topk needs algo = RN_PP_LAZY");
+    int64_t level_off[RN_MAX_LEVELS + 1];
+    level_off[0] = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const int32_t *d = level_desc_host + 3 * l;
+        RN_CHECK_ARG(d[0] >= 0 && d[1] >= 0 && d[2] >= 1, RN_E_BADARG, "rn_postprocess_levels: bad level %d descriptor", l);
+        level_off[l + 1] = level_off[l] + (int64_t)d[0] * d[1] * d[2];
+    }
+    RN_CHECK_ARG(level_off[num_levels] == A, RN_E_BADARG, "rn_postprocess_levels: levels hold %lld anchors, A = %lld",
+                 (long long)level_off[num_levels], (long long)A);
+    PPWorkspace w = carve(workspace, N, C, cand_capacity);
+    const size_t box_off = align_up(w.total_bytes, 256);
+    RN_CHECK_ARG(workspace_bytes >= box_off + (size_t)N * (size_t)A * 16, RN_E_WORKSPACE, "rn_postprocess_levels: workspace too small");
+    float4 *bbox_nac = (float4 *)((char *)workspace + box_off);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, w.zero_bytes, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out_status, 0, 4 * sizeof(int32_t), s);
+    if (e != cudaSuccess) { rn_set_error("rn_postprocess_levels: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    const float thr = score_thr;
+    float x_lo;
+    if (!(thr > 0.0f)) x_lo = -INFINITY;
+    else if (thr >= 1.0f) x_lo = INFINITY;
+    else {
+        double xt = log((double)thr / (1.0 - (double)thr));
+        x_lo = (float)(xt - 1e-3 * fmax(1.0, fabs(xt)));
+    }
+    const bool lazy = algo == RN_PP_LAZY;
+    FilterParams F;
+    F.logits = nullptr; F.bbox = bbox_nac; F.anchors = (const float4 *)anchors; F.im_hw = im_hw;
+    F.A = A; F.anchor_stride = anchor_image_stride; F.C = C; F.magic = 0; F.x_lo = x_lo; F.thr = thr; F.cap = (u32)cand_capacity;
+    F.cap_n = (u32)max((int64_t)1, cand_capacity / N); F.w = w;
+    F.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
+    for (int l = 0; l < num_levels; ++l) {
+        const int32_t *d = level_desc_host + 3 * l;
+        const int HW = d[0] * d[1], na = d[2];
+        if (HW == 0) continue;
+        RN_CHECK_ARG(cls_levels_host[l] && bbox_levels_host[l], RN_E_BADARG, "rn_postprocess_levels: null level %d", l);
+        dim3 gg((unsigned)(((long long)na * HW + 255) / 256), (unsigned)N);
+        gather_bbox_level_kernel<<<gg, 256, 0, s>>>(bbox_levels_host[l], HW, na, A, level_off[l], bbox_nac);
+        RN_CHECK_LAUNCH("rn_postprocess_levels/gather_bbox");
+        LevelFilterParams Q;
+        Q.cls = cls_levels_host[l]; Q.len = (long long)na * C * HW; Q.HW = HW; Q.na = na; Q.C = C; Q.lvl_off = level_off[l];
+        const bool vec4 = (Q.len % 4 == 0) && (((uintptr_t)Q.cls & 15) == 0);
+        const long long tasks = (Q.len + LVF_SPAN - 1) / LVF_SPAN;
+        dim3 grid((unsigned)((tasks + PP_BLOCK / 32 - 1) / (PP_BLOCK / 32)), (unsigned)N);
+        if (lazy) {
+            if (vec4) score_filter_levels_kernel<4, true><<<grid, PP_BLOCK, 0, s>>>(F, Q);
+            else score_filter_levels_kernel<1, true><<<grid, PP_BLOCK, 0, s>>>(F, Q);
+        } else {
+            if (vec4) score_filter_levels_kernel<4, false><<<grid, PP_BLOCK, 0, s>>>(F, Q);
+            else score_filter_levels_kernel<1, false><<<grid, PP_BLOCK, 0, s>>>(F, Q);
+        }
+        RN_CHECK_LAUNCH("rn_postprocess_levels/score_filter");
+    }
+    return pp_tail(w, F, (const float *)bbox_nac, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
+                   level_off, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count, out_status, s);
 }
 
 extern "C" int rn_nms_segments(const float *boxes, const int32_t *seg_off, int num_segments, int64_t total_boxes,

@@ -18,7 +18,7 @@ from torch import Tensor
 from . import _native
 from .config import BBOX_REG_WEIGHTS, MAX_DETECTIONS_PER_IMAGE, NMS_THRES, SCORE_THRES
 from .box_utils import _REG_WEIGHTS_C
-from .losses import _shared_anchors
+from .losses import _f32_contig, _level_desc, _ptr_array, _shared_anchors
 
 _HW_CACHE: Dict[Tuple, Tensor] = {}
 _WS_CACHE: Dict[Tuple, Tensor] = {}
@@ -66,18 +66,32 @@ class PendingDetections:
         a = self._a
         lib = _native.load()
         dev, N, A, C = a["dev"], a["N"], a["A"], a["C"]
-        ws_bytes = lib.rn_postprocess_workspace_bytes(N, A, C, a["cap"], a["max_det"])
-        ws = _workspace(ws_bytes, dev)
         meta = torch.empty((N + 4,), dtype=torch.int32, device=dev)   # counts [N] + status [4]
+        outs = (_native.ptr(a["out_boxes"]), _native.ptr(a["out_scores"]), _native.ptr(a["out_labels"]),
+                meta.data_ptr(), meta.data_ptr() + 4 * N)
+        algo_id = 1 if a["use_general"] else 0
         with torch.cuda.device(dev):
-            rc = lib.rn_postprocess(_native.ptr(a["x"], torch.float32, "cls_preds"), _native.ptr(a["b"], torch.float32, "bbox_preds"),
-                                    _native.ptr(a["anchors"], torch.float32, "anchors"), a["anchor_stride"], _native.ptr(a["hw"]),
-                                    N, A, C, a["score_thres"], a["nms_thres"], a["max_det"], _REG_WEIGHTS_C, a["topk"],
-                                    a["lvl"], a["nlev"], 1 if a["use_general"] else 0, a["cap"],
-                                    _native.ptr(a["out_boxes"]), _native.ptr(a["out_scores"]), _native.ptr(a["out_labels"]),
-                                    meta.data_ptr(), meta.data_ptr() + 4 * N, _native.ptr(ws), ws_bytes,
-                                    _native.stream_ptr(dev))
-        _native.check(rc, "rn_postprocess")
+            if a.get("levels") is not None:               # raw per-level conv outputs (row N1)
+                xs, bs, desc = a["levels"]
+                ws_bytes = lib.rn_postprocess_levels_workspace_bytes(N, A, C, a["cap"], a["max_det"])
+                ws = _workspace(ws_bytes, dev)
+                rc = lib.rn_postprocess_levels(_ptr_array(xs), _ptr_array(bs), desc, len(xs),
+                                               _native.ptr(a["anchors"], torch.float32, "anchors"), a["anchor_stride"],
+                                               _native.ptr(a["hw"]), N, A, C, a["score_thres"], a["nms_thres"], a["max_det"],
+                                               _REG_WEIGHTS_C, a["topk"], algo_id, a["cap"], *outs,
+                                               _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+                what = "rn_postprocess_levels"
+            else:
+                ws_bytes = lib.rn_postprocess_workspace_bytes(N, A, C, a["cap"], a["max_det"])
+                ws = _workspace(ws_bytes, dev)
+                rc = lib.rn_postprocess(_native.ptr(a["x"], torch.float32, "cls_preds"),
+                                        _native.ptr(a["b"], torch.float32, "bbox_preds"),
+                                        _native.ptr(a["anchors"], torch.float32, "anchors"), a["anchor_stride"],
+                                        _native.ptr(a["hw"]), N, A, C, a["score_thres"], a["nms_thres"], a["max_det"],
+                                        _REG_WEIGHTS_C, a["topk"], a["lvl"], a["nlev"], algo_id, a["cap"], *outs,
+                                        _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+                what = "rn_postprocess"
+        _native.check(rc, what)
         self._host = torch.empty((N + 4,), dtype=torch.int32, pin_memory=True)
         self._host.copy_(meta, non_blocking=True)       # the single D2H copy of the path
         self._event = torch.cuda.Event()
@@ -148,6 +162,30 @@ def postprocess_batch_async(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tens
     return PendingDetections(args)
 
 
+def postprocess_levels_async(cls_levels: Sequence[Tensor], bbox_levels: Sequence[Tensor], num_classes: int, anchors: Tensor,
+                             anchor_stride: int, im_szs: Sequence[Tuple[int, int]], score_thres: float, nms_thres: float,
+                             max_det: int, pre_nms_topk: Optional[int] = None, cand_capacity: Optional[int] = None,
+                             algo: str = "auto") -> PendingDetections:
+    """:func:`postprocess_batch_async` on the RAW per-level conv outputs."""
+    xs, bs = [_f32_contig(t) for t in cls_levels], [_f32_contig(t) for t in bbox_levels]
+    desc, A, N = _level_desc(xs, bs, num_classes)
+    dev, C = xs[0].device, num_classes
+    if len(im_szs) != N:
+        raise ValueError(f"{len(im_szs)} image sizes for {N} images")
+    topk = int(pre_nms_topk) if pre_nms_topk else 0
+    if topk and (algo == "general" or A * C >= (1 << 32)):
+        raise ValueError("pre_nms_topk is implemented by the lazy algorithm only (needs A*C < 2^32)")
+    args = dict(dev=dev, N=N, A=A, C=C, levels=(xs, bs, desc), anchors=anchors, anchor_stride=anchor_stride,
+                hw=_image_sizes_tensor(im_szs, dev), score_thres=float(score_thres), nms_thres=float(nms_thres),
+                max_det=int(max_det), topk=topk, lvl=None, nlev=0, algo=algo,
+                use_general=(algo == "general" or (A * C >= (1 << 32))),
+                cap=int(cand_capacity) if cand_capacity else default_candidate_capacity(N, A, C),
+                out_boxes=torch.empty((N, max_det, 4), dtype=torch.float32, device=dev),
+                out_scores=torch.empty((N, max_det), dtype=torch.float32, device=dev),
+                out_labels=torch.empty((N, max_det), dtype=torch.int64, device=dev))
+    return PendingDetections(args)
+
+
 def postprocess_batch(*args, **kw):
     """Synchronous form of :func:`postprocess_batch_async`: returns
     (boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int])."""
@@ -169,9 +207,16 @@ def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Ten
                              im_szs: List[Tuple[int, int]]) -> PendingDetections:
     """Same arguments and side effects as :func:`process_detections`; returns a handle whose
     ``.detections()`` yields the reference's ``List[Dict]``."""
+    an, stride = _shared_anchors(anchors)
+    if "cls_levels" in outputs:                       # raw per-level conv outputs (SURVEY.md 8f N1)
+        cls_levels, box_levels = outputs.pop("cls_levels"), outputs.pop("bbox_levels")
+        C = getattr(self, "num_classes", None) or cls_levels[0].shape[1] // (box_levels[0].shape[1] // 4)
+        return postprocess_levels_async(cls_levels, box_levels, C, an, stride, im_szs,
+                                        getattr(self, "score_thres", SCORE_THRES), getattr(self, "nms_thres", NMS_THRES),
+                                        getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE),
+                                        getattr(self, "pre_nms_topk", None))
     class_logits = outputs.pop("cls_preds")
     bboxes = outputs.pop("bbox_preds")
-    an, stride = _shared_anchors(anchors)
     return postprocess_batch_async(class_logits, bboxes, an, stride, im_szs,
                                    getattr(self, "score_thres", SCORE_THRES), getattr(self, "nms_thres", NMS_THRES),
                                    getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE),

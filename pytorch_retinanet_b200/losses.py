@@ -105,6 +105,109 @@ class _FusedRetinaNetLoss(torch.autograd.Function):
         return outs[0], outs[1], None, None, None, None
 
 
+def _level_desc(cls_levels: Sequence[Tensor], box_levels: Sequence[Tensor], C: int):
+    """(ctypes level_desc [L][3] = H,W,na ; total anchors A ; N) after validating the per-level NCHW tensors."""
+    import ctypes
+    if len(cls_levels) != len(box_levels) or not len(cls_levels):
+        raise ValueError("cls_levels and bbox_levels must be non-empty lists of equal length")
+    N = cls_levels[0].shape[0]
+    desc, A = [], 0
+    for x, b in zip(cls_levels, box_levels):
+        if x.dim() != 4 or b.dim() != 4 or x.shape[0] != N or b.shape[0] != N or x.shape[-2:] != b.shape[-2:]:
+            raise ValueError(f"level tensors must be [N, na*C, H, W] / [N, na*4, H, W]; got {tuple(x.shape)} / {tuple(b.shape)}")
+        na = b.shape[1] // 4
+        if b.shape[1] != na * 4 or x.shape[1] != na * C:
+            raise ValueError(f"level channels {x.shape[1]} / {b.shape[1]} do not match na*C / na*4 with C={C}")
+        H, W = int(x.shape[2]), int(x.shape[3])
+        desc += [H, W, na]
+        A += H * W * na
+    return (ctypes.c_int32 * len(desc))(*desc), A, N
+
+
+def _ptr_array(tensors: Sequence[Optional[Tensor]]):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def _f32_contig(t: Tensor) -> Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def fused_loss_forward_levels(cls_levels, box_levels, anchors: Tensor, anchor_stride: int, packed: PackedTargets, C: int,
+                              alpha, gamma, beta, match_thr, back_thr, batch_div, want_grad: bool):
+    """rn_match + rn_loss_levels on the RAW per-level conv outputs: no permute/cat pass."""
+    lib = _native.load()
+    xs, bs = [_f32_contig(t) for t in cls_levels], [_f32_contig(t) for t in box_levels]
+    desc, A, N = _level_desc(xs, bs, C)
+    dev = xs[0].device
+    if packed.num_images != N:
+        raise ValueError(f"{packed.num_images} targets for {N} images")
+    if anchors.shape[-2] != A:
+        raise ValueError(f"anchors hold {anchors.shape[-2]} rows, the levels {A}")
+    _, codes, fg = match_batch(anchors, anchor_stride, packed, A, match_thr, back_thr, False, True)
+    out_total = torch.empty((4,), dtype=torch.float32, device=dev)
+    out_image = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    gxs = [torch.empty_like(t) for t in xs] if want_grad else None
+    gbs = [torch.empty_like(t) for t in bs] if want_grad else None
+    L = len(xs)
+    ws_bytes = lib.rn_loss_levels_workspace_bytes(N, desc, L)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.rn_loss_levels(_ptr_array(xs), _ptr_array(bs), desc, L, _native.ptr(anchors, torch.float32, "anchors"),
+                                anchor_stride, _native.ptr(packed.boxes), _native.ptr(packed.offsets), _native.ptr(codes),
+                                _native.ptr(fg), N, A, C, float(alpha), float(gamma), float(beta), _REG_WEIGHTS_C,
+                                float(batch_div), _native.ptr(out_image), _native.ptr(out_total),
+                                _ptr_array(gxs) if want_grad else None, _ptr_array(gbs) if want_grad else None,
+                                _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+    _native.check(rc, "rn_loss_levels")
+    return out_total, out_image, gxs, gbs
+
+
+class _FusedRetinaNetLossLevels(torch.autograd.Function):
+    """inputs: anchors, anchor_stride, packed, hp, C, L, then L class-level tensors and L box-level tensors."""
+
+    @staticmethod
+    def forward(ctx, anchors, anchor_stride, packed, hp, C, L, *levels):
+        cls_levels, box_levels = levels[:L], levels[L:]
+        want = any(t.requires_grad for t in levels)
+        total, image, gxs, gbs = fused_loss_forward_levels(cls_levels, box_levels, anchors, anchor_stride, packed, C,
+                                                           hp["alpha"], hp["gamma"], hp["beta"], hp["match_thr"],
+                                                           hp["back_thr"], hp["batch_div"], want)
+        group = hp.get("all_reduce_group", False)
+        if group is not False:
+            import torch.distributed as dist
+            dist.all_reduce(total, group=group)
+        ctx.grads = (gxs, gbs)
+        ctx.L = L
+        ctx.in_dtypes = [t.dtype for t in levels]
+        ctx.mark_non_differentiable(image, total)
+        return total[0], total[1], image, total
+
+    @staticmethod
+    def backward(ctx, g_cls, g_reg, _g_image, _g_total):
+        gxs, gbs = ctx.grads
+        ctx.grads = (None, None)
+        L = ctx.L
+        if gxs is None:
+            return (None,) * (6 + 2 * L)
+        lib = _native.load()
+        outs = []
+        for bufs, g in ((gxs, g_cls), (gbs, g_reg)):
+            gs = None if g is None else g.detach().to(device=bufs[0].device, dtype=torch.float32).contiguous()
+            for buf in bufs:
+                if gs is None:
+                    outs.append(None)
+                    continue
+                with torch.cuda.device(buf.device):
+                    rc = lib.rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
+                                                       _native.stream_ptr(buf.device))
+                _native.check(rc, "rn_scale_by_device_scalar")
+                outs.append(buf)
+        outs = [o if (o is None or dt == torch.float32) else o.to(dt) for o, dt in zip(outs, ctx.in_dtypes)]
+        return (None,) * 6 + tuple(outs)
+
+
 class _DenseLoss(torch.autograd.Function):
     """sum-reduced element-wise loss with its gradient produced in the same pass (focal or smooth-L1)."""
 
@@ -178,6 +281,8 @@ class RetinaNetLosses(nn.Module):
 
     def forward(self, targets: List[Dict[str, Tensor]], head_outputs: Dict[str, Tensor],
                 anchors: List[Tensor]) -> Dict[str, Tensor]:
+        if "cls_levels" in head_outputs:        # raw per-level conv outputs: no permute/cat pass
+            return self.forward_levels(targets, head_outputs["cls_levels"], head_outputs["bbox_levels"], anchors)
         clas_preds, bbox_preds = head_outputs["cls_preds"], head_outputs["bbox_preds"]
         if clas_preds.shape[-1] != self.n_c:
             raise ValueError(f"cls_preds has {clas_preds.shape[-1]} classes, expected {self.n_c}")
@@ -185,4 +290,21 @@ class RetinaNetLosses(nn.Module):
         packed = PackedTargets([t["boxes"] for t in targets], [t["labels"] for t in targets], clas_preds.device)
         c, r, image, _ = _FusedRetinaNetLoss.apply(clas_preds, bbox_preds, an, stride, packed, self._hp(len(targets)))
         self.last_per_image = image   # [N,3]: cls_i, reg_i, F_i (device tensor, no sync)
+        return {"classification_loss": c, "regression_loss": r}
+
+    def forward_levels(self, targets: List[Dict[str, Tensor]], cls_levels: Sequence[Tensor], bbox_levels: Sequence[Tensor],
+                       anchors: List[Tensor], hp_extra: Optional[dict] = None) -> Dict[str, Tensor]:
+        """Same loss as :meth:`forward`, computed directly on the head's per-level conv outputs
+        ``cls_levels[l] = [N, na*C, H_l, W_l]`` / ``bbox_levels[l] = [N, na*4, H_l, W_l]`` (what
+        ``RetinaNetClassSubnet`` / ``RetinaNetBoxSubnet`` hold before ``view/permute/contiguous/cat``,
+        layers.py:189-195, 253-259).  Gradients come back in the same layout."""
+        an, stride = _shared_anchors(anchors)
+        packed = PackedTargets([t["boxes"] for t in targets], [t["labels"] for t in targets], cls_levels[0].device)
+        hp = self._hp(len(targets))
+        if hp_extra:
+            hp.update(hp_extra)
+        L = len(cls_levels)
+        c, r, image, total = _FusedRetinaNetLossLevels.apply(an, stride, packed, hp, self.n_c, L, *cls_levels, *bbox_levels)
+        self.last_per_image = image
+        self.last_stats = total
         return {"classification_loss": c, "regression_loss": r}

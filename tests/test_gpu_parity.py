@@ -455,6 +455,54 @@ def test_postprocess_pre_nms_topk_extension(P, cid, topk):
         assert_dets_equal(got, plain, exact=True, ctx="no-op topk")
 
 
+@pytest.mark.parametrize("cid,n_img", [(2, 16), (5, 6)])
+def test_full_batch_properties(P, cid, n_img):
+    """Size-independent properties at the full per-image sizes of configs 2 (batch 16) and 5 (G=500):
+    batch loss = mean of the single-image losses, batch gradients = single-image gradients / N,
+    batch detections = single-image detections, invariance under a permutation of the images,
+    linearity of backward in grad_output, bit-reproducibility, and loss consistency with the matcher
+    (F_i from the loss == number of non-negative matches)."""
+    from types import SimpleNamespace
+    cfg = S.CONFIGS[cid]
+    b = S.make_batch(cfg, 40, n_img)
+    dev = torch.device("cuda")
+    anc = b["anchors"].to(dev)
+    tg = to_cuda_targets(b["targets"])
+    x, bb = b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
+    L = P.RetinaNetLosses(cfg.num_classes)
+    xb, bbb = x.clone().requires_grad_(True), bb.clone().requires_grad_(True)
+    out = L(tg, {"cls_preds": xb, "bbox_preds": bbb}, [anc] * n_img)
+    (out["classification_loss"] + 3.0 * out["regression_loss"]).backward()
+    per_image = L.last_per_image.clone()
+    stub = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
+    dets = P.process_detections(stub, {"cls_preds": x, "bbox_preds": bb}, [anc] * n_img, b["im_szs"])
+    cls_sum = reg_sum = 0.0
+    for i in (0, n_img // 2, n_img - 1):
+        xi, bi = x[i:i + 1].clone().requires_grad_(True), bb[i:i + 1].clone().requires_grad_(True)
+        oi = L(tg[i:i + 1], {"cls_preds": xi, "bbox_preds": bi}, [anc])
+        (oi["classification_loss"] + oi["regression_loss"]).backward()
+        assert rel_close(oi["classification_loss"], per_image[i, 0], 1e-6) and rel_close(oi["regression_loss"], per_image[i, 1], 1e-6)
+        assert rel_close(xb.grad[i] * n_img, xi.grad[0], 1e-6, 1e-12)
+        assert rel_close(bbb.grad[i] * n_img / 3.0, bi.grad[0], 2e-6, 1e-12)       # linear in grad_output
+        di = P.process_detections(stub, {"cls_preds": x[i:i + 1], "bbox_preds": bb[i:i + 1]}, [anc], b["im_szs"][i:i + 1])[0]
+        assert_dets_equal(dets[i], di, exact=True, ctx=f"image {i}")
+        m = P.matcher(anc, tg[i]["boxes"])
+        assert int(per_image[i, 2]) == int((m >= 0).sum())
+    assert rel_close(out["classification_loss"], per_image[:, 0].double().mean(), 1e-6)
+    assert rel_close(out["regression_loss"], per_image[:, 1].double().mean(), 1e-6)
+    perm = torch.randperm(n_img, generator=torch.Generator().manual_seed(1)).tolist()
+    outp = L([tg[i] for i in perm], {"cls_preds": x[perm], "bbox_preds": bb[perm]}, [anc] * n_img)
+    assert rel_close(outp["classification_loss"], out["classification_loss"].detach(), 1e-6)
+    assert torch.equal(L.last_per_image[:, :], per_image[perm])                     # per-image values are bit-stable
+    detp = P.process_detections(stub, {"cls_preds": x[perm], "bbox_preds": bb[perm]}, [anc] * n_img, [b["im_szs"][i] for i in perm])
+    for j, i in enumerate(perm):
+        assert_dets_equal(detp[j], dets[i], exact=True, ctx=f"perm {j}")
+    for d in dets:                                                                  # sorted, capped, labelled 1..C
+        assert d["boxes"].shape[0] <= 100 and bool((d["scores"][:-1] >= d["scores"][1:]).all())
+        assert int(d["labels"].min()) >= 1 and int(d["labels"].max()) <= cfg.num_classes
+        assert bool((d["boxes"][:, 0] >= 0).all()) and bool((d["boxes"][:, 2] <= b["im_szs"][0][1]).all())
+
+
 def test_nms_segments_vs_torchvision(P):
     import ctypes
     import torchvision
