@@ -296,6 +296,36 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(3):
             fn()
         kern[name] = timed(fn, max(5, args.steps))
+
+    # ---- row N1: the same work on the head's raw per-level conv outputs, and the cost of the
+    # reference head's view/permute/contiguous/cat pass that it makes unnecessary (layers.py:189-195, 253-259)
+    n1 = None
+    if not args.no_levels:
+        from pytorch_retinanet_b200.detections import postprocess_levels_async
+        from pytorch_retinanet_b200.losses import fused_loss_forward_levels
+        cls_lv = [t.to(dev) for t in S.nac_to_levels(h_cls, cfg.padded_hw)]
+        box_lv = [t.to(dev) for t in S.nac_to_levels(h_box, cfg.padded_hw)]
+
+        def relayout():
+            outs = []
+            for x in cls_lv:
+                Nn, _, H, W = x.shape
+                outs.append(x.view(Nn, -1, C, H, W).permute(0, 3, 4, 1, 2).contiguous().view(Nn, -1, C))
+            return torch.cat(outs, dim=1)
+
+        lv = {}
+        for name, fn in (("loss_fwd_bwd", lambda: fused_loss_forward_levels(cls_lv, box_lv, anc, 0, packed, C, 0.25, 2.0, 0.1,
+                                                                           0.5, 0.4, float(n_img), True)),
+                         ("postprocess", lambda: postprocess_levels_async(cls_lv, box_lv, C, anc, 0, batch["im_szs"], 0.05, 0.5,
+                                                                          100).result()),
+                         ("reference_head_relayout_cls_fwd", relayout)):
+            for _ in range(3):
+                fn()
+            lv[name] = timed(fn, max(5, args.steps))
+        n1 = {"ms": lv, "note": "loss / post-processing on raw [N, 9*C, H_l, W_l] conv outputs (no permute+cat); "
+                                "reference_head_relayout_cls_fwd = torch time of the re-layout pass this removes (forward only; "
+                                "its backward costs the same again)"}
+        del cls_lv, box_lv
     peak, peak_src = measured_peak_gbs()
     gsum = sum(int(t["boxes"].shape[0]) for t in batch["targets"])
     bytes_fb = n_img * (2 * 4 * A * C + 2 * 16 * A) + 16 * A + 24 * gsum + 12 * n_img     # B_fb
@@ -331,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
             "pipelined": {"value": total / (ms_pipe * 1e-3), "unit": "images/s", "ms_per_step": ms_pipe,
                           "note": "same step with process_detections_async: results of step i read while step i+1 is enqueued"},
             "gpu_launches": args.steps * 8,    # per step: match, loss, finalize, 2x scale (early exit), score filter, lazy NMS, status
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "n1_levels": n1,
         }
         print(json.dumps(line), flush=True)
 
@@ -343,6 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-levels", action="store_true", help="skip the row-N1 (per-level NCHW) timing leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -65,6 +65,18 @@ def default_anchors(padded_hw: Tuple[int, int]) -> torch.Tensor:
     return torch.cat(out)
 
 
+def nac_to_levels(x: torch.Tensor, padded_hw: Tuple[int, int], na: int = 9) -> List[torch.Tensor]:
+    """[N, A, K] (the reference head's output layout) -> the per-level conv outputs [N, na*K, H_l, W_l]
+    it was permuted from (inverse of retinanet/layers.py:189-195); used to feed the row-N1 entry points."""
+    N, _, K = x.shape
+    out, off = [], 0
+    for h, w in grid_sizes(padded_hw):
+        n = h * w * na
+        out.append(x[:, off:off + n].reshape(N, h, w, na, K).permute(0, 3, 4, 1, 2).reshape(N, na * K, h, w).contiguous())
+        off += n
+    return out
+
+
 def _gt_boxes(g: torch.Generator, n: int, hw: Tuple[int, int]) -> torch.Tensor:
     H, W = hw
     boxes = torch.empty((n, 4), dtype=torch.float32)
