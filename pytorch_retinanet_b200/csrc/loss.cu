@@ -359,11 +359,11 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
 // right before this path.  loss_levels_kernel consumes the conv outputs directly (index math only) and
 // writes the gradients back in NCHW, so that pass disappears.  Element (n, a, c, y, x) of a level lives
 // at ((n*na + a)*C + c)*H*W + y*W + x and belongs to anchor lvl_off + (y*W + x)*na + a.
-// One CTA = 128 consecutive positions of one level x all na*C channel planes; the tile's packed codes
-// are staged in shared memory as [a][position]; each warp walks channel planes (4 in flight), each lane
-// owning 4 positions (one 128-bit load when H*W % 4 == 0, else 4 coalesced scalar loads).
+// One CTA = 512 consecutive positions of one level x all na*C channel planes; the tile's packed codes
+// are staged in shared memory as [a][position]; each warp walks whole channel planes of the tile (2 KB
+// contiguous, four 128-bit loads in flight per lane when H*W % 4 == 0, else coalesced scalar loads).
 namespace {
-constexpr int LV_TILE = 128;
+constexpr int LV_TILE = 512;
 constexpr int LV_BLOCK = 256;
 constexpr int LV_MAX_NA = 16;
 constexpr int LV_U = 4;
@@ -403,43 +403,44 @@ __global__ void __launch_bounds__(LV_BLOCK) loss_levels_kernel(const LvlLossPara
     }
     __syncthreads();
 
+    // Each warp walks whole channel planes of the tile: LV_TILE = 512 positions = 2 KB contiguous per plane,
+    // LV_U = 4 x 128-bit loads in flight per lane (lane owns positions u*128 + lane*4 .. +3).
     float acc_neg = 0.0f, acc_pos = 0.0f;
     const int nch = P.na * P.C;
     const long long img_base = (long long)n * nch * P.HW;
-    for (int ch0 = warp; ch0 < nch; ch0 += (LV_BLOCK / 32) * LV_U) {
+    for (int ch = warp; ch < nch; ch += LV_BLOCK / 32) {
+        const float *plane = P.cls + img_base + (long long)ch * P.HW + p0;
         float v[LV_U][4];
-        int ch[LV_U];
 #pragma unroll
         for (int u = 0; u < LV_U; ++u) {
-            ch[u] = ch0 + u * (LV_BLOCK / 32);
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[u][k] = -30.0f;
-            if (ch[u] < nch) {
-                const float *plane = P.cls + img_base + (long long)ch[u] * P.HW + p0;
-                if (VEC == 4) {
-                    if (lane * 4 < np) {
-                        const float4 q = rn::ld_stream_f4((const float4 *)plane + lane);
-                        v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
-                    }
-                } else {
+            if (VEC == 4) {
+                const int p = u * 128 + lane * 4;
+                if (p < np) {
+                    const float4 q = rn::ld_stream_f4((const float4 *)(plane + p));
+                    v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
+                }
+            } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (lane + 32 * k < np) v[u][k] = __ldg(plane + lane + 32 * k);
+                for (int k = 0; k < 4; ++k) {
+                    const int p = u * 128 + k * 32 + lane;
+                    if (p < np) v[u][k] = __ldg(plane + p);
                 }
             }
         }
+        const int a = P.magicC ? (int)__umulhi((unsigned)ch, P.magicC) : ch;  // ch / C (warp-uniform)
+        const int c = ch - a * P.C;
+        float *gplane = WANT_GRAD ? P.gcls + img_base + (long long)ch * P.HW + p0 : nullptr;
 #pragma unroll
         for (int u = 0; u < LV_U; ++u) {
-            if (ch[u] >= nch) continue;                              // warp-uniform
-            const int a = P.magicC ? (int)__umulhi((unsigned)ch[u], P.magicC) : ch[u];  // ch / C
-            const int c = ch[u] - a * P.C;
             int code[4];
             bool use[4];
             float g[4];
             float vmax = -30.0f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int p = VEC == 4 ? lane * 4 + k : lane + 32 * k;
+                const int p = VEC == 4 ? u * 128 + lane * 4 + k : u * 128 + k * 32 + lane;
                 code[k] = s_codes[a][p];
                 use[k] = code[k] != -2;
                 vmax = fmaxf(vmax, use[k] ? v[u][k] : -30.0f);
@@ -466,13 +467,15 @@ __global__ void __launch_bounds__(LV_BLOCK) loss_levels_kernel(const LvlLossPara
             }
             acc_neg += local;
             if (WANT_GRAD) {
-                float *gplane = P.gcls + img_base + (long long)ch[u] * P.HW + p0;
                 if (VEC == 4) {
-                    if (lane * 4 < np) rn::st_stream_f4((float4 *)gplane + lane, make_float4(g[0], g[1], g[2], g[3]));
+                    const int p = u * 128 + lane * 4;
+                    if (p < np) rn::st_stream_f4((float4 *)(gplane + p), make_float4(g[0], g[1], g[2], g[3]));
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (lane + 32 * k < np) gplane[lane + 32 * k] = g[k];
+                    for (int k = 0; k < 4; ++k) {
+                        const int p = u * 128 + k * 32 + lane;
+                        if (p < np) gplane[p] = g[k];
+                    }
                 }
             }
         }

@@ -1184,8 +1184,9 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
 // NMS kernels' random access.
 struct LevelFilterParams {
     const float *cls;        // one level, [N, na*C*HW] flat
-    long long len;           // na*C*HW
+    long long len;           // na*C*HW (< 2^31)
     int HW, na, C;
+    unsigned magicHW, magicC;   // ceil(2^32 / d); 0 when d == 1
     long long lvl_off;
 };
 
@@ -1197,9 +1198,12 @@ __device__ __noinline__ void emit_candidates_level(const FilterParams &P, const 
         if (!(vals[k] > P.x_lo)) continue;
         const float s = rn::sigmoid_ref(vals[k]);
         if (!(s > P.thr)) continue;
-        const long long e = e0 + k;
-        const int ch = (int)(e / Q.HW), pos = (int)(e - (long long)ch * Q.HW);
-        const int a = ch / Q.C, c = ch - a * Q.C;
+        const unsigned e = (unsigned)(e0 + k);                      // < 2^31: exact magic division below
+        int ch = Q.magicHW ? (int)__umulhi(e, Q.magicHW) : (int)e;
+        int pos = (int)e - ch * Q.HW;
+        if (pos < 0) { --ch; pos += Q.HW; }                          // magic quotient can be one too large for big e
+        const int a = Q.magicC ? (int)__umulhi((unsigned)ch, Q.magicC) : ch;
+        const int c = ch - a * Q.C;
         const long long anchor = Q.lvl_off + (long long)pos * Q.na + a;
         const u32 lo = LAZY ? (u32)((long long)c * P.A + anchor) : (u32)anchor;
         const u64 key = ((u64)(~__float_as_uint(s)) << 32) | (u64)lo;
@@ -1357,6 +1361,9 @@ extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const 
         RN_CHECK_LAUNCH("rn_postprocess_levels/gather_bbox");
         LevelFilterParams Q;
         Q.cls = cls_levels_host[l]; Q.len = (long long)na * C * HW; Q.HW = HW; Q.na = na; Q.C = C; Q.lvl_off = level_off[l];
+        RN_CHECK_ARG(Q.len < (1LL << 31), RN_E_TOOLARGE, "rn_postprocess_levels: level %d has more than 2^31 elements per image", l);
+        Q.magicHW = HW == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)HW - 1) / (unsigned)HW);
+        Q.magicC = C == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)C - 1) / (unsigned)C);
         const bool vec4 = (Q.len % 4 == 0) && (((uintptr_t)Q.cls & 15) == 0);
         const long long tasks = (Q.len + LVF_SPAN - 1) / LVF_SPAN;
         dim3 grid((unsigned)((tasks + PP_BLOCK / 32 - 1) / (PP_BLOCK / 32)), (unsigned)N);
