@@ -23,6 +23,7 @@
 // Reductions: fp32 per thread (<= a few hundred terms), fp64 from the warp level on, per-CTA
 // partials to the workspace and a fixed-order final kernel => bit-reproducible.
 #include <algorithm>
+#include <cstring>
 
 #include "loss_math.cuh"
 #include "rn_common.cuh"
@@ -212,54 +213,59 @@ __global__ void __launch_bounds__(LOSS_BLOCK) loss_kernel(const LossParams P) {
     }
 }
 
-// Fixed-order final reduction (one CTA of 1024 threads): warp w reduces images w, w+32, ... over
-// their chunk partials with four independent accumulators per lane (loads in flight), then thread 0
-// sums the images in index order.  The summation order depends only on (N, chunks) => deterministic.
-__global__ void __launch_bounds__(1024) loss_finalize_kernel(const double *__restrict__ partials,
-                                                             const int *__restrict__ fg_count, int N, int chunks,
-                                                             float batch_div, float *__restrict__ out_image,
-                                                             float *__restrict__ out_total) {
-    extern __shared__ double s_img[];   // [N][2]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int n = warp; n < N; n += nw) {
-        const double2 *p = (const double2 *)partials + (long long)n * chunks;
-        double c[4] = {0.0, 0.0, 0.0, 0.0}, r[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = lane; k < chunks; k += 128) {
+// Fixed-order final reduction: block n reduces image n's chunk partials (thread-strided partial sums, then a
+// fixed tree), the last block to finish (ticket) sums the images in index order.  The summation order
+// depends only on (N, chunks) => bit-reproducible.  `tail` = [N][2] image sums + ticket, after the partials.
+constexpr int FIN_BLOCK = 256;
+__global__ void __launch_bounds__(FIN_BLOCK) loss_finalize_kernel(const double *__restrict__ partials,
+                                                                  const int *__restrict__ fg_count, int N, int chunks,
+                                                                  float batch_div, float *__restrict__ out_image,
+                                                                  float *__restrict__ out_total, double *__restrict__ tail) {
+    __shared__ double s_c[FIN_BLOCK / 32], s_r[FIN_BLOCK / 32];
+    __shared__ bool s_last;
+    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const double2 *p = (const double2 *)partials + (long long)n * chunks;
+    double c = 0.0, r = 0.0;
+    for (int k = t; k < chunks; k += FIN_BLOCK) {
+        const double2 v = p[k];
+        c += v.x;
+        r += v.y;
+    }
+    c = rn::warp_sum(c);
+    r = rn::warp_sum(r);
+    if (lane == 0) { s_c[warp] = c; s_r[warp] = r; }
+    __syncthreads();
+    unsigned *ticket = (unsigned *)(tail + 2 * (long long)N);
+    if (t == 0) {
+        double cs = 0.0, rs = 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int kk = k + 32 * u;
-                if (kk < chunks) {
-                    const double2 v = p[kk];
-                    c[u] += v.x;
-                    r[u] += v.y;
-                }
-            }
+        for (int w = 0; w < FIN_BLOCK / 32; ++w) { cs += s_c[w]; rs += s_r[w]; }
+        const int F = fg_count[n];
+        const double den = F > 0 ? (double)F : 1.0;             // clamp(F, min=1)  losses.py:108-109
+        cs /= den;
+        rs /= den;
+        tail[2 * n] = cs;
+        tail[2 * n + 1] = rs;
+        if (out_image) {
+            out_image[3 * n + 0] = (float)cs;
+            out_image[3 * n + 1] = (float)rs;
+            out_image[3 * n + 2] = (float)F;
         }
-        double cs = rn::warp_sum((c[0] + c[1]) + (c[2] + c[3]));
-        double rs = rn::warp_sum((r[0] + r[1]) + (r[2] + r[3]));
-        if (lane == 0) {
-            const int F = fg_count[n];
-            const double den = F > 0 ? (double)F : 1.0;     // clamp(F, min=1)  losses.py:108-109
-            cs /= den;
-            rs /= den;
-            s_img[2 * n] = cs;
-            s_img[2 * n + 1] = rs;
-            if (out_image) {
-                out_image[3 * n + 0] = (float)cs;
-                out_image[3 * n + 1] = (float)rs;
-                out_image[3 * n + 2] = (float)F;
-            }
-        }
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == (unsigned)(N - 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double c = 0.0, r = 0.0;
+    if (s_last && t == 0) {
+        __threadfence();
+        double cs = 0.0, rs = 0.0;
         long long fsum = 0;
-        for (int n = 0; n < N; ++n) { c += s_img[2 * n]; r += s_img[2 * n + 1]; fsum += fg_count[n]; }
-        out_total[0] = (float)(c / (double)batch_div);      // losses.py:138-140
-        out_total[1] = (float)(r / (double)batch_div);
-        out_total[2] = (float)fsum;                         // sum_n F_n   } carried for the image-sharded
-        out_total[3] = (float)N;                            // local images } all-reduce
+        const volatile double *vt = tail;
+        for (int i = 0; i < N; ++i) { cs += vt[2 * i]; rs += vt[2 * i + 1]; fsum += fg_count[i]; }
+        out_total[0] = (float)(cs / (double)batch_div);         // losses.py:138-140
+        out_total[1] = (float)(rs / (double)batch_div);
+        out_total[2] = (float)fsum;                             // sum_n F_n   } carried for the image-sharded
+        out_total[3] = (float)N;                                // local images } all-reduce
+        *ticket = 0u;
     }
 }
 
@@ -305,7 +311,7 @@ extern "C" int rn_loss_set_math_mode(int mode) {
 extern "C" size_t rn_loss_workspace_bytes(int N, int64_t A, int C) {
     (void)C;
     if (N <= 0 || A <= 0) return 16;
-    return (size_t)N * (size_t)loss_chunks(A) * 2 * sizeof(double);
+    return ((size_t)N * (size_t)loss_chunks(A) * 2 + (size_t)N * 2 + 2) * sizeof(double);
 }
 
 extern "C" int rn_loss(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
@@ -325,7 +331,6 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     RN_CHECK_ARG(batch_div > 0.0f, RN_E_BADARG, "rn_loss: batch_div must be positive");
     RN_CHECK_ARG(workspace && workspace_bytes >= rn_loss_workspace_bytes(N, A, C), RN_E_WORKSPACE,
                  "rn_loss: workspace too small (%zu < %zu)", workspace_bytes, rn_loss_workspace_bytes(N, A, C));
-    RN_CHECK_ARG((size_t)N * 2 * sizeof(double) <= 96 * 1024, RN_E_TOOLARGE, "rn_loss: N too large for finalize");
     cudaStream_t s = (cudaStream_t)stream;
     LossParams P;
     P.logits = logits; P.bbox = (const float4 *)bbox; P.anchors = (const float4 *)anchors;
@@ -345,10 +350,13 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
         if (grad_logits) launch_loss_g<1, true>(P, grid, s, precise); else launch_loss_g<1, false>(P, grid, s, precise);
     }
     RN_CHECK_LAUNCH("rn_loss");
-    size_t smem = (size_t)N * 2 * sizeof(double);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    loss_finalize_kernel<<<1, 1024, smem, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
-                                              out_total);
+    {
+        double *tail = (double *)workspace + (size_t)N * P.chunks * 2;
+        cudaError_t e = cudaMemsetAsync(tail + 2 * (size_t)N, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) { rn_set_error("rn_loss: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+        loss_finalize_kernel<<<N, FIN_BLOCK, 0, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
+                                                     out_total, tail);
+    }
     RN_CHECK_LAUNCH("rn_loss_finalize");
     return 0;
 }
@@ -359,145 +367,159 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
 // right before this path.  loss_levels_kernel consumes the conv outputs directly (index math only) and
 // writes the gradients back in NCHW, so that pass disappears.  Element (n, a, c, y, x) of a level lives
 // at ((n*na + a)*C + c)*H*W + y*W + x and belongs to anchor lvl_off + (y*W + x)*na + a.
-// One CTA = 512 consecutive positions of one level x all na*C channel planes; the tile's packed codes
-// are staged in shared memory as [a][position]; each warp walks whole channel planes of the tile (2 KB
-// contiguous, four 128-bit loads in flight per lane when H*W % 4 == 0, else coalesced scalar loads).
+// One CTA = 128 consecutive positions of one level x one cell-anchor index a x its C class planes; the
+// tile's packed codes (one per position) are staged in shared memory; each warp walks class planes, four
+// in flight, each lane owning 4 positions (a 128-bit load when H*W % 4 == 0, else coalesced scalar loads).
 namespace {
-constexpr int LV_TILE = 512;
+#ifndef LV_PU
+#define LV_PU 1      // 128-position chunks of one plane in flight per lane
+#endif
+#ifndef LV_CU
+#define LV_CU 4      // channel planes in flight per warp
+#endif
+constexpr int LV_TILE = 128 * LV_PU;
 constexpr int LV_BLOCK = 256;
-constexpr int LV_MAX_NA = 16;
-constexpr int LV_U = 4;
 
-struct LvlLossParams {
+struct LvlDesc {             // one pyramid level
     const float *cls;
     const float *box;
     float *gcls;
     float *gbox;
+    long long lvl_off;       // anchor offset of the level
+    int HW, na, tile_base, chunk_base, vec4;
+};
+
+struct LvlLossParams {
+    LvlDesc lv[RN_MAX_LEVELS];
+    int num_levels, total_tiles;
     const float4 *anchors;
     const float4 *gt;
     const int *gt_off;
     const int *codes;
     const int *fg_count;
     double *partials;
-    long long A, anchor_stride, lvl_off;
-    int HW, na, C, chunks_total, chunk_base;
-    unsigned magicC;
+    long long A, anchor_stride;
+    int C, chunks_total;
     float alpha, gamma, beta, batch_div;
     float4 wts;
 };
 
+// One CTA = (tile of 128 positions of one level, image n, cell-anchor index a): C class planes of 512 B.
+// No shared memory and no barrier before the streaming loop: each lane keeps the packed codes of its 4
+// positions in registers (they are the same for all C planes) and the first plane loads are issued together
+// with the code loads.
 template <int VEC, bool WANT_GRAD, bool GAMMA2>
-__global__ void __launch_bounds__(LV_BLOCK) loss_levels_kernel(const LvlLossParams P) {
-    __shared__ int s_codes[LV_MAX_NA][LV_TILE];
-    const int n = blockIdx.y, tile = blockIdx.x;
+__device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const LvlDesc &D, int tile, int n, int a) {
     const int p0 = tile * LV_TILE;
-    const int np = min(LV_TILE, P.HW - p0);
+    const int np = min(LV_TILE, D.HW - p0);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long anchor0 = D.lvl_off + (long long)p0 * D.na + a;   // anchor of position p: anchor0 + p*na
+    const int *codes = P.codes + (long long)n * P.A + anchor0;
+    int code[LV_PU][4];
+#pragma unroll
+    for (int pu = 0; pu < LV_PU; ++pu)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int p = VEC == 4 ? pu * 128 + lane * 4 + k : pu * 128 + k * 32 + lane;
+            code[pu][k] = p < np ? __ldg(codes + (long long)p * D.na) : -2;
+        }
     const int F = P.fg_count[n];
     const float inv = 1.0f / (fmaxf((float)F, 1.0f) * P.batch_div);
     const float neg_gscale = P.alpha * inv;
-    const int *codes = P.codes + (long long)n * P.A + P.lvl_off + (long long)p0 * P.na;
-    for (int idx = t; idx < LV_TILE * P.na; idx += LV_BLOCK) {      // idx = p*na + a: coalesced read, transposed store
-        const int p = idx / P.na, a = idx - p * P.na;
-        s_codes[a][p] = p < np ? __ldg(codes + idx) : -2;
-    }
-    __syncthreads();
 
-    // Each warp walks whole channel planes of the tile: LV_TILE = 512 positions = 2 KB contiguous per plane,
-    // LV_U = 4 x 128-bit loads in flight per lane (lane owns positions u*128 + lane*4 .. +3).
     float acc_neg = 0.0f, acc_pos = 0.0f;
-    const int nch = P.na * P.C;
-    const long long img_base = (long long)n * nch * P.HW;
-    for (int ch = warp; ch < nch; ch += LV_BLOCK / 32) {
-        const float *plane = P.cls + img_base + (long long)ch * P.HW + p0;
-        float v[LV_U][4];
+    const long long img_base = ((long long)n * D.na + a) * P.C * D.HW;
+    for (int c0 = warp; c0 < P.C; c0 += (LV_BLOCK / 32) * LV_CU) {
+        float v[LV_CU][LV_PU][4];
 #pragma unroll
-        for (int u = 0; u < LV_U; ++u) {
+        for (int cu = 0; cu < LV_CU; ++cu) {
+            const int c = c0 + cu * (LV_BLOCK / 32);
+            const float *plane = D.cls + img_base + (long long)c * D.HW + p0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[u][k] = -30.0f;
-            if (VEC == 4) {
-                const int p = u * 128 + lane * 4;
-                if (p < np) {
-                    const float4 q = rn::ld_stream_f4((const float4 *)(plane + p));
-                    v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
-                }
-            } else {
+            for (int pu = 0; pu < LV_PU; ++pu) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int p = u * 128 + k * 32 + lane;
-                    if (p < np) v[u][k] = __ldg(plane + p);
+                for (int k = 0; k < 4; ++k) v[cu][pu][k] = -30.0f;
+                if (c < P.C) {
+                    if (VEC == 4) {
+                        const int p = pu * 128 + lane * 4;
+                        if (p < np) {
+                            const float4 q = rn::ld_stream_f4((const float4 *)(plane + p));
+                            v[cu][pu][0] = q.x; v[cu][pu][1] = q.y; v[cu][pu][2] = q.z; v[cu][pu][3] = q.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int p = pu * 128 + k * 32 + lane;
+                            if (p < np) v[cu][pu][k] = __ldg(plane + p);
+                        }
+                    }
                 }
             }
         }
-        const int a = P.magicC ? (int)__umulhi((unsigned)ch, P.magicC) : ch;  // ch / C (warp-uniform)
-        const int c = ch - a * P.C;
-        float *gplane = WANT_GRAD ? P.gcls + img_base + (long long)ch * P.HW + p0 : nullptr;
 #pragma unroll
-        for (int u = 0; u < LV_U; ++u) {
-            int code[4];
-            bool use[4];
-            float g[4];
-            float vmax = -30.0f;
+        for (int cu = 0; cu < LV_CU; ++cu) {
+            const int c = c0 + cu * (LV_BLOCK / 32);
+            if (c >= P.C) continue;                                   // warp-uniform
+            float *gplane = WANT_GRAD ? D.gcls + img_base + (long long)c * D.HW + p0 : nullptr;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int p = VEC == 4 ? u * 128 + lane * 4 + k : u * 128 + k * 32 + lane;
-                code[k] = s_codes[a][p];
-                use[k] = code[k] != -2;
-                vmax = fmaxf(vmax, use[k] ? v[u][k] : -30.0f);
-            }
-            const bool small = __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
-            float local = 0.0f;
+            for (int pu = 0; pu < LV_PU; ++pu) {
+                float g[4];
+                float vmax = -30.0f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float pk, spk;
-                if (small) sigmoid_softplus_small(v[u][k], pk, spk);
-                else sigmoid_softplus<false>(v[u][k] + 1.0f, pk, spk);
-                const float w = pow_gamma<GAMMA2>(pk, P.gamma);
-                local = fmaf(use[k] ? w : 0.0f, spk, local);
-                g[k] = use[k] ? w * pk * neg_gscale : 0.0f;
-                if (code[k] >= 0 && (code[k] >> 20) == c) {          // this element is its anchor's positive
-                    const float x = v[u][k] + 1.0f;
-                    float p, sp;
-                    sigmoid_softplus<false>(x, p, sp);
-                    const float wn = pow_gamma<GAMMA2>(p, P.gamma);
-                    const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
-                    acc_pos += wp * (sp - x) - P.alpha * wn * sp;
-                    g[k] = wp * (p - 1.0f) * inv;
+                for (int k = 0; k < 4; ++k) vmax = fmaxf(vmax, code[pu][k] != -2 ? v[cu][pu][k] : -30.0f);
+                const bool small = __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
+                float local = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool use = code[pu][k] != -2;
+                    float pk, spk;
+                    if (small) sigmoid_softplus_small(v[cu][pu][k], pk, spk);
+                    else sigmoid_softplus<false>(v[cu][pu][k] + 1.0f, pk, spk);
+                    const float w = pow_gamma<GAMMA2>(pk, P.gamma);
+                    local = fmaf(use ? w : 0.0f, spk, local);
+                    g[k] = use ? w * pk * neg_gscale : 0.0f;
+                    if (code[pu][k] >= 0 && (code[pu][k] >> 20) == c) {   // this element is its anchor's positive
+                        const float x = v[cu][pu][k] + 1.0f;
+                        float p, sp;
+                        sigmoid_softplus<false>(x, p, sp);
+                        const float wn = pow_gamma<GAMMA2>(p, P.gamma);
+                        const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
+                        acc_pos += wp * (sp - x) - P.alpha * wn * sp;
+                        g[k] = wp * (p - 1.0f) * inv;
+                    }
                 }
-            }
-            acc_neg += local;
-            if (WANT_GRAD) {
-                if (VEC == 4) {
-                    const int p = u * 128 + lane * 4;
-                    if (p < np) rn::st_stream_f4((float4 *)(gplane + p), make_float4(g[0], g[1], g[2], g[3]));
-                } else {
+                acc_neg += local;
+                if (WANT_GRAD) {
+                    if (VEC == 4) {
+                        const int p = pu * 128 + lane * 4;
+                        if (p < np) rn::st_stream_f4((float4 *)(gplane + p), make_float4(g[0], g[1], g[2], g[3]));
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int p = u * 128 + k * 32 + lane;
-                        if (p < np) gplane[p] = g[k];
+                        for (int k = 0; k < 4; ++k) {
+                            const int p = pu * 128 + k * 32 + lane;
+                            if (p < np) gplane[p] = g[k];
+                        }
                     }
                 }
             }
         }
     }
 
-    // ---- regression: (anchor a, position p) pairs of the tile; box channel (a*4 + k) plane, stride HW ----
+    // ---- regression: the tile's positions for this anchor index; box channel (a*4 + k) plane, stride HW ----
     float reg = 0.0f;
-    for (int idx = t; idx < LV_TILE * P.na; idx += LV_BLOCK) {
-        const int a = idx / LV_TILE, p = idx - a * LV_TILE;
-        if (p >= np) continue;
-        const int code = s_codes[a][p];
-        const long long b0 = ((long long)(n * P.na + a) * 4) * P.HW + p0 + p;
+    for (int p = t; p < np; p += LV_BLOCK) {
+        const int cd = __ldg(codes + (long long)p * D.na);
+        const long long b0 = ((long long)(n * D.na + a) * 4) * D.HW + p0 + p;
         float gr[4] = {0.f, 0.f, 0.f, 0.f};
-        if (code >= 0) {
-            const long long anchor = P.lvl_off + (long long)(p0 + p) * P.na + a;
-            const float4 gtb = P.gt[P.gt_off[n] + (code & 0xFFFFF)];
+        if (cd >= 0) {
+            const long long anchor = anchor0 + (long long)p * D.na;
+            const float4 gtb = P.gt[P.gt_off[n] + (cd & 0xFFFFF)];
             const float4 an = P.anchors[(long long)n * P.anchor_stride + anchor];
             const float4 tt = rn::encode_box(gtb, an, P.wts);
             const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float d = __ldg(P.box + b0 + (long long)k * P.HW) - tv[k];
+                const float d = __ldg(D.box + b0 + (long long)k * D.HW) - tv[k];
                 const float nabs = fabsf(d);
                 if (P.beta < 1e-5f) {
                     reg += nabs;
@@ -513,17 +535,33 @@ __global__ void __launch_bounds__(LV_BLOCK) loss_levels_kernel(const LvlLossPara
         }
         if (WANT_GRAD) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) P.gbox[b0 + (long long)k * P.HW] = gr[k];
+            for (int k = 0; k < 4; ++k) D.gbox[b0 + (long long)k * D.HW] = gr[k];
         }
     }
 
     double s_neg = acc_neg, s_pos = acc_pos, s_reg = reg;
     block_sum3(s_neg, s_pos, s_reg);
     if (t == 0) {
-        double *o = P.partials + ((long long)n * P.chunks_total + P.chunk_base + tile) * 2;
+        double *o = P.partials + ((long long)n * P.chunks_total + D.chunk_base + (long long)tile * D.na + a) * 2;
         o[0] = (double)P.alpha * s_neg + s_pos;
         o[1] = s_reg;
     }
+}
+
+// All pyramid levels in ONE launch: blockIdx.x enumerates the tiles of every level (the small P5-P7 levels
+// would otherwise be latency-bound launches of their own), blockIdx.y = image, blockIdx.z = cell anchor.
+template <bool WANT_GRAD, bool GAMMA2>
+__global__ void __launch_bounds__(LV_BLOCK) loss_levels_kernel(const __grid_constant__ LvlLossParams P) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < RN_MAX_LEVELS; ++k)
+        if (k < P.num_levels && (int)blockIdx.x >= P.lv[k].tile_base) l = k;
+    const LvlDesc &D = P.lv[l];
+    const int a = blockIdx.z;
+    if (a >= D.na) return;                                           // levels may differ in anchors per cell
+    const int tile = blockIdx.x - D.tile_base;
+    if (D.vec4) loss_levels_body<4, WANT_GRAD, GAMMA2>(P, D, tile, blockIdx.y, a);
+    else loss_levels_body<1, WANT_GRAD, GAMMA2>(P, D, tile, blockIdx.y, a);
 }
 
 inline int lv_tiles(int HW) { return (HW + LV_TILE - 1) / LV_TILE; }
@@ -532,8 +570,9 @@ inline int lv_tiles(int HW) { return (HW + LV_TILE - 1) / LV_TILE; }
 extern "C" size_t rn_loss_levels_workspace_bytes(int N, const int32_t *level_desc_host, int num_levels) {
     if (N <= 0 || !level_desc_host || num_levels <= 0) return 16;
     size_t chunks = 0;
-    for (int l = 0; l < num_levels; ++l) chunks += (size_t)lv_tiles(level_desc_host[3 * l] * level_desc_host[3 * l + 1]);
-    return (size_t)N * chunks * 2 * sizeof(double);
+    for (int l = 0; l < num_levels; ++l)
+        chunks += (size_t)lv_tiles(level_desc_host[3 * l] * level_desc_host[3 * l + 1]) * (size_t)level_desc_host[3 * l + 2];
+    return ((size_t)N * chunks * 2 + (size_t)N * 2 + 2) * sizeof(double);
 }
 
 extern "C" int rn_loss_levels(const float *const *cls_levels_host, const float *const *bbox_levels_host,
@@ -552,52 +591,48 @@ extern "C" int rn_loss_levels(const float *const *cls_levels_host, const float *
     RN_CHECK_ARG(batch_div > 0.0f, RN_E_BADARG, "rn_loss_levels: batch_div must be positive");
     RN_CHECK_ARG(workspace && workspace_bytes >= rn_loss_levels_workspace_bytes(N, level_desc_host, num_levels),
                  RN_E_WORKSPACE, "rn_loss_levels: workspace too small");
-    RN_CHECK_ARG((size_t)N * 2 * sizeof(double) <= 96 * 1024, RN_E_TOOLARGE, "rn_loss_levels: N too large for finalize");
     cudaStream_t s = (cudaStream_t)stream;
-    int chunks_total = 0;
-    long long total_anchors = 0;
-    for (int l = 0; l < num_levels; ++l) {
-        const int32_t *d = level_desc_host + 3 * l;
-        RN_CHECK_ARG(d[0] >= 0 && d[1] >= 0 && d[2] >= 1 && d[2] <= LV_MAX_NA, RN_E_BADARG,
-                     "rn_loss_levels: bad level %d descriptor {%d,%d,%d} (na <= %d)", l, d[0], d[1], d[2], LV_MAX_NA);
-        chunks_total += lv_tiles(d[0] * d[1]);
-        total_anchors += (long long)d[0] * d[1] * d[2];
-    }
-    RN_CHECK_ARG(total_anchors == A, RN_E_BADARG, "rn_loss_levels: levels hold %lld anchors, A = %lld", total_anchors, (long long)A);
     const bool want = grad_cls_levels_host != nullptr;
-    int chunk_base = 0;
+    LvlLossParams P;
+    memset(&P, 0, sizeof(P));
+    int tiles = 0, chunks = 0, max_na = 1;
     long long lvl_off = 0;
     for (int l = 0; l < num_levels; ++l) {
         const int32_t *d = level_desc_host + 3 * l;
+        RN_CHECK_ARG(d[0] >= 0 && d[1] >= 0 && d[2] >= 1 && d[2] <= 64, RN_E_BADARG,
+                     "rn_loss_levels: bad level %d descriptor {%d,%d,%d}", l, d[0], d[1], d[2]);
         const int HW = d[0] * d[1];
-        if (HW > 0) {
-            RN_CHECK_ARG(cls_levels_host[l] && bbox_levels_host[l], RN_E_BADARG, "rn_loss_levels: null level %d", l);
-            LvlLossParams P;
-            P.cls = cls_levels_host[l]; P.box = bbox_levels_host[l];
-            P.gcls = want ? grad_cls_levels_host[l] : nullptr; P.gbox = want ? grad_bbox_levels_host[l] : nullptr;
-            P.anchors = (const float4 *)anchors; P.gt = (const float4 *)gt_boxes; P.gt_off = gt_off; P.codes = codes;
-            P.fg_count = fg_count; P.partials = (double *)workspace; P.A = A; P.anchor_stride = anchor_image_stride;
-            P.lvl_off = lvl_off; P.HW = HW; P.na = d[2]; P.C = C; P.chunks_total = chunks_total; P.chunk_base = chunk_base;
-            P.magicC = C == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)C - 1) / (unsigned)C);
-            P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
-            P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
-            const bool vec4 = (HW % 4 == 0) && (((uintptr_t)P.cls & 15) == 0) && (!want || ((uintptr_t)P.gcls & 15) == 0);
-            dim3 grid((unsigned)lv_tiles(HW), (unsigned)N);
-            const bool g2 = gamma == 2.0f;
-#define RN_LV_LAUNCH(V, W, G) loss_levels_kernel<V, W, G><<<grid, LV_BLOCK, 0, s>>>(P)
-            if (vec4) { if (want) { if (g2) RN_LV_LAUNCH(4, true, true); else RN_LV_LAUNCH(4, true, false); }
-                        else      { if (g2) RN_LV_LAUNCH(4, false, true); else RN_LV_LAUNCH(4, false, false); } }
-            else      { if (want) { if (g2) RN_LV_LAUNCH(1, true, true); else RN_LV_LAUNCH(1, true, false); }
-                        else      { if (g2) RN_LV_LAUNCH(1, false, true); else RN_LV_LAUNCH(1, false, false); } }
-#undef RN_LV_LAUNCH
-            RN_CHECK_LAUNCH("rn_loss_levels");
-        }
-        chunk_base += lv_tiles(HW);
+        RN_CHECK_ARG(HW == 0 || (cls_levels_host[l] && bbox_levels_host[l]), RN_E_BADARG, "rn_loss_levels: null level %d", l);
+        LvlDesc &D = P.lv[l];
+        D.cls = cls_levels_host[l]; D.box = bbox_levels_host[l];
+        D.gcls = want ? grad_cls_levels_host[l] : nullptr; D.gbox = want ? grad_bbox_levels_host[l] : nullptr;
+        D.lvl_off = lvl_off; D.HW = HW; D.na = d[2]; D.tile_base = tiles; D.chunk_base = chunks;
+        D.vec4 = (HW % 4 == 0) && (((uintptr_t)D.cls & 15) == 0) && (!want || ((uintptr_t)D.gcls & 15) == 0);
+        tiles += lv_tiles(HW);
+        chunks += lv_tiles(HW) * d[2];
         lvl_off += (long long)HW * d[2];
+        max_na = d[2] > max_na ? d[2] : max_na;
     }
-    size_t smem = (size_t)N * 2 * sizeof(double);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    loss_finalize_kernel<<<1, 1024, smem, s>>>((const double *)workspace, fg_count, N, chunks_total, batch_div, out_image, out_total);
+    RN_CHECK_ARG(lvl_off == A, RN_E_BADARG, "rn_loss_levels: levels hold %lld anchors, A = %lld", lvl_off, (long long)A);
+    P.num_levels = num_levels; P.total_tiles = tiles;
+    P.anchors = (const float4 *)anchors; P.gt = (const float4 *)gt_boxes; P.gt_off = gt_off; P.codes = codes;
+    P.fg_count = fg_count; P.partials = (double *)workspace; P.A = A; P.anchor_stride = anchor_image_stride;
+    P.C = C; P.chunks_total = chunks; P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
+    P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
+    if (tiles > 0) {
+        dim3 grid((unsigned)tiles, (unsigned)N, (unsigned)max_na);
+        const bool g2 = gamma == 2.0f;
+        if (want) { if (g2) loss_levels_kernel<true, true><<<grid, LV_BLOCK, 0, s>>>(P); else loss_levels_kernel<true, false><<<grid, LV_BLOCK, 0, s>>>(P); }
+        else      { if (g2) loss_levels_kernel<false, true><<<grid, LV_BLOCK, 0, s>>>(P); else loss_levels_kernel<false, false><<<grid, LV_BLOCK, 0, s>>>(P); }
+        RN_CHECK_LAUNCH("rn_loss_levels");
+    }
+    {
+        double *tail = (double *)workspace + (size_t)N * chunks * 2;
+        cudaError_t e = cudaMemsetAsync(tail + 2 * (size_t)N, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) { rn_set_error("rn_loss_levels: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+        loss_finalize_kernel<<<N, FIN_BLOCK, 0, s>>>((const double *)workspace, fg_count, N, chunks, batch_div, out_image,
+                                                     out_total, tail);
+    }
     RN_CHECK_LAUNCH("rn_loss_levels/finalize");
     return 0;
 }

@@ -28,7 +28,7 @@ def test_abi_exports_every_declared_symbol():
     assert lib.rn_match(None, 10, 0, None, None, None, 1, 0.5, 0.4, None, None, None, None) == -1
     assert b"null" in lib.rn_last_error()
     assert lib.rn_postprocess_workspace_bytes(16, 201600, 80, 1 << 20, 100) > (1 << 20) * 8
-    assert lib.rn_loss_workspace_bytes(16, 201600, 80) == 16 * 788 * 16
+    assert lib.rn_loss_workspace_bytes(16, 201600, 80) == (16 * 788 * 2 + 16 * 2 + 2) * 8
 
 
 def test_no_cpu_fallback_and_loud_failure():
