@@ -415,35 +415,44 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long anchor0 = D.lvl_off + (long long)p0 * D.na + a;   // anchor of position p: anchor0 + p*na
     const int *codes = P.codes + (long long)n * P.A + anchor0;
-    int code[LV_PU][4];
+    // per-lane constants of the 4 positions this lane owns in every class plane
+    int posc[LV_PU][4];        // positive class of the position's anchor, or -1
+    bool ign[LV_PU][4];        // ignore anchor (or out of range): logit replaced by -100 -> p = sp = grad = 0 exactly
+    bool ok[LV_PU];            // lane's vector lies inside the tile (VEC == 4)
 #pragma unroll
-    for (int pu = 0; pu < LV_PU; ++pu)
+    for (int pu = 0; pu < LV_PU; ++pu) {
+        ok[pu] = pu * 128 + lane * 4 < np;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int p = VEC == 4 ? pu * 128 + lane * 4 + k : pu * 128 + k * 32 + lane;
-            code[pu][k] = p < np ? __ldg(codes + (long long)p * D.na) : -2;
+            const int cd = p < np ? __ldg(codes + (long long)p * D.na) : -2;
+            ign[pu][k] = cd == -2;
+            posc[pu][k] = cd >= 0 ? (cd >> 20) : -1;
         }
+    }
     const int F = P.fg_count[n];
     const float inv = 1.0f / (fmaxf((float)F, 1.0f) * P.batch_div);
     const float neg_gscale = P.alpha * inv;
 
     float acc_neg = 0.0f, acc_pos = 0.0f;
-    const long long img_base = ((long long)n * D.na + a) * P.C * D.HW;
-    for (int c0 = warp; c0 < P.C; c0 += (LV_BLOCK / 32) * LV_CU) {
+    const long long plane_stride = (long long)(LV_BLOCK / 32) * D.HW;
+    const long long first = ((long long)n * D.na + a) * P.C * D.HW + (long long)warp * D.HW + p0;
+    const float *src = D.cls + first;
+    float *dst = WANT_GRAD ? D.gcls + first : nullptr;
+    for (int c0 = warp; c0 < P.C; c0 += (LV_BLOCK / 32) * LV_CU, src += LV_CU * plane_stride, dst += WANT_GRAD ? LV_CU * plane_stride : 0) {
         float v[LV_CU][LV_PU][4];
 #pragma unroll
         for (int cu = 0; cu < LV_CU; ++cu) {
-            const int c = c0 + cu * (LV_BLOCK / 32);
-            const float *plane = D.cls + img_base + (long long)c * D.HW + p0;
+            const bool live = c0 + cu * (LV_BLOCK / 32) < P.C;         // warp-uniform
+            const float *plane = src + cu * plane_stride;
 #pragma unroll
             for (int pu = 0; pu < LV_PU; ++pu) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[cu][pu][k] = -30.0f;
-                if (c < P.C) {
+                for (int k = 0; k < 4; ++k) v[cu][pu][k] = -100.0f;
+                if (live) {
                     if (VEC == 4) {
-                        const int p = pu * 128 + lane * 4;
-                        if (p < np) {
-                            const float4 q = rn::ld_stream_f4((const float4 *)(plane + p));
+                        if (ok[pu]) {
+                            const float4 q = rn::ld_stream_f4((const float4 *)(plane + pu * 128 + lane * 4));
                             v[cu][pu][0] = q.x; v[cu][pu][1] = q.y; v[cu][pu][2] = q.z; v[cu][pu][3] = q.w;
                         }
                     } else {
@@ -460,39 +469,37 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
         for (int cu = 0; cu < LV_CU; ++cu) {
             const int c = c0 + cu * (LV_BLOCK / 32);
             if (c >= P.C) continue;                                   // warp-uniform
-            float *gplane = WANT_GRAD ? D.gcls + img_base + (long long)c * D.HW + p0 : nullptr;
 #pragma unroll
             for (int pu = 0; pu < LV_PU; ++pu) {
-                float g[4];
-                float vmax = -30.0f;
+                float x[4], g[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) vmax = fmaxf(vmax, code[pu][k] != -2 ? v[cu][pu][k] : -30.0f);
+                for (int k = 0; k < 4; ++k) x[k] = ign[pu][k] ? -100.0f : v[cu][pu][k];
+                const float vmax = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
                 const bool small = __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
                 float local = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const bool use = code[pu][k] != -2;
                     float pk, spk;
-                    if (small) sigmoid_softplus_small(v[cu][pu][k], pk, spk);
-                    else sigmoid_softplus<false>(v[cu][pu][k] + 1.0f, pk, spk);
+                    if (small) sigmoid_softplus_small(x[k], pk, spk);
+                    else sigmoid_softplus<false>(x[k] + 1.0f, pk, spk);
                     const float w = pow_gamma<GAMMA2>(pk, P.gamma);
-                    local = fmaf(use ? w : 0.0f, spk, local);
-                    g[k] = use ? w * pk * neg_gscale : 0.0f;
-                    if (code[pu][k] >= 0 && (code[pu][k] >> 20) == c) {   // this element is its anchor's positive
-                        const float x = v[cu][pu][k] + 1.0f;
+                    local = fmaf(w, spk, local);
+                    g[k] = w * pk * neg_gscale;
+                    if (posc[pu][k] == c) {                            // this element is its anchor's positive (rare)
+                        const float xx = x[k] + 1.0f;
                         float p, sp;
-                        sigmoid_softplus<false>(x, p, sp);
+                        sigmoid_softplus<false>(xx, p, sp);
                         const float wn = pow_gamma<GAMMA2>(p, P.gamma);
                         const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
-                        acc_pos += wp * (sp - x) - P.alpha * wn * sp;
+                        acc_pos += wp * (sp - xx) - P.alpha * wn * sp;
                         g[k] = wp * (p - 1.0f) * inv;
                     }
                 }
                 acc_neg += local;
                 if (WANT_GRAD) {
+                    float *gplane = dst + cu * plane_stride;
                     if (VEC == 4) {
-                        const int p = pu * 128 + lane * 4;
-                        if (p < np) rn::st_stream_f4((float4 *)(gplane + p), make_float4(g[0], g[1], g[2], g[3]));
+                        if (ok[pu]) rn::st_stream_f4((float4 *)(gplane + pu * 128 + lane * 4), make_float4(g[0], g[1], g[2], g[3]));
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {

@@ -22,3 +22,10 @@ e0.record()
 for i in range(30): run()
 e1.record(); torch.cuda.synchronize()
 print(os.path.basename(_native.lib_path()), "levels loss fwd+grad ms", e0.elapsed_time(e1) / 30)
+def run2(): return fused_loss_forward_levels(xs, bs, anc, 0, packed, 80, .25, 2., .1, .5, .4, 16.0, False)
+for i in range(5): run2()
+torch.cuda.synchronize()
+e0.record()
+for i in range(30): run2()
+e1.record(); torch.cuda.synchronize()
+print(os.path.basename(_native.lib_path()), "levels loss fwd-only ms", e0.elapsed_time(e1) / 30)
