@@ -12,6 +12,10 @@
 //    list of GT boxes that can have non-zero intersection with ANY anchor of the warp; only those
 //    are evaluated.  A culled pair has clamp(rb-lt,0)=0 in at least one axis, so its IoU is
 //    exactly +0 — bit-identical to evaluating it;
+//  * size culling: IoU <= min(area)/max(area), so a GT box whose area is below bg_thr*(1-2^-20) times the
+//    smallest anchor area of the warp, or above the largest anchor area divided by that factor, cannot
+//    reach bg_thr with any anchor of the warp and is skipped like a pruned pair (anchors of one pyramid
+//    level only meet GT boxes of comparable size);
 //  * the IEEE division is only issued for pairs whose IoU can reach bg_thr: pairs with
 //    inter < bg_thr*(1-2^-20)*union are provably below bg_thr after rounding and can neither
 //    change the fg/bg/ignore decision nor win the argmax of a foreground anchor;
@@ -61,8 +65,7 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
              const long long *__restrict__ labels, const int *__restrict__ gt_off, float fg_thr, float bg_thr,
              float prune_c, long long *__restrict__ matches, int *__restrict__ codes, int *__restrict__ fg_count) {
     __shared__ float4 s_box[GT_TILE];
-    __shared__ float s_area[GT_TILE];
-    __shared__ unsigned char s_bad[GT_TILE];
+    __shared__ float s_area[GT_TILE];      // NaN marks a malformed GT box (evaluated by the generic path)
 
     const int n = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -77,14 +80,18 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
 
     // warp-uniform: may this warp use culling / pruning / the non-NaN fast path?
     bool warp_fast = FAST;
-    float bx1 = 0.f, by1 = 0.f, bx2 = 0.f, by2 = 0.f;
+    float bx1 = 0.f, by1 = 0.f, bx2 = 0.f, by2 = 0.f, ag_lo = 0.f, ag_hi = INFINITY;
     if (FAST) {
-        bool ok = !live || (box_well_formed(a) && aa > 0.0f && aa <= 3.0e38f);
+        // positive finite extents imply finite, ordered coordinates differences; NaN fails every test
+        bool ok = !live || ((a.z - a.x) > 0.0f && (a.w - a.y) > 0.0f && aa <= 3.0e38f && fabsf(a.x) <= 3.0e38f && fabsf(a.y) <= 3.0e38f);
         warp_fast = __all_sync(0xffffffffu, ok);
         bx1 = rn::warp_min(live ? a.x : INFINITY);
         by1 = rn::warp_min(live ? a.y : INFINITY);
         bx2 = rn::warp_max(live ? a.z : -INFINITY);
         by2 = rn::warp_max(live ? a.w : -INFINITY);
+        const float amin = rn::warp_min(live ? aa : INFINITY), amax = rn::warp_max(live ? aa : 0.0f);
+        ag_lo = amin * prune_c * 0.999f;                 // GT areas outside [ag_lo, ag_hi] give IoU < bg_thr with
+        ag_hi = amax / (prune_c * 0.999f);               // every anchor of this warp (IoU <= area ratio)
     }
 
     float best = warp_fast ? 0.0f : -INFINITY;
@@ -97,8 +104,7 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
             float4 g = gt[g0 + t0 + j];
             float ag = box_area(g);
             s_box[j] = g;
-            s_area[j] = ag;
-            s_bad[j] = !(box_well_formed(g) && ag <= 3.0e38f);
+            s_area[j] = (box_well_formed(g) && ag <= 3.0e38f) ? ag : __int_as_float(0x7fc00000);
         }
         __syncthreads();
 
@@ -109,9 +115,10 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
                 bool hit = j < tn;
                 if (hit && warp_fast) {
                     float4 g = s_box[j];
+                    const float ag = s_area[j];
                     float w = __fsub_rn(fminf(g.z, bx2), fmaxf(g.x, bx1));
                     float h = __fsub_rn(fminf(g.w, by2), fmaxf(g.y, by1));
-                    hit = s_bad[j] || (w > 0.0f && h > 0.0f);
+                    hit = (ag != ag) || (w > 0.0f && h > 0.0f && ag >= ag_lo && ag <= ag_hi);
                 }
                 mask = __ballot_sync(0xffffffffu, hit);
             }
@@ -121,7 +128,7 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
                 const float4 g = s_box[j];
                 const float ag = s_area[j];
                 const int gi = t0 + j;
-                if (warp_fast && !s_bad[j]) {
+                if (warp_fast && ag == ag) {
                     // well-formed pair: no NaN possible, IoU is +0 unless both extents are positive
                     float w = __fsub_rn(fminf(g.z, a.z), fmaxf(g.x, a.x));
                     float h = __fsub_rn(fminf(g.w, a.w), fmaxf(g.y, a.y));
@@ -134,7 +141,7 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
                         }
                     }
                 } else {
-                    float v = iou_generic(g, ag, a, aa);
+                    float v = iou_generic(g, box_area(g), a, aa);   // s_area holds the NaN marker for malformed boxes
                     if (best == best) {                             // NaN, once taken, stays
                         if (v != v || v > best) { best = v; bi = gi; }
                     }
