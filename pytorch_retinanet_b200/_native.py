@@ -105,5 +105,24 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class on_device:
+    """``with on_device(dev):`` — like ``torch.cuda.device(dev)`` but free when ``dev`` already is the current
+    device (the common case: one process per GPU); the host path of a step is latency critical."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index
+        self.ctx = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 def host_floats(vals) -> ctypes.Array:
     return (_f32 * len(vals))(*[float(v) for v in vals])

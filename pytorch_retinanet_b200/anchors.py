@@ -123,7 +123,7 @@ class AnchorGenerator(nn.Module):
             total += h * w * c.shape[0]
         out = torch.empty((total, 4), dtype=torch.float32, device=device)
         lib = _native.load()
-        with torch.cuda.device(device):
+        with _native.on_device(device):
             rc = lib.rn_anchor_grid(_native.ptr(cells_dev), (ctypes.c_int32 * len(desc))(*desc), len(grid_sizes),
                                     float(self.offset), _native.ptr(out), total, _native.stream_ptr(device))
         _native.check(rc, "rn_anchor_grid")

@@ -39,7 +39,7 @@ def _boxcode(fn_name: str, a: Tensor, anchors: Tensor) -> Tensor:
     if a32.shape != an32.shape:
         raise ValueError(f"{fn_name}: shapes {tuple(a.shape)} and {tuple(anchors.shape)} differ")
     out = torch.empty_like(a32)
-    with torch.cuda.device(a32.device):
+    with _native.on_device(a32.device):
         rc = getattr(lib, fn_name)(_native.ptr(a32, what=fn_name + " input"), _native.ptr(an32, what="anchors"),
                                    a32.shape[0], _REG_WEIGHTS_C, _native.ptr(out),
                                    _native.stream_ptr(a32.device))
@@ -109,7 +109,7 @@ def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_
     matches = torch.empty((N, A), dtype=torch.int64, device=dev) if want_matches else None
     codes = torch.empty((N, A), dtype=torch.int32, device=dev) if want_codes else None
     fg = torch.empty((N,), dtype=torch.int32, device=dev) if want_codes else None   # zeroed by rn_match
-    with torch.cuda.device(dev):
+    with _native.on_device(dev):
         rc = lib.rn_match(_native.ptr(anchors, torch.float32, "anchors"), A, anchor_stride,
                           _native.ptr(packed.boxes, torch.float32, "target boxes"),
                           _native.ptr(packed.labels, torch.int64, "target labels") if want_codes else None,

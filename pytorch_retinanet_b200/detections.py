@@ -70,7 +70,7 @@ class PendingDetections:
         outs = (_native.ptr(a["out_boxes"]), _native.ptr(a["out_scores"]), _native.ptr(a["out_labels"]),
                 meta.data_ptr(), meta.data_ptr() + 4 * N)
         algo_id = 1 if a["use_general"] else 0
-        with torch.cuda.device(dev):
+        with _native.on_device(dev):
             if a.get("levels") is not None:               # raw per-level conv outputs (row N1)
                 xs, bs, desc = a["levels"]
                 ws_bytes = lib.rn_postprocess_levels_workspace_bytes(N, A, C, a["cap"], a["max_det"])

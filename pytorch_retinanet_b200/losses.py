@@ -55,7 +55,7 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
     gb = torch.empty_like(b) if want_grad else None
     ws_bytes = lib.rn_loss_workspace_bytes(N, A, C)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _native.on_device(dev):
         rc = lib.rn_loss(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
                          _native.ptr(anchors, torch.float32, "anchors"), anchor_stride,
                          _native.ptr(packed.boxes), _native.ptr(packed.offsets), _native.ptr(codes), _native.ptr(fg),
@@ -70,9 +70,15 @@ class _FusedRetinaNetLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cls_preds, bbox_preds, anchors, anchor_stride, packed, hp):
         want = cls_preds.requires_grad or bbox_preds.requires_grad
-        total, image, gl, gb, _ = fused_loss_forward(cls_preds, bbox_preds, anchors, anchor_stride, packed,
-                                                     hp["alpha"], hp["gamma"], hp["beta"], hp["match_thr"],
-                                                     hp["back_thr"], hp["batch_div"], want)
+        if cls_preds.shape[0] == 0:      # an empty shard of an image-sharded batch still joins the all-reduce
+            total = torch.zeros((4,), dtype=torch.float32, device=cls_preds.device)
+            image = torch.zeros((0, 3), dtype=torch.float32, device=cls_preds.device)
+            gl = torch.zeros_like(cls_preds, dtype=torch.float32) if want else None
+            gb = torch.zeros_like(bbox_preds, dtype=torch.float32) if want else None
+        else:
+            total, image, gl, gb, _ = fused_loss_forward(cls_preds, bbox_preds, anchors, anchor_stride, packed,
+                                                         hp["alpha"], hp["gamma"], hp["beta"], hp["match_thr"],
+                                                         hp["back_thr"], hp["batch_div"], want)
         group = hp.get("all_reduce_group", False)
         if group is not False:
             # image-sharded batch: the ONE collective of the path — 16 bytes over NCCL/NVLink.  The local
@@ -97,7 +103,7 @@ class _FusedRetinaNetLoss(torch.autograd.Function):
                 outs.append(None)
                 continue
             gs = g.detach().to(device=buf.device, dtype=torch.float32).contiguous()
-            with torch.cuda.device(buf.device):
+            with _native.on_device(buf.device):
                 rc = lib.rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
                                                    _native.stream_ptr(buf.device))
             _native.check(rc, "rn_scale_by_device_scalar")
@@ -153,7 +159,7 @@ def fused_loss_forward_levels(cls_levels, box_levels, anchors: Tensor, anchor_st
     L = len(xs)
     ws_bytes = lib.rn_loss_levels_workspace_bytes(N, desc, L)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _native.on_device(dev):
         rc = lib.rn_loss_levels(_ptr_array(xs), _ptr_array(bs), desc, L, _native.ptr(anchors, torch.float32, "anchors"),
                                 anchor_stride, _native.ptr(packed.boxes), _native.ptr(packed.offsets), _native.ptr(codes),
                                 _native.ptr(fg), N, A, C, float(alpha), float(gamma), float(beta), _REG_WEIGHTS_C,
@@ -199,7 +205,7 @@ class _FusedRetinaNetLossLevels(torch.autograd.Function):
                 if gs is None:
                     outs.append(None)
                     continue
-                with torch.cuda.device(buf.device):
+                with _native.on_device(buf.device):
                     rc = lib.rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
                                                        _native.stream_ptr(buf.device))
                 _native.check(rc, "rn_scale_by_device_scalar")
@@ -223,7 +229,7 @@ class _DenseLoss(torch.autograd.Function):
         grad = torch.empty_like(xc) if x.requires_grad else None
         nb = lib.rn_dense_loss_workspace_bytes()
         ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _native.on_device(dev):
             if kind == "focal":
                 rc = lib.rn_focal_loss_dense(_native.ptr(xc, what="clas_pred"), _native.ptr(tc, what="clas_tgt"), xc.numel(),
                                              float(p0), float(p1), _native.ptr(out), _native.ptr(grad), _native.ptr(ws), nb,

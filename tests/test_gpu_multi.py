@@ -23,7 +23,7 @@ def _worker(rank, world, port, ret):
     from pytorch_retinanet_b200.distributed import ShardedRetinaNetLosses, shard_range
 
     cfg = S.CONFIGS[1]
-    n_total = 6
+    n_total = world + 2            # uneven shards; with 8 ranks some hold a single image
     b = S.make_batch(cfg, 100, n_total, clustered=True)
     lo, hi = shard_range(n_total, rank, world)
     dev = torch.device("cuda", rank)
