@@ -266,12 +266,41 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end: pinned host inputs -> H2D every step, results read back ----
     stage_cls, stage_box = torch.empty_like(d_cls), torch.empty_like(d_box)
 
+    # The batch is ingested in chunks of images on a copy stream while the previous chunk is processed on the
+    # compute stream (images are independent; every chunk's loss is divided by the GLOBAL batch, so the sum of
+    # the chunk losses is the loss of the batch — the same mechanism as the multi-GPU sharding).
+    n_chunks = 4 if n_img % 4 == 0 else 1
+    per = n_img // n_chunks
+    copy_stream = torch.cuda.Stream(device=dev)
+    chunk_losses = ShardedRetinaNetLosses(C, global_batch=n_img * world)
+
     def e2e_step():
-        stage_cls.copy_(h_cls, non_blocking=True)
-        stage_box.copy_(h_box, non_blocking=True)
-        out, dets, _ = step(stage_cls, stage_box)
-        host = torch.stack([out["classification_loss"].detach(), out["regression_loss"].detach()]).cpu()
-        host_d = [(d["boxes"].cpu(), d["scores"].cpu(), d["labels"].cpu()) for d in dets]
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)                       # staging buffers of the previous step are free again
+        ready = []
+        with torch.cuda.stream(copy_stream):
+            for k in range(n_chunks):
+                sl = slice(k * per, (k + 1) * per)
+                stage_cls[sl].copy_(h_cls[sl], non_blocking=True)
+                stage_box[sl].copy_(h_box[sl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append(ev)
+        anchors = gen(images, fmaps)
+        tot_c, tot_r, pend = None, None, []
+        for k in range(n_chunks):
+            sl = slice(k * per, (k + 1) * per)
+            main.wait_event(ready[k])
+            x, b = stage_cls[sl].requires_grad_(True), stage_box[sl].requires_grad_(True)
+            out = chunk_losses(targets[sl], {"cls_preds": x, "bbox_preds": b}, anchors[:per])
+            (out["classification_loss"] + out["regression_loss"]).backward()
+            tot_c = out["classification_loss"].detach() if tot_c is None else tot_c + out["classification_loss"].detach()
+            tot_r = out["regression_loss"].detach() if tot_r is None else tot_r + out["regression_loss"].detach()
+            pend.append(P.process_detections_async(stub, {"cls_preds": stage_cls[sl], "bbox_preds": stage_box[sl]},
+                                                   anchors[:per], batch["im_szs"][sl]))
+        # (world > 1: every chunk loss already went through the ranks' all-reduce inside the loss function)
+        host = torch.stack([tot_c, tot_r]).cpu()
+        host_d = [(d["boxes"].cpu(), d["scores"].cpu(), d["labels"].cpu()) for p_ in pend for d in p_.detections()]
         return host, host_d
 
     for _ in range(2):
