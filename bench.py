@@ -300,7 +300,10 @@ def run_ours(args, rank, world, local_rank):
                                                    anchors[:per], batch["im_szs"][sl]))
         # (world > 1: every chunk loss already went through the ranks' all-reduce inside the loss function)
         host = torch.stack([tot_c, tot_r]).cpu()
-        host_d = [(d["boxes"].cpu(), d["scores"].cpu(), d["labels"].cpu()) for p_ in pend for d in p_.detections()]
+        host_d = []
+        for p_ in pend:                                       # padded [n,100,*] slabs + counts: 3 D2H copies per chunk
+            ob, os_, ol, counts = p_.result()
+            host_d.append((ob.cpu(), os_.cpu(), ol.cpu(), counts))
         return host, host_d
 
     for _ in range(2):
