@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                         if (lane >= o) incl += y;
                     }
                     const u32 need = S.need, excl = incl - sum;
+                    __syncwarp();                                  // every lane has read S.need before one lane rewrites it
                     if (excl < need && need <= incl) {            // exactly one lane
                         u32 acc = excl;
                         int b = 0;
@@ -967,6 +968,7 @@ __global__ void __launch_bounds__(TOPK_BLOCK) image_topk_kernel(const TopkParams
                 }
                 const u32 need = s_need;
                 const u32 excl = incl - sum;
+                __syncwarp();                          // every lane has read s_need before one lane rewrites it
                 if (excl < need && need <= incl) {    // exactly one lane
                     u32 acc = excl;
                     int b = 0;
