@@ -206,7 +206,9 @@ def run_ours(args, rank, world, local_rank):
     fmaps = [torch.empty((n_img, 1, h, w), device=dev) for h, w in S.grid_sizes(cfg.padded_hw)]
     images = SimpleNamespace(image_sizes=batch["im_szs"])
     losses = ShardedRetinaNetLosses(C, global_batch=n_img * world)
-    stub = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
+    if os.environ.get("RN_BENCH_NO_ALLREDUCE"):             # DIAGNOSTIC ONLY (not a valid bench line): isolates the
+        losses = P.RetinaNetLosses(C)                       # cost of the per-step collective at N > 1
+    stub =SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
 
     def step(cls, box):
         anchors = gen(images, fmaps)
