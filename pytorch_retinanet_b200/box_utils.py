@@ -95,8 +95,9 @@ class PackedTargets:
                     self.labels = torch.zeros((1,), dtype=torch.int64, device=device)
             else:
                 self.labels = None
-            off = torch.tensor(offs, dtype=torch.int32)
-            self.offsets = off.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else off
+            # <= a few hundred bytes: the driver embeds a pageable copy of this size in the command stream and
+            # returns without waiting for the GPU, which is cheaper than allocating pinned staging memory
+            self.offsets = torch.tensor(offs, dtype=torch.int32, device=device)
 
 
 def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_anchors: int,
