@@ -503,6 +503,60 @@ def test_full_batch_properties(P, cid, n_img):
         assert bool((d["boxes"][:, 0] >= 0).all()) and bool((d["boxes"][:, 2] <= b["im_szs"][0][1]).all())
 
 
+def test_randomized_differential(P):
+    """Seeded random problems (N 1-4, ragged G incl. 0, C 1-90 incl. odd, A 1-6000, random thresholds):
+    matches bit-exact, losses/gradients 1e-5 vs the CPU oracle, detections bit-exact vs the oracle run on
+    the same device."""
+    from types import SimpleNamespace
+    gen = torch.Generator().manual_seed(20260117)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=gen))
+    for case in range(22):
+        N, C = ri(1, 4), [1, 2, 3, 7, 20, 33, 80, 90][case % 8]
+        H, W = 8 * ri(2, 30), 8 * ri(2, 30)
+        if case % 5 == 0:
+            anc = torch.rand((ri(1, 200), 2), generator=gen) * 100
+            anc = torch.cat([anc, anc + 2 + torch.rand((anc.shape[0], 2), generator=gen) * 50], 1)
+        else:
+            anc = S.default_anchors((H, W))
+        A = anc.shape[0]
+        targets = []
+        for i in range(N):
+            G = [0, 1, ri(2, 60)][ri(0, 2)]
+            if G:
+                src = anc[torch.randint(0, A, (G,), generator=gen)]
+                g = src + (torch.rand((G, 4), generator=gen) - 0.5) * (12.0 if i % 2 else 0.0)
+                g = torch.stack([g[:, 0], g[:, 1], torch.maximum(g[:, 2], g[:, 0] + 1), torch.maximum(g[:, 3], g[:, 1] + 1)], 1)
+            else:
+                g = torch.zeros((0, 4))
+            targets.append({"boxes": g, "labels": torch.randint(1, C + 1, (G,), generator=gen)})
+        cls = torch.randn((N, A, C), generator=gen) * 2.5 - 3.0
+        box = torch.randn((N, A, 4), generator=gen) * 0.4
+        fg_t, bg_t = (0.5, 0.4) if case % 3 else (0.3 + 0.4 * float(torch.rand(1, generator=gen)), 0.25)
+        dev = torch.device("cuda")
+        anc_g = anc.to(dev)
+        for i in range(N):
+            m = P.matcher(anc_g, targets[i]["boxes"].to(dev), fg_t, bg_t).cpu()
+            assert torch.equal(m, O.match(anc, targets[i]["boxes"], fg_t, bg_t)), (case, i)
+        xo, bo = cls.clone().requires_grad_(True), box.clone().requires_grad_(True)
+        want = O.batch_loss(targets, xo, bo, [anc] * N, C)
+        tot = want["classification_loss"] + want["regression_loss"]
+        if tot.requires_grad:
+            tot.backward()
+        out, x, b, _ = run_gpu_loss(P, cls, box, targets, [anc_g] * N, C)
+        assert rel_close(out["classification_loss"], want["classification_loss"].detach(), LOSS_RTOL, 1e-7), case
+        assert rel_close(out["regression_loss"], want["regression_loss"].detach(), LOSS_RTOL, 1e-7), case
+        if xo.grad is not None:
+            assert rel_close(x.grad, xo.grad, 2e-5, 1e-8), (case, max_rel(x.grad, xo.grad, 1e-6))
+            assert rel_close(b.grad, bo.grad if bo.grad is not None else torch.zeros_like(bo), 2e-5, 1e-8), case
+        sz = [(H - ri(0, 7), W - ri(0, 7)) for _ in range(N)]
+        thr, nms, md = [0.05, 0.3, 0.01][case % 3], [0.5, 0.35, 0.7][case % 3], [100, 7, 300][case % 3]
+        wantd = O.postprocess(cls.to(dev), box.to(dev), [anc_g] * N, sz, score_thr=thr, nms_thr=nms, max_det=md)
+        for algo in ("auto", "general"):
+            got = gpu_detect(P, cls, box, [anc_g] * N, sz, algo=algo, score=thr, nms=nms, max_det=md)
+            for i in range(N):
+                assert_dets_equal(got[i], wantd[i], exact=True, ctx=f"case {case} {algo} image {i}")
+
+
 def test_nms_segments_vs_torchvision(P):
     import ctypes
     import torchvision
