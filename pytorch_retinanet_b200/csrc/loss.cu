@@ -119,11 +119,16 @@ __global__ void __launch_bounds__(LOSS_BLOCK) loss_kernel(const LossParams P) {
 #pragma unroll
         for (int u = 0; u < LOSS_U; ++u) {
             float g[VEC];
-            const bool use = code[u] != -2;
+            // ignore anchors (and the padding lanes): the logits are replaced by -100, for which p, softplus,
+            // the loss term and the gradient are all exactly 0 — no separate masking below
+            if (code[u] == -2) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) v[u][k] = -100.0f;
+            }
             float vmax = v[u][0];
 #pragma unroll
             for (int k = 1; k < VEC; ++k) vmax = fmaxf(vmax, v[u][k]);
-            const bool small = !PRECISE && __all_sync(0xffffffffu, !use || vmax <= kSmallX - 1.0f);
+            const bool small = !PRECISE && __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
             float pk[VEC], spk[VEC];
             if (small) {
 #pragma unroll
@@ -139,27 +144,21 @@ __global__ void __launch_bounds__(LOSS_BLOCK) loss_kernel(const LossParams P) {
                 local = fmaf(w, spk[k], local);
                 g[k] = w * pk[k] * neg_gscale;
             }
-            if (use) {
-                acc_neg += local;
-                const int col = code[u] >= 0 ? (code[u] >> 20) : -1;
-                const int k = col - c0[u];
-                if (k >= 0 && k < VEC) {               // this vector holds the anchor's positive column
-                    float x = v[u][0];
+            acc_neg += local;
+            const int k = (code[u] >> 20) - c0[u];     // code < 0 -> (code >> 20) == -1 -> k < 0
+            if ((unsigned)k < (unsigned)VEC) {          // this vector holds the anchor's positive column (rare)
+                float x = v[u][0];
 #pragma unroll
-                    for (int q = 1; q < VEC; ++q) x = (k == q) ? v[u][q] : x;
-                    x += 1.0f;
-                    float p, sp;
-                    sigmoid_softplus<PRECISE>(x, p, sp);
-                    const float wn = pow_gamma<GAMMA2>(p, P.gamma);
-                    const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
-                    acc_pos += wp * (sp - x) - P.alpha * wn * sp;   // softplus(-x) = softplus(x) - x
-                    const float gp = wp * (p - 1.0f) * inv;
+                for (int q = 1; q < VEC; ++q) x = (k == q) ? v[u][q] : x;
+                x += 1.0f;
+                float p, sp;
+                sigmoid_softplus<PRECISE>(x, p, sp);
+                const float wn = pow_gamma<GAMMA2>(p, P.gamma);
+                const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
+                acc_pos += wp * (sp - x) - P.alpha * wn * sp;   // softplus(-x) = softplus(x) - x
+                const float gp = wp * (p - 1.0f) * inv;
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) g[q] = (k == q) ? gp : g[q];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) g[k] = 0.0f;
+                for (int q = 0; q < VEC; ++q) g[q] = (k == q) ? gp : g[q];
             }
             if (WANT_GRAD && valid[u]) {
                 const int f = base + u * LOSS_BLOCK + threadIdx.x;
