@@ -55,6 +55,17 @@ const char *rn_last_error(void);
 int rn_anchor_grid(const float *cells, const int32_t *level_desc_host /*[L][4]*/, int num_levels,
                    double offset, float *out_anchors /*[A,4]*/, int64_t num_anchors, rn_stream_t stream);
 
+/* ---- target packing -------------------------------------------------------
+ * Packs the reference's per-image target lists (targets[i]["boxes"] [G_i,4] fp32, targets[i]["labels"] [G_i]
+ * int64; retinanet/losses.py:126-128) into gt_boxes [sumG,4], gt_labels [sumG], gt_off [N+1] in ONE launch:
+ * boxes_host / labels_host are HOST arrays of N DEVICE pointers, counts_host the N box counts.  No host->device
+ * copy is issued (pointers and counts travel in the kernel parameters).  ratios_hw_host (optional, [N][2] =
+ * ratio_h, ratio_w) additionally applies torchvision's resize_boxes to the boxes while packing (what
+ * GeneralizedRCNNTransform.forward does to the targets, retinanet/models.py:279).  labels may be NULL.   */
+int rn_pack_targets(const float *const *boxes_host, const int64_t *const *labels_host, const int32_t *counts_host, int N,
+                    const float *ratios_hw_host /*[N][2] or NULL*/, float *out_boxes, int64_t *out_labels /*or NULL*/,
+                    int32_t *out_off /*[N+1]*/, rn_stream_t stream);
+
 /* ---- matcher ----------------------------------------------------------------------------------
  * Replaces matcher (retinanet/box_utils.py:51-80) + torchvision box_iou for a whole batch:
  * fused IoU + first-index argmax + strict 0.5/0.4 thresholds.  matches[n,a] = -2 ignore,

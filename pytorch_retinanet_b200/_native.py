@@ -23,6 +23,7 @@ SIGNATURES = {
     "rn_abi_version": (_c.c_int, []),
     "rn_last_error": (_c.c_char_p, []),
     "rn_anchor_grid": (_c.c_int, [_vp, _vp, _c.c_int, _f64, _vp, _i64, _vp]),
+    "rn_pack_targets": (_c.c_int, [_vp, _vp, _vp, _c.c_int, _vp, _vp, _vp, _vp, _vp]),
     "rn_match": (_c.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _c.c_int, _f32, _f32, _vp, _vp, _vp, _vp]),
     "rn_encode": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "rn_decode": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -4,6 +4,7 @@ Same function names, argument meaning and error behaviour (``assert match_thr > 
 """
 from __future__ import annotations
 
+import ctypes
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -65,17 +66,25 @@ class PackedTargets:
     Host cost matters here (the GPU part of a step is < 1 ms): one ``torch.cat`` per field, offsets
     computed from shapes (no device sync) and shipped through pinned memory."""
 
-    def __init__(self, boxes: Sequence[Tensor], labels: Optional[Sequence[Tensor]], device: torch.device):
+    def __init__(self, boxes: Sequence[Tensor], labels: Optional[Sequence[Tensor]], device: torch.device,
+                 ratios_hw: Optional[Sequence[Tuple[float, float]]] = None):
         counts = [b.shape[0] if b.numel() else 0 for b in boxes]       # numel()==0 -> "no targets" (box_utils.py:70)
+        self.num_images = len(counts)
+        self.total = sum(counts)
+        self.counts = counts
+        device = torch.device(device)
+        if device.type == "cuda" and self._pack_native(boxes, labels, counts, device, ratios_hw):
+            return
+        # generic path (dtype/device conversions needed, or host-side use in the CPU tests): torch ops
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + c)
-        self.num_images = len(counts)
-        self.total = offs[-1]
-        self.counts = counts
         with torch.no_grad():
             if self.total:
-                live = [b for b, c in zip(boxes, counts) if c]
+                live = [b.reshape(-1, 4) for b, c in zip(boxes, counts) if c]
+                if ratios_hw is not None:
+                    live = [b.to(torch.float32) * b.new_tensor([rw, rh, rw, rh], dtype=torch.float32)
+                            for b, (rh, rw) in zip(live, [r for r, c in zip(ratios_hw, counts) if c])]
                 bx = live[0] if len(live) == 1 else torch.cat(live)
                 if bx.dtype != torch.float32 or bx.device != device:
                     bx = bx.to(device=device, dtype=torch.float32)
@@ -98,6 +107,38 @@ class PackedTargets:
             # <= a few hundred bytes: the driver embeds a pageable copy of this size in the command stream and
             # returns without waiting for the GPU, which is cheaper than allocating pinned staging memory
             self.offsets = torch.tensor(offs, dtype=torch.int32, device=device)
+
+    def _pack_native(self, boxes, labels, counts, device, ratios_hw) -> bool:
+        """One ``rn_pack_targets`` launch (row N3) when every tensor already is a contiguous fp32 / int64 tensor
+        on ``device``; returns False to let the torch path handle conversions."""
+        for b, c in zip(boxes, counts):
+            if c and not (b.dtype == torch.float32 and b.device == device and b.is_contiguous() and b.dim() == 2
+                          and b.shape[1] == 4 and b.data_ptr() % 16 == 0):
+                return False
+        if labels is not None:
+            for l, c in zip(labels, counts):
+                if l.numel() != c:
+                    raise ValueError("targets: number of labels does not match number of boxes")
+                if c and not (l.dtype == torch.int64 and l.device == device and l.is_contiguous()):
+                    return False
+        N, total = len(counts), self.total
+        self.boxes = torch.empty((max(total, 1), 4), dtype=torch.float32, device=device)
+        self.labels = torch.empty((max(total, 1),), dtype=torch.int64, device=device) if labels is not None else None
+        self.offsets = torch.empty((N + 1,), dtype=torch.int32, device=device)
+        vp = ctypes.c_void_p
+        bp = (vp * N)(*[b.data_ptr() if c else None for b, c in zip(boxes, counts)])
+        lp = (vp * N)(*[l.data_ptr() if c else None for l, c in zip(labels, counts)]) if labels is not None else None
+        cnt = (ctypes.c_int32 * N)(*counts)
+        rat = None
+        if ratios_hw is not None:
+            flat = [float(v) for r in ratios_hw for v in r]
+            rat = (ctypes.c_float * len(flat))(*flat)
+        with _native.on_device(device):
+            rc = _native.load().rn_pack_targets(bp, lp, cnt, N, rat, self.boxes.data_ptr(),
+                                                None if self.labels is None else self.labels.data_ptr(),
+                                                self.offsets.data_ptr(), _native.stream_ptr(device))
+        _native.check(rc, "rn_pack_targets")
+        return True
 
 
 def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_anchors: int,

@@ -503,6 +503,32 @@ def test_full_batch_properties(P, cid, n_img):
         assert bool((d["boxes"][:, 0] >= 0).all()) and bool((d["boxes"][:, 2] <= b["im_szs"][0][1]).all())
 
 
+def test_pack_targets_one_launch(P):
+    """Row N3: ragged targets packed by rn_pack_targets (no torch.cat, no H2D) == the torch packing; with
+    per-image ratios == torchvision's resize_boxes applied to every image's boxes first."""
+    import numpy as np
+    from pytorch_retinanet_b200.box_utils import PackedTargets
+    gen = torch.Generator().manual_seed(9)
+    dev = torch.device("cuda")
+    counts = [0, 3, 1, 0, 57, 200, 0] + [5] * 140                     # > 128 images -> two launches
+    boxes = [S._gt_boxes(gen, c, (600, 900)) if c else torch.zeros((0, 4)) for c in counts]
+    labels = [torch.randint(1, 81, (c,), generator=gen) for c in counts]
+    bg, lg = [b.to(dev) for b in boxes], [l.to(dev) for l in labels]
+    native = PackedTargets(bg, lg, dev)
+    assert native.offsets.cpu().tolist() == [0] + list(np.cumsum(counts))
+    assert torch.equal(native.boxes[:native.total].cpu(), torch.cat(boxes)) and torch.equal(native.labels[:native.total].cpu(), torch.cat(labels))
+    generic = PackedTargets([b.double() for b in bg], lg, dev)          # dtype conversion -> torch path
+    assert torch.equal(generic.boxes, native.boxes[:native.total]) and torch.equal(generic.offsets, native.offsets)
+    orig = [(480 + 7 * i, 640 + 3 * i) for i in range(len(counts))]
+    new = [(800, 1066 + (i % 5)) for i in range(len(counts))]
+    ratios = [(float(np.float32(n[0]) / np.float32(o[0])), float(np.float32(n[1]) / np.float32(o[1]))) for o, n in zip(orig, new)]
+    scaled = PackedTargets(bg, lg, dev, ratios_hw=ratios)
+    want = torch.cat([O.resize_boxes(b, o, n) for b, o, n in zip(boxes, orig, new)])
+    assert torch.equal(scaled.boxes[:scaled.total].cpu(), want)
+    m = PackedTargets([torch.zeros((0, 4), device=dev)], [torch.zeros((0,), dtype=torch.int64, device=dev)], dev)
+    assert m.total == 0 and m.offsets.cpu().tolist() == [0, 0]
+
+
 def test_randomized_differential(P):
     """Seeded random problems (N 1-4, ragged G incl. 0, C 1-90 incl. odd, A 1-6000, random thresholds):
     matches bit-exact, losses/gradients 1e-5 vs the CPU oracle, detections bit-exact vs the oracle run on
