@@ -141,6 +141,10 @@ int rn_scale_by_device_scalar(float *buf, int64_t n, const float *scale, rn_stre
  *   the fallback flag when an image could not be completed within its round budget — the caller
  *   then repeats the call with algo = RN_PP_GENERAL (per-(image,class) segments, any size).  Both
  *   algorithms produce identical results.
+ * Output epilogue options (both off = reference output of process_detections):
+ *   out_ratio_hw [N,2] (ratio_h, ratio_w per image): the final boxes are multiplied like torchvision's
+ *     resize_boxes does in transform.postprocess right after the path (retinanet/models.py:271);
+ *   out_format 1: boxes are written as COCO xywh (utils/coco/coco_eval.py:159-161), after the resize.
  * workspace: rn_postprocess_workspace_bytes(N, A, C, cand_capacity, max_det).                      */
 size_t rn_postprocess_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
 int rn_postprocess(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, const float *anchors,
@@ -148,7 +152,8 @@ int rn_postprocess(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*
                    int max_det, const float *weights_host /*[4]*/, int pre_nms_topk,
                    const int64_t *level_off_host /*[L+1] or NULL*/, int num_levels, int algo, int64_t cand_capacity,
                    float *out_boxes, float *out_scores, int64_t *out_labels, int32_t *out_count,
-                   int32_t *out_status, void *workspace, size_t workspace_bytes, rn_stream_t stream);
+                   int32_t *out_status, void *workspace, size_t workspace_bytes, rn_stream_t stream,
+                   const float *out_ratio_hw /*[N,2] device or NULL*/, int out_format /*0 xyxy, 1 xywh*/);
 
 /* ---- per-level NCHW entry points -------------------------------------------
  * Same semantics and outputs as rn_loss / rn_postprocess, but the class and box activations are the
@@ -173,7 +178,7 @@ int rn_postprocess_levels(const float *const *cls_levels_host, const float *cons
                           double nms_thr, int max_det, const float *weights_host, int pre_nms_topk, int algo,
                           int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
                           int32_t *out_count, int32_t *out_status, void *workspace, size_t workspace_bytes,
-                          rn_stream_t stream);
+                          rn_stream_t stream, const float *out_ratio_hw /*[N,2] or NULL*/, int out_format);
 
 /* Stand-alone batched greedy NMS (torchvision `nms` semantics, tv:ops/boxes.py:20-48) over
  * segments whose boxes are ALREADY sorted by score descending (ties: original order): boxes [K,4],

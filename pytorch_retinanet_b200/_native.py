@@ -36,13 +36,13 @@ SIGNATURES = {
     "rn_scale_by_device_scalar": (_c.c_int, [_vp, _i64, _vp, _vp]),
     "rn_postprocess_workspace_bytes": (_sz, [_c.c_int, _i64, _c.c_int, _i64, _c.c_int]),
     "rn_postprocess": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _c.c_int, _i64, _c.c_int, _f32, _f64, _c.c_int, _vp,
-                                  _c.c_int, _vp, _c.c_int, _c.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                  _c.c_int, _vp, _c.c_int, _c.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _c.c_int]),
     "rn_loss_levels_workspace_bytes": (_sz, [_c.c_int, _vp, _c.c_int]),
     "rn_loss_levels": (_c.c_int, [_vp, _vp, _vp, _c.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _c.c_int, _i64, _c.c_int, _f32,
                                   _f32, _f32, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rn_postprocess_levels_workspace_bytes": (_sz, [_c.c_int, _i64, _c.c_int, _i64, _c.c_int]),
     "rn_postprocess_levels": (_c.c_int, [_vp, _vp, _vp, _c.c_int, _vp, _i64, _vp, _c.c_int, _i64, _c.c_int, _f32, _f64,
-                                         _c.c_int, _vp, _c.c_int, _c.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                         _c.c_int, _vp, _c.c_int, _c.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _c.c_int]),
     "rn_nms_segments": (_c.c_int, [_vp, _vp, _c.c_int, _i64, _f64, _vp, _vp, _sz, _vp]),
     "rn_loss_set_math_mode": (_c.c_int, [_c.c_int]),
 }

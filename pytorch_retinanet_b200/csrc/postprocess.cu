@@ -483,6 +483,22 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
     if (!RAW && t == 0) P.kept_count[seg] = K;
 }
 
+// Output epilogue shared by both algorithms:
+//  * ratio (optional, [N,2] = ratio_h, ratio_w): torchvision resize_boxes of the final boxes back to the original
+//    image size, as transform.postprocess does right after the path (retinanet/models.py:271,
+//    tv:models/detection/transform.py:306-319): x * ratio_w, y * ratio_h, one fp32 multiply each;
+//  * format 1: COCO xywh, as CocoEvaluator.prepare_for_coco_detection converts them
+//    (utils/coco/coco_eval.py:159-161): (x1, y1, x2 - x1, y2 - y1), applied after the resize.
+__device__ __forceinline__ float4 finish_box(float4 b, const float *__restrict__ ratio, int n, int format) {
+    if (ratio) {
+        const float rh = __ldg(ratio + 2 * n), rw = __ldg(ratio + 2 * n + 1);
+        b.x = __fmul_rn(b.x, rw); b.z = __fmul_rn(b.z, rw);
+        b.y = __fmul_rn(b.y, rh); b.w = __fmul_rn(b.w, rh);
+    }
+    if (format == 1) { b.z = __fsub_rn(b.z, b.x); b.w = __fsub_rn(b.w, b.y); }
+    return b;
+}
+
 // ------------------------------------------------------------------------------------------- LAZY
 struct LazyParams {
     const float4 *bbox;
@@ -503,6 +519,8 @@ struct LazyParams {
     long long *out_labels;
     int *out_count;
     int *status;             // [0] max candidates/image * N (atomicMax), [2] fallback flag
+    const float *out_ratio;  // [N,2] or null (row N2)
+    int out_format;          // 0 xyxy, 1 xywh (row N4)
     int topk;                // pre_nms_topk per (image, pyramid level); 0 = off (reference behaviour)
     int nlev;
     long long lvl_off[RN_MAX_LEVELS + 1];   // anchor offsets of the pyramid levels
@@ -822,7 +840,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     if (kept < P.max_det && processed < K && t == 0) atomicOr(P.status + 2, 1);   // general algorithm needed
     for (int i = t; i < kept; i += LZ_BLOCK) {
         const long long o = (long long)n * P.max_det + i;
-        ((float4 *)P.out_boxes)[o] = S.kbox[i];
+        ((float4 *)P.out_boxes)[o] = finish_box(S.kbox[i], P.out_ratio, n, P.out_format);
         P.out_scores[o] = __uint_as_float(S.kscore[i]);
         P.out_labels[o] = (long long)S.kcls[i] + 1;            // models.py:230 labels + 1
     }
@@ -849,6 +867,8 @@ struct TopkParams {
     float *out_scores;
     long long *out_labels;
     int *out_count;
+    const float *out_ratio;  // [N,2] or null (row N2)
+    int out_format;          // 0 xyxy, 1 xywh (row N4)
 };
 
 constexpr int TOPK_BLOCK = 1024;
@@ -1046,7 +1066,7 @@ __global__ void __launch_bounds__(TOPK_BLOCK) image_topk_kernel(const TopkParams
         }
         const float4 b = P.kept_box[s_sel_pos[i]];
         const long long o = (long long)n * P.max_det + rank;
-        ((float4 *)P.out_boxes)[o] = b;
+        ((float4 *)P.out_boxes)[o] = finish_box(b, P.out_ratio, n, P.out_format);
         P.out_scores[o] = __uint_as_float(~(u32)(hi >> 32));
         P.out_labels[o] = (long long)(u32)hi + 1;          // models.py:230 labels + 1
     }
@@ -1065,7 +1085,7 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const float *bbo
                    int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A, int C, double nms_thr,
                    int max_det, int pre_nms_topk, const int64_t *level_off_host, int num_levels, bool lazy,
                    int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
-                   int32_t *out_count, int32_t *out_status, cudaStream_t s) {
+                   int32_t *out_count, int32_t *out_status, const float *out_ratio_hw, int out_format, cudaStream_t s) {
     // round the double threshold DOWN to fp32: (double)ovr > thr  <=>  ovr > thr_f  for every fp32 ovr
     float thr_f = (float)nms_thr;
     if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
@@ -1077,6 +1097,7 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const float *bbo
         Z.cand_key = w.pool_key; Z.img_count = w.img_count; Z.cap_n = F.cap_n; Z.out_boxes = out_boxes;
         Z.out_scores = out_scores; Z.out_labels = (long long *)out_labels; Z.out_count = out_count; Z.status = out_status;
         Z.topk = pre_nms_topk; Z.nlev = pre_nms_topk ? num_levels : 0;
+        Z.out_ratio = out_ratio_hw; Z.out_format = out_format;
         for (int l = 0; l <= RN_MAX_LEVELS; ++l)
             Z.lvl_off[l] = (pre_nms_topk && l <= num_levels) ? (long long)level_off_host[l] : (long long)A;
         const size_t smem = ((sizeof(LazySmem) + 15) & ~(size_t)15) + (size_t)LZ_CACHE * sizeof(u64);
@@ -1106,6 +1127,7 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const float *bbo
     TopkParams T;
     T.seg_off = w.seg_off; T.kept_count = w.kept_count; T.kept_key = w.kept_key; T.kept_box = w.kept_box;
     T.C = C; T.max_det = max_det; T.out_boxes = out_boxes; T.out_scores = out_scores;
+    T.out_ratio = out_ratio_hw; T.out_format = out_format;
     T.out_labels = (long long *)out_labels; T.out_count = out_count;
     const size_t topk_smem = ((size_t)C + 1 + TOPK_CACHE) * sizeof(u32);
     if (topk_smem > 48 * 1024)
@@ -1121,7 +1143,8 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
                               const float *weights_host, int pre_nms_topk, const int64_t *level_off_host,
                               int num_levels, int algo, int64_t cand_capacity, float *out_boxes, float *out_scores,
                               int64_t *out_labels, int32_t *out_count, int32_t *out_status, void *workspace,
-                              size_t workspace_bytes, rn_stream_t stream) {
+                              size_t workspace_bytes, rn_stream_t stream, const float *out_ratio_hw, int out_format) {
+    RN_CHECK_ARG(out_format == 0 || out_format == 1, RN_E_BADARG, "rn_postprocess: out_format must be 0 (xyxy) or 1 (xywh)");
     RN_CHECK_ARG(logits && bbox && anchors && im_hw && weights_host && out_boxes && out_scores && out_labels &&
                      out_count && out_status && workspace,
                  RN_E_BADARG, "rn_postprocess: null pointer");
@@ -1176,7 +1199,7 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
 
     return pp_tail(w, F, bbox, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
                    level_off_host, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count,
-                   out_status, s);
+                   out_status, out_ratio_hw, out_format, s);
 }
 
 // ---- per-level NCHW inputs ------------------------------------------------------------
@@ -1308,7 +1331,9 @@ extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const 
                                      float score_thr, double nms_thr, int max_det, const float *weights_host,
                                      int pre_nms_topk, int algo, int64_t cand_capacity, float *out_boxes,
                                      float *out_scores, int64_t *out_labels, int32_t *out_count, int32_t *out_status,
-                                     void *workspace, size_t workspace_bytes, rn_stream_t stream) {
+                                     void *workspace, size_t workspace_bytes, rn_stream_t stream,
+                                     const float *out_ratio_hw, int out_format) {
+    RN_CHECK_ARG(out_format == 0 || out_format == 1, RN_E_BADARG, "rn_postprocess_levels: out_format must be 0 (xyxy) or 1 (xywh)");
     RN_CHECK_ARG(cls_levels_host && bbox_levels_host && level_desc_host && anchors && im_hw && weights_host && out_boxes &&
                      out_scores && out_labels && out_count && out_status && workspace,
                  RN_E_BADARG, "rn_postprocess_levels: null pointer");
@@ -1379,7 +1404,8 @@ extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const 
         RN_CHECK_LAUNCH("rn_postprocess_levels/score_filter");
     }
     return pp_tail(w, F, (const float *)bbox_nac, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
-                   level_off, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count, out_status, s);
+                   level_off, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count, out_status,
+                   out_ratio_hw, out_format, s);
 }
 
 extern "C" int rn_nms_segments(const float *boxes, const int32_t *seg_off, int num_segments, int64_t total_boxes,

@@ -47,6 +47,31 @@ def _image_sizes_tensor(im_szs, dev) -> Tensor:
     return t
 
 
+_RATIO_CACHE: Dict[Tuple, Tensor] = {}
+
+
+def _resize_ratio_tensor(im_szs, original_image_sizes, dev) -> Optional[Tensor]:
+    """[N,2] fp32 (ratio_h, ratio_w) = fp32(original) / fp32(resized), exactly torchvision's resize_boxes ratios
+    (tv:models/detection/transform.py:307-311); None when no resize is requested."""
+    if original_image_sizes is None:
+        return None
+    if len(original_image_sizes) != len(im_szs):
+        raise ValueError("original_image_sizes and im_szs differ in length")
+    key = (tuple((int(h), int(w)) for h, w in im_szs), tuple((int(h), int(w)) for h, w in original_image_sizes), dev.index)
+    t = _RATIO_CACHE.get(key)
+    if t is None:
+        if len(_RATIO_CACHE) > 64:
+            _RATIO_CACHE.clear()
+        new = torch.tensor(key[1], dtype=torch.float32).reshape(-1, 2)
+        old = torch.tensor(key[0], dtype=torch.float32).reshape(-1, 2)
+        t = (new / old).to(dev)
+        _RATIO_CACHE[key] = t
+    return t
+
+
+_FORMATS = {"xyxy": 0, "xywh": 1}
+
+
 def default_candidate_capacity(N: int, A: int, C: int) -> int:
     return int(min(N * A * C, max(1 << 20, N * (1 << 16))))
 
@@ -79,7 +104,8 @@ class PendingDetections:
                                                _native.ptr(a["anchors"], torch.float32, "anchors"), a["anchor_stride"],
                                                _native.ptr(a["hw"]), N, A, C, a["score_thres"], a["nms_thres"], a["max_det"],
                                                _REG_WEIGHTS_C, a["topk"], algo_id, a["cap"], *outs,
-                                               _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+                                               _native.ptr(ws), ws_bytes, _native.stream_ptr(dev),
+                                               _native.ptr(a["ratio"]), a["fmt"])
                 what = "rn_postprocess_levels"
             else:
                 ws_bytes = lib.rn_postprocess_workspace_bytes(N, A, C, a["cap"], a["max_det"])
@@ -89,7 +115,8 @@ class PendingDetections:
                                         _native.ptr(a["anchors"], torch.float32, "anchors"), a["anchor_stride"],
                                         _native.ptr(a["hw"]), N, A, C, a["score_thres"], a["nms_thres"], a["max_det"],
                                         _REG_WEIGHTS_C, a["topk"], a["lvl"], a["nlev"], algo_id, a["cap"], *outs,
-                                        _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+                                        _native.ptr(ws), ws_bytes, _native.stream_ptr(dev),
+                                        _native.ptr(a["ratio"]), a["fmt"])
                 what = "rn_postprocess"
         _native.check(rc, what)
         self._host = torch.empty((N + 4,), dtype=torch.int32, pin_memory=True)
@@ -118,6 +145,19 @@ class PendingDetections:
                 return self._done
             self._launch()
 
+    def coco_results(self, image_ids: Sequence[int]) -> List[dict]:
+        """COCO-format results of the batch (row N4): what ``CocoEvaluator.prepare_for_coco_detection``
+        (utils/coco/coco_eval.py:71-93) builds with three ``.tolist()`` syncs per image, from THREE device->host
+        copies for the whole batch.  Requires ``box_format="xywh"``."""
+        if self._a["fmt"] != 1:
+            raise ValueError("coco_results() needs box_format='xywh'")
+        ob, os_, ol, counts = self.result()
+        hb, hs, hl = ob.cpu().tolist(), os_.cpu().tolist(), ol.cpu().tolist()
+        out = []
+        for i, (img, k) in enumerate(zip(image_ids, counts)):
+            out.extend({"image_id": img, "category_id": hl[i][j], "bbox": hb[i][j], "score": hs[i][j]} for j in range(k))
+        return out
+
     def detections(self) -> List[Dict[str, Tensor]]:
         ob, os_, ol, counts = self.result()
         # one unbind per tensor + one slice per field (half the view ops of ob[i, :k])
@@ -128,7 +168,9 @@ class PendingDetections:
 def postprocess_batch_async(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
                             im_szs: Sequence[Tuple[int, int]], score_thres: float, nms_thres: float, max_det: int,
                             pre_nms_topk: Optional[int] = None, level_offsets: Optional[Sequence[int]] = None,
-                            cand_capacity: Optional[int] = None, algo: str = "auto") -> PendingDetections:
+                            cand_capacity: Optional[int] = None, algo: str = "auto",
+                            original_image_sizes: Optional[Sequence[Tuple[int, int]]] = None,
+                            box_format: str = "xyxy") -> PendingDetections:
     """Enqueues the whole post-processing of a batch and returns without synchronising.
 
     ``algo``: "auto" = lazy per-image algorithm, transparently repeated with the general
@@ -152,6 +194,7 @@ def postprocess_batch_async(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tens
     if topk and (algo == "general" or A * C >= (1 << 32)):
         raise ValueError("pre_nms_topk is implemented by the lazy algorithm only (needs A*C < 2^32)")
     args = dict(dev=dev, N=N, A=A, C=C, x=x, b=b, anchors=anchors, anchor_stride=anchor_stride,
+                ratio=_resize_ratio_tensor(im_szs, original_image_sizes, dev), fmt=_FORMATS[box_format],
                 hw=_image_sizes_tensor(im_szs, dev), score_thres=float(score_thres), nms_thres=float(nms_thres),
                 max_det=int(max_det), topk=topk, lvl=lvl, nlev=nlev, algo=algo,
                 use_general=(algo == "general" or (A * C >= (1 << 32))),
@@ -165,7 +208,8 @@ def postprocess_batch_async(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tens
 def postprocess_levels_async(cls_levels: Sequence[Tensor], bbox_levels: Sequence[Tensor], num_classes: int, anchors: Tensor,
                              anchor_stride: int, im_szs: Sequence[Tuple[int, int]], score_thres: float, nms_thres: float,
                              max_det: int, pre_nms_topk: Optional[int] = None, cand_capacity: Optional[int] = None,
-                             algo: str = "auto") -> PendingDetections:
+                             algo: str = "auto", original_image_sizes: Optional[Sequence[Tuple[int, int]]] = None,
+                             box_format: str = "xyxy") -> PendingDetections:
     """:func:`postprocess_batch_async` on the RAW per-level conv outputs."""
     xs, bs = [_f32_contig(t) for t in cls_levels], [_f32_contig(t) for t in bbox_levels]
     desc, A, N = _level_desc(xs, bs, num_classes)
@@ -176,6 +220,7 @@ def postprocess_levels_async(cls_levels: Sequence[Tensor], bbox_levels: Sequence
     if topk and (algo == "general" or A * C >= (1 << 32)):
         raise ValueError("pre_nms_topk is implemented by the lazy algorithm only (needs A*C < 2^32)")
     args = dict(dev=dev, N=N, A=A, C=C, levels=(xs, bs, desc), anchors=anchors, anchor_stride=anchor_stride,
+                ratio=_resize_ratio_tensor(im_szs, original_image_sizes, dev), fmt=_FORMATS[box_format],
                 hw=_image_sizes_tensor(im_szs, dev), score_thres=float(score_thres), nms_thres=float(nms_thres),
                 max_det=int(max_det), topk=topk, lvl=None, nlev=0, algo=algo,
                 use_general=(algo == "general" or (A * C >= (1 << 32))),
@@ -204,9 +249,13 @@ def _level_offsets(self):
 
 
 def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Tensor],
-                             im_szs: List[Tuple[int, int]]) -> PendingDetections:
+                             im_szs: List[Tuple[int, int]],
+                             original_image_sizes: Optional[Sequence[Tuple[int, int]]] = None,
+                             box_format: str = "xyxy") -> PendingDetections:
     """Same arguments and side effects as :func:`process_detections`; returns a handle whose
-    ``.detections()`` yields the reference's ``List[Dict]``."""
+    ``.detections()`` yields the reference's ``List[Dict]``.  ``original_image_sizes`` folds
+    ``transform.postprocess``'s box resize (models.py:271) into the output write (row N2); ``box_format="xywh"``
+    writes COCO boxes (row N4, see :meth:`PendingDetections.coco_results`)."""
     an, stride = _shared_anchors(anchors)
     if "cls_levels" in outputs:                       # raw per-level conv outputs (SURVEY.md 8f N1)
         cls_levels, box_levels = outputs.pop("cls_levels"), outputs.pop("bbox_levels")
@@ -214,15 +263,18 @@ def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Ten
         return postprocess_levels_async(cls_levels, box_levels, C, an, stride, im_szs,
                                         getattr(self, "score_thres", SCORE_THRES), getattr(self, "nms_thres", NMS_THRES),
                                         getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE),
-                                        getattr(self, "pre_nms_topk", None))
+                                        getattr(self, "pre_nms_topk", None), original_image_sizes=original_image_sizes,
+                                        box_format=box_format)
     class_logits = outputs.pop("cls_preds")
     bboxes = outputs.pop("bbox_preds")
     return postprocess_batch_async(class_logits, bboxes, an, stride, im_szs,
                                    getattr(self, "score_thres", SCORE_THRES), getattr(self, "nms_thres", NMS_THRES),
                                    getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE),
-                                   getattr(self, "pre_nms_topk", None), _level_offsets(self))
+                                   getattr(self, "pre_nms_topk", None), _level_offsets(self),
+                                   original_image_sizes=original_image_sizes, box_format=box_format)
 
 
 def process_detections(self, outputs: Dict[str, Tensor], anchors: List[Tensor],
-                       im_szs: List[Tuple[int, int]]) -> List[Dict[str, Tensor]]:
-    return process_detections_async(self, outputs, anchors, im_szs).detections()
+                       im_szs: List[Tuple[int, int]],
+                       original_image_sizes: Optional[Sequence[Tuple[int, int]]] = None) -> List[Dict[str, Tensor]]:
+    return process_detections_async(self, outputs, anchors, im_szs, original_image_sizes).detections()

@@ -159,3 +159,39 @@ def test_patch_retinanet_with_fused_head_layout():
         assert rel_close(l1[k], l0[k].detach(), 1e-6), k
     for a, b in zip(d0, d1):
         assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_patch_retinanet_fold_box_resize():
+    """Row N2 through the integration helper: the patched ``predict`` (models.py:245-272 flow) returns the boxes
+    transform.postprocess would have produced, for both transform.training states."""
+    import pytorch_retinanet_b200 as P
+    torch.manual_seed(1)
+    C, hw = 5, (96, 128)
+    dev = torch.device("cuda")
+    model = _FakeRetinanet(C).to(dev)
+    fmaps = [torch.randn((2, 8, h, w), device=dev) for h, w in S.grid_sizes(hw)]
+    with torch.no_grad():
+        model.retinanet_head.classification_head.class_subnet_output.bias.fill_(-1.5)
+
+    class FakeTransform:
+        training = False
+
+        def __call__(self, images, targets):
+            return SimpleNamespace(tensors=torch.stack([torch.zeros((3,) + hw, device=dev)] * len(images)),
+                                   image_sizes=[(90, 128), (96, 120)]), targets
+
+    model.transform = FakeTransform()
+    model.backbone = lambda t: fmaps
+    model.fpn = lambda f: f
+    model.process_detections = None
+    P.patch_retinanet(model, fold_box_resize=True)
+    images = [torch.zeros((3, 180, 256), device=dev), torch.zeros((3, 48, 60), device=dev)]
+    got = model.predict(images)
+    outputs = model.retinanet_head(fmaps)
+    anchors = model.anchor_generator(SimpleNamespace(image_sizes=[(90, 128), (96, 120)]), fmaps)
+    plain = model.process_detections(outputs, anchors, [(90, 128), (96, 120)])
+    for g, d, s_, o in zip(got, plain, [(90, 128), (96, 120)], [(180, 256), (48, 60)]):
+        assert torch.equal(g["boxes"], O.resize_boxes(d["boxes"], s_, o)) and torch.equal(g["labels"], d["labels"])
+    model.transform.training = True                      # transform.postprocess is a no-op in training mode
+    for g, d in zip(model.predict(images), plain):
+        assert torch.equal(g["boxes"], d["boxes"])

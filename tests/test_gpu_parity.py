@@ -503,6 +503,39 @@ def test_full_batch_properties(P, cid, n_img):
         assert bool((d["boxes"][:, 0] >= 0).all()) and bool((d["boxes"][:, 2] <= b["im_szs"][0][1]).all())
 
 
+def test_output_epilogue_resize_and_coco(P):
+    """Rows N2 / N4: the box resize of transform.postprocess (torchvision resize_boxes) and the COCO xywh
+    conversion folded into the detection write are bit-identical to applying them afterwards."""
+    from types import SimpleNamespace
+    from pytorch_retinanet_b200.detections import postprocess_batch_async
+    b, _ = config_image(1)
+    cfg = b["config"]
+    dev = torch.device("cuda")
+    x = torch.cat([b["cls_preds"], b["cls_preds"].flip(1)]).to(dev)
+    bb = torch.cat([b["bbox_preds"], b["bbox_preds"].flip(1)]).to(dev)
+    anc = b["anchors"].to(dev)
+    sz = [(512, 480), (500, 512)]
+    orig = [(375, 352), (1080, 1106)]
+    stub = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
+    plain = P.process_detections(stub, {"cls_preds": x, "bbox_preds": bb}, [anc] * 2, sz)
+    resized = P.process_detections(stub, {"cls_preds": x, "bbox_preds": bb}, [anc] * 2, sz, orig)
+    for d, r, s_, o in zip(plain, resized, sz, orig):
+        assert torch.equal(r["boxes"], O.resize_boxes(d["boxes"], s_, o))       # transform.postprocess, models.py:271
+        assert torch.equal(r["scores"], d["scores"]) and torch.equal(r["labels"], d["labels"])
+    for algo in ("auto", "general"):
+        h = postprocess_batch_async(x, bb, anc, 0, sz, 0.05, 0.5, 100, algo=algo, original_image_sizes=orig, box_format="xywh")
+        res = h.coco_results([11, 22])
+        want = []
+        for img, r in zip([11, 22], resized):                                   # utils/coco/coco_eval.py:71-93, 159-161
+            x0, y0, x1, y1 = r["boxes"].unbind(1)
+            xywh = torch.stack((x0, y0, x1 - x0, y1 - y0), dim=1).tolist()
+            want.extend({"image_id": img, "category_id": l, "bbox": bx, "score": sc}
+                        for l, bx, sc in zip(r["labels"].tolist(), xywh, r["scores"].tolist()))
+        assert res == want, algo
+    with pytest.raises(ValueError):
+        postprocess_batch_async(x, bb, anc, 0, sz, 0.05, 0.5, 100).coco_results([1, 2])
+
+
 def test_pack_targets_one_launch(P):
     """Row N3: ragged targets packed by rn_pack_targets (no torch.cat, no H2D) == the torch packing; with
     per-image ratios == torchvision's resize_boxes applied to every image's boxes first."""
