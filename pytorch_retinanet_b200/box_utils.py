@@ -5,7 +5,7 @@ Same function names, argument meaning and error behaviour (``assert match_thr > 
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor

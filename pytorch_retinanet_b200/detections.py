@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from . import _native
-from .config import BBOX_REG_WEIGHTS, MAX_DETECTIONS_PER_IMAGE, NMS_THRES, SCORE_THRES
+from .config import MAX_DETECTIONS_PER_IMAGE, NMS_THRES, SCORE_THRES
 from .box_utils import _REG_WEIGHTS_C
 from .losses import _f32_contig, _level_desc, _ptr_array, _shared_anchors
 

@@ -16,7 +16,7 @@ from torch import Tensor, nn
 
 from . import _native
 from .box_utils import _REG_WEIGHTS_C, PackedTargets, match_batch
-from .config import (BBOX_REG_WEIGHTS, FOCAL_LOSS_ALPHA, FOCAL_LOSS_GAMMA, IOU_THRESHOLDS_BACKGROUND,
+from .config import (FOCAL_LOSS_ALPHA, FOCAL_LOSS_GAMMA, IOU_THRESHOLDS_BACKGROUND,
                      IOU_THRESHOLDS_FOREGROUND, SMOOTH_L1_LOSS_BETA)
 
 
