@@ -1,0 +1,287 @@
+"""The whole dense per-anchor path of one batch as ONE CUDA graph with two concurrent branches.
+
+The drop-in entry points (``RetinaNetLosses.forward``, ``process_detections``) cost ~0.9 ms of host
+time per batch of 16 images (torch allocations, autograd, ctypes marshalling) for ~0.6 ms of GPU
+work, and they run the training half and the inference half back to back.  ``HotPathGraph`` captures
+the SAME C-ABI calls (``rn_match`` -> ``rn_loss`` with gradients; ``rn_postprocess``) once, for fixed
+shapes and static buffers, into a CUDA graph:
+
+    capture stream:   rn_match ---------> rn_loss (fwd + gradients) -> finalize ---.
+    side stream (hi): score filter -> lazy NMS -> status --------------------------+--> join
+
+so that a step is one ``cudaGraphLaunch`` (+ one ``rn_pack_targets`` launch for the ragged ground
+truth and one 4*(N+4)-byte D2H copy of the detection counts), and the ALU-bound matcher and the
+latency-bound NMS (one CTA per image) run in the shadow of the two HBM-bound streaming kernels.
+Results are bit-identical to the drop-in calls (tests/test_gpu_graph.py) — the kernels and their
+arguments are the same; only the launch mechanism differs.
+
+Reference flow covered: retinanet/losses.py:113-145 (+ box_utils.py:51-80) and
+retinanet/models.py:160-243, on the head outputs of retinanet/layers.py:110-115.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native
+from .box_utils import _REG_WEIGHTS_C
+from .config import (FOCAL_LOSS_ALPHA, FOCAL_LOSS_GAMMA, IOU_THRESHOLDS_BACKGROUND, IOU_THRESHOLDS_FOREGROUND,
+                     MAX_DETECTIONS_PER_IMAGE, NMS_THRES, SCORE_THRES, SMOOTH_L1_LOSS_BETA)
+from .detections import (_FORMATS, _image_sizes_tensor, _resize_ratio_tensor, default_candidate_capacity,
+                         postprocess_batch)
+
+_vp = ctypes.c_void_p
+
+
+class GraphStepResult:
+    """Outcome of one :meth:`HotPathGraph.step`.  Tensors are views of the graph's static buffers: they stay
+    valid until the next ``step`` of the same graph."""
+
+    def __init__(self, owner: "HotPathGraph", event: Optional[torch.cuda.Event]):
+        self._o = owner
+        self._event = event
+        self._dets = None
+
+    @property
+    def losses(self) -> Dict[str, Tensor]:
+        """{"classification_loss", "regression_loss"} of the (global) batch — device scalars, no sync."""
+        t = self._o.total
+        return {"classification_loss": t[0], "regression_loss": t[1]}
+
+    @property
+    def per_image(self) -> Tensor:
+        """[N,3] = cls_i / max(1,F_i), reg_i / max(1,F_i), F_i."""
+        return self._o.per_image
+
+    @property
+    def grads(self) -> Tuple[Tensor, Tensor]:
+        """d(classification_loss)/d cls_preds and d(regression_loss)/d bbox_preds, already divided by the batch size."""
+        return self._o.grad_cls_preds, self._o.grad_bbox_preds
+
+    def result(self):
+        """(boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int]) — waits for the
+        count copy only."""
+        o = self._o
+        if not o.detect:
+            raise RuntimeError("HotPathGraph was built with detect=False")
+        if self._dets is None:
+            self._event.synchronize()
+            host = o._host.tolist()
+            N = o.N
+            found, capacity, fallback = host[N], host[N + 1], host[N + 2]
+            if found > capacity or fallback:
+                # rare: candidate pool overflow / an image needs more rounds than the lazy budget -> eager re-run of the
+                # same inputs through the drop-in call, which knows how to grow the pool and switch algorithm
+                self._dets = postprocess_batch(o.cls_preds, o.bbox_preds, o.anchors, o.anchor_stride, o.im_szs, o.score_thres,
+                                               o.nms_thres, o.max_det, cand_capacity=max(found, o.cap),
+                                               original_image_sizes=o.original_image_sizes, box_format=o.box_format)
+            else:
+                self._dets = (o.out_boxes, o.out_scores, o.out_labels, host[:N])
+        return self._dets
+
+    def detections(self) -> List[Dict[str, Tensor]]:
+        """The reference's ``List[Dict]`` (models.py:236-242): three ``split_with_sizes`` calls for the batch."""
+        ob, os_, ol, counts = self.result()
+        N, M = ob.shape[0], ob.shape[1]
+        sizes = []
+        for k in counts:
+            sizes.append(k)
+            sizes.append(M - k)
+        b = ob.view(N * M, -1).split_with_sizes(sizes)
+        s = os_.view(N * M).split_with_sizes(sizes)
+        l = ol.view(N * M).split_with_sizes(sizes)
+        return [{"boxes": b[2 * i], "scores": s[2 * i], "labels": l[2 * i]} for i in range(N)]
+
+
+class HotPathGraph:
+    """CUDA graph of loss (forward + gradients) and/or post-processing for fixed shapes.
+
+    ``cls_preds [N,A,C]`` / ``bbox_preds [N,A,4]`` are the STATIC inputs: pass the tensors the head writes into
+    (or copy into ``graph.cls_preds`` / ``graph.bbox_preds``); ``anchors`` is the shared ``[A,4]`` tensor of
+    :class:`AnchorGenerator`.  ``max_targets`` bounds the total number of GT boxes of a batch (static packed
+    buffers).  ``global_batch`` / ``group``: image-sharded multi-GPU use — the loss is divided by the global
+    batch and ``step`` all-reduces the 16-byte loss vector (NCCL), exactly as ``ShardedRetinaNetLosses``.
+    """
+
+    def __init__(self, num_classes: int, cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor,
+                 im_szs: Optional[Sequence[Tuple[int, int]]] = None, *, train: bool = True, detect: bool = True,
+                 max_targets: int = 4096, global_batch: Optional[int] = None, group=None,
+                 score_thres: float = SCORE_THRES, nms_thres: float = NMS_THRES,
+                 detections_per_img: int = MAX_DETECTIONS_PER_IMAGE,
+                 original_image_sizes: Optional[Sequence[Tuple[int, int]]] = None, box_format: str = "xyxy",
+                 alpha: float = FOCAL_LOSS_ALPHA, gamma: float = FOCAL_LOSS_GAMMA, beta: float = SMOOTH_L1_LOSS_BETA,
+                 match_thr: float = IOU_THRESHOLDS_FOREGROUND, back_thr: float = IOU_THRESHOLDS_BACKGROUND,
+                 cand_capacity: Optional[int] = None, concurrent: bool = True):
+        if not (train or detect):
+            raise ValueError("HotPathGraph: nothing to do (train=False, detect=False)")
+        lib = _native.load()
+        for t, name, dt in ((cls_preds, "cls_preds", torch.float32), (bbox_preds, "bbox_preds", torch.float32),
+                            (anchors, "anchors", torch.float32)):
+            _native.ptr(t, dt, name)                      # CUDA + dtype + contiguity, or NativeError (no CPU path)
+        dev = cls_preds.device
+        N, A, C = cls_preds.shape
+        if C != num_classes:
+            raise ValueError(f"cls_preds has {C} classes, expected {num_classes}")
+        if bbox_preds.shape != (N, A, 4):
+            raise ValueError(f"bbox_preds must be [{N},{A},4], got {tuple(bbox_preds.shape)}")
+        if anchors.dim() == 2:
+            stride = 0
+        elif anchors.dim() == 3 and anchors.shape[0] == N:
+            stride = anchors.shape[1]
+        else:
+            raise ValueError("anchors must be [A,4] (shared) or [N,A,4]")
+        if anchors.shape[-2] != A:
+            raise ValueError(f"anchors hold {anchors.shape[-2]} rows, cls_preds {A}")
+        if detect and (im_szs is None or len(im_szs) != N):
+            raise ValueError("detect=True needs one (h, w) per image in im_szs")
+        assert match_thr > back_thr                       # box_utils.py:66
+        self.lib, self.dev, self.N, self.A, self.C = lib, dev, N, A, C
+        self.train, self.detect = train, detect
+        self.cls_preds, self.bbox_preds, self.anchors, self.anchor_stride = cls_preds, bbox_preds, anchors, stride
+        self.im_szs = list(im_szs) if im_szs is not None else None
+        self.original_image_sizes, self.box_format = original_image_sizes, box_format
+        self.score_thres, self.nms_thres, self.max_det = float(score_thres), float(nms_thres), int(detections_per_img)
+        self.group = group
+        self.world = 1
+        if global_batch is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.batch_div = float(global_batch if global_batch is not None else N)
+        self.hp = (float(alpha), float(gamma), float(beta), float(match_thr), float(back_thr))
+        self.max_targets = int(max_targets)
+
+        f32, i32, i64 = torch.float32, torch.int32, torch.int64
+        if train:
+            self.gt_boxes = torch.zeros((max(self.max_targets, 1), 4), dtype=f32, device=dev)
+            self.gt_labels = torch.ones((max(self.max_targets, 1),), dtype=i64, device=dev)
+            self.gt_off = torch.zeros((N + 1,), dtype=i32, device=dev)
+            self.codes = torch.empty((N, A), dtype=i32, device=dev)
+            self.fg = torch.empty((N,), dtype=i32, device=dev)
+            self.total = torch.zeros((4,), dtype=f32, device=dev)
+            self.per_image = torch.zeros((N, 3), dtype=f32, device=dev)
+            self.grad_cls_preds = torch.empty_like(cls_preds)
+            self.grad_bbox_preds = torch.empty_like(bbox_preds)
+            self._loss_ws_bytes = lib.rn_loss_workspace_bytes(N, A, C)
+            self._loss_ws = torch.empty((self._loss_ws_bytes,), dtype=torch.uint8, device=dev)
+        else:
+            self.total = self.per_image = self.grad_cls_preds = self.grad_bbox_preds = None
+        if detect:
+            M = self.max_det
+            self.cap = int(cand_capacity) if cand_capacity else default_candidate_capacity(N, A, C)
+            self.out_boxes = torch.empty((N, M, 4), dtype=f32, device=dev)
+            self.out_scores = torch.empty((N, M), dtype=f32, device=dev)
+            self.out_labels = torch.empty((N, M), dtype=i64, device=dev)
+            self.meta = torch.zeros((N + 4,), dtype=i32, device=dev)          # counts [N] + status [4]
+            self._host = torch.empty((N + 4,), dtype=i32, pin_memory=True)
+            self._hw = _image_sizes_tensor(self.im_szs, dev)
+            self._ratio = _resize_ratio_tensor(self.im_szs, original_image_sizes, dev)
+            self._pp_ws_bytes = lib.rn_postprocess_workspace_bytes(N, A, C, self.cap, M)
+            self._pp_ws = torch.empty((self._pp_ws_bytes,), dtype=torch.uint8, device=dev)
+        self._side = torch.cuda.Stream(device=dev, priority=-1) if (train and detect and concurrent) else None
+        self.graph = torch.cuda.CUDAGraph()
+        self._capture()
+
+    # ---- raw C-ABI launches on the CURRENT stream (the same calls the drop-in path makes) ----
+    def _enqueue_train(self):
+        self._enqueue_match()
+        self._enqueue_loss()
+
+    def _enqueue_match(self):
+        lib, N, A = self.lib, self.N, self.A
+        match_thr, back_thr = self.hp[3], self.hp[4]
+        s = _native.stream_ptr(self.dev)
+        rc = lib.rn_match(self.anchors.data_ptr(), A, self.anchor_stride, self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(),
+                          self.gt_off.data_ptr(), N, match_thr, back_thr, None, self.codes.data_ptr(), self.fg.data_ptr(), s)
+        _native.check(rc, "rn_match")
+
+    def _enqueue_loss(self):
+        lib, N, A, C = self.lib, self.N, self.A, self.C
+        alpha, gamma, beta = self.hp[:3]
+        s = _native.stream_ptr(self.dev)
+        rc = lib.rn_loss(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(), self.anchor_stride,
+                         self.gt_boxes.data_ptr(), self.gt_off.data_ptr(), self.codes.data_ptr(), self.fg.data_ptr(), N, A, C,
+                         alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div, self.per_image.data_ptr(), self.total.data_ptr(),
+                         self.grad_cls_preds.data_ptr(), self.grad_bbox_preds.data_ptr(), self._loss_ws.data_ptr(),
+                         self._loss_ws_bytes, s)
+        _native.check(rc, "rn_loss")
+
+    def _enqueue_detect(self):
+        lib, N, A, C = self.lib, self.N, self.A, self.C
+        meta = self.meta.data_ptr()
+        rc = lib.rn_postprocess(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(),
+                                self.anchor_stride, self._hw.data_ptr(), N, A, C, self.score_thres, self.nms_thres, self.max_det,
+                                _REG_WEIGHTS_C, 0, None, 0, 0, self.cap, self.out_boxes.data_ptr(), self.out_scores.data_ptr(),
+                                self.out_labels.data_ptr(), meta, meta + 4 * N, self._pp_ws.data_ptr(), self._pp_ws_bytes,
+                                _native.stream_ptr(self.dev), None if self._ratio is None else self._ratio.data_ptr(),
+                                _FORMATS[self.box_format])
+        _native.check(rc, "rn_postprocess")
+
+    def _enqueue_all(self):
+        cur = torch.cuda.current_stream(self.dev)
+        if self._side is not None:
+            self._side.wait_stream(cur)                   # fork
+            with torch.cuda.stream(self._side):
+                self._enqueue_detect()
+            self._enqueue_train()
+            cur.wait_stream(self._side)                   # join
+        else:
+            if self.detect:
+                self._enqueue_detect()
+            if self.train:
+                self._enqueue_train()
+
+    def _capture(self):
+        with _native.on_device(self.dev):
+            warm = torch.cuda.Stream(device=self.dev)
+            warm.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(warm):                 # eager warm-up: module loading / func attributes before capture
+                self._enqueue_all()
+            torch.cuda.current_stream(self.dev).wait_stream(warm)
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(self.graph):
+                self._enqueue_all()
+
+    # ---- per step ----
+    def load_targets(self, targets: Sequence[Dict[str, Tensor]]) -> None:
+        """Packs ``targets[i]["boxes"] [G_i,4] fp32 / ["labels"] [G_i] int64`` (CUDA tensors, the reference's
+        format, losses.py:126-128) into the graph's static buffers with one ``rn_pack_targets`` launch."""
+        N = self.N
+        if len(targets) != N:
+            raise ValueError(f"{len(targets)} targets for {N} images")
+        boxes = [t["boxes"] for t in targets]
+        labels = [t["labels"] for t in targets]
+        counts = [b.shape[0] if b.numel() else 0 for b in boxes]
+        if sum(counts) > self.max_targets:
+            raise ValueError(f"{sum(counts)} GT boxes exceed max_targets={self.max_targets} of this graph")
+        dev = self.dev
+        for b, l, c in zip(boxes, labels, counts):
+            if c and not (b.dtype == torch.float32 and b.device == dev and b.is_contiguous() and l.dtype == torch.int64
+                          and l.device == dev and l.is_contiguous() and l.numel() == c and b.dim() == 2 and b.shape[1] == 4):
+                raise _native.NativeError("HotPathGraph.load_targets: boxes must be contiguous CUDA fp32 [G,4] and labels "
+                                          "contiguous CUDA int64 [G] on the graph's device")
+        bp = (_vp * N)(*[b.data_ptr() if c else None for b, c in zip(boxes, counts)])
+        lp = (_vp * N)(*[l.data_ptr() if c else None for l, c in zip(labels, counts)])
+        cnt = (ctypes.c_int32 * N)(*counts)
+        with _native.on_device(dev):
+            rc = self.lib.rn_pack_targets(bp, lp, cnt, N, None, self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(),
+                                          self.gt_off.data_ptr(), _native.stream_ptr(dev))
+        _native.check(rc, "rn_pack_targets")
+
+    def step(self, targets: Optional[Sequence[Dict[str, Tensor]]] = None) -> GraphStepResult:
+        """One pass of the path over the current contents of ``cls_preds`` / ``bbox_preds``.  ``targets=None`` keeps the
+        ground truth loaded by the last :meth:`load_targets`."""
+        if self.train and targets is not None:
+            self.load_targets(targets)
+        self.graph.replay()
+        if self.train and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.total, group=self.group)       # the one collective of the path: 16 bytes
+        ev = None
+        if self.detect:
+            self._host.copy_(self.meta, non_blocking=True)      # the single D2H copy of the path
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev))
+        return GraphStepResult(self, ev)

@@ -1,0 +1,105 @@
+"""GPU tests (-m gpu) of ``HotPathGraph``: the CUDA graph of the path must give bit-identical results to
+the drop-in calls (same kernels, same arguments), which the parity tests pin against the oracle; it is also
+checked against the oracle directly at the north-star tolerances."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import synth_data as S
+from helpers import rel_close, to_cuda_targets
+from oracle import torch_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pytorch_retinanet_b200 as pkg
+    from pytorch_retinanet_b200 import _native
+    _native.load()
+    return pkg
+
+
+def _dropin(P, cfg, x, bb, anc, tg, im_szs):
+    n = x.shape[0]
+    xg, bg = x.clone().requires_grad_(True), bb.clone().requires_grad_(True)
+    L = P.RetinaNetLosses(cfg.num_classes)
+    out = L(tg, {"cls_preds": xg, "bbox_preds": bg}, [anc] * n)
+    (out["classification_loss"] + out["regression_loss"]).backward()
+    stub = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
+    dets = P.process_detections(stub, {"cls_preds": x, "bbox_preds": bb}, [anc] * n, im_szs)
+    return out, xg.grad, bg.grad, L.last_per_image.clone(), dets
+
+
+def _assert_same_dets(a, b):
+    assert len(a) == len(b)
+    for d, r in zip(a, b):
+        for k in ("boxes", "scores", "labels"):
+            assert d[k].dtype == r[k].dtype and d[k].shape == r[k].shape, k
+            assert torch.equal(d[k], r[k]), k
+
+
+@pytest.mark.parametrize("concurrent", [True, False])
+@pytest.mark.parametrize("cid,n_img", [(1, 3), (2, 4)])
+def test_graph_step_equals_dropin_calls(P, cid, n_img, concurrent):
+    from pytorch_retinanet_b200.graphs import HotPathGraph
+    cfg = S.CONFIGS[cid]
+    dev = torch.device("cuda")
+    b = S.make_batch(cfg, 7, n_img, clustered=True)
+    anc = b["anchors"].to(dev)
+    x, bb = b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
+    tg = to_cuda_targets(b["targets"])
+    g = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"], max_targets=2048, concurrent=concurrent)
+    for rep in range(3):                      # replays; the 2nd with other targets and inputs written into the static buffers
+        if rep == 1:
+            b2 = S.make_batch(cfg, 100, n_img, clustered=True)
+            x.copy_(b2["cls_preds"])
+            bb.copy_(b2["bbox_preds"])
+            tg = to_cuda_targets(b2["targets"])
+            tg[1] = {"boxes": torch.zeros((0, 4), device=dev), "labels": torch.zeros((0,), dtype=torch.int64, device=dev)}
+        res = g.step(tg)
+        want_out, want_gx, want_gb, want_img, want_dets = _dropin(P, cfg, x, bb, anc, tg, b["im_szs"])
+        got = res.losses
+        for k in want_out:
+            assert torch.equal(got[k], want_out[k].detach()), (k, float(got[k]), float(want_out[k]))
+        assert torch.equal(res.per_image, want_img)
+        gx, gb = res.grads
+        assert torch.equal(gx, want_gx) and torch.equal(gb, want_gb)
+        _assert_same_dets(res.detections(), want_dets)
+    # and against the oracle (CPU restatement of the reference), north-star tolerances
+    xo, bo = x.cpu().requires_grad_(True), bb.cpu().requires_grad_(True)
+    cpu_t = [{k: v.cpu() for k, v in t.items()} for t in tg]
+    want = O.batch_loss(cpu_t, xo, bo, [b["anchors"]] * n_img, cfg.num_classes)
+    (want["classification_loss"] + want["regression_loss"]).backward()
+    for k in want:
+        assert rel_close(res.losses[k], want[k].detach(), 1e-5), k
+    assert torch.allclose(res.grads[0].cpu(), xo.grad, rtol=2e-5, atol=1e-9)
+    assert torch.allclose(res.grads[1].cpu(), bo.grad, rtol=2e-5, atol=1e-9)
+
+
+def test_graph_train_only_and_detect_only(P):
+    from pytorch_retinanet_b200.graphs import HotPathGraph
+    cfg = S.CONFIGS[1]
+    dev = torch.device("cuda")
+    b = S.make_batch(cfg, 3, 2, clustered=True)
+    anc = b["anchors"].to(dev)
+    x, bb = b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
+    tg = to_cuda_targets(b["targets"])
+    want_out, want_gx, _, _, want_dets = _dropin(P, cfg, x, bb, anc, tg, b["im_szs"])
+    gt = HotPathGraph(cfg.num_classes, x, bb, anc, train=True, detect=False)
+    r = gt.step(tg)
+    assert torch.equal(r.losses["classification_loss"], want_out["classification_loss"].detach())
+    assert torch.equal(r.grads[0], want_gx)
+    with pytest.raises(RuntimeError):
+        r.detections()
+    gd = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"], train=False, detect=True)
+    _assert_same_dets(gd.step().detections(), want_dets)
+    # a tiny candidate pool overflows: the result must come from the eager re-run and still be identical
+    gs = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"], train=False, detect=True, cand_capacity=8)
+    _assert_same_dets(gs.step().detections(), want_dets)
+    with pytest.raises(ValueError):
+        HotPathGraph(cfg.num_classes, x, bb, anc, train=True, detect=False, max_targets=4).step(tg)
+    from pytorch_retinanet_b200._native import NativeError
+    with pytest.raises(NativeError):
+        HotPathGraph(cfg.num_classes, x.cpu(), bb.cpu(), anc.cpu(), train=True, detect=False)
