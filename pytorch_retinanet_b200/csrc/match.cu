@@ -26,37 +26,11 @@
 //  * culling/pruning rely on 0 < bg_thr < fg_thr and on well-formed boxes (finite, x2>=x1,
 //    y2>=y1, anchors with positive area); malformed GT boxes or anchors fall back — per GT box /
 //    per warp — to the unculled NaN-propagating path, other thresholds disable both tricks.
-#include "rn_common.cuh"
+#include "match_body.cuh"
 
 namespace {
 
-constexpr int GT_TILE = 512;
-constexpr int MATCH_BLOCK = 256;
-
-// torch.max / torch.min / clamp(min=0) propagate NaN; fmaxf/fminf do not.
-__device__ __forceinline__ float nan_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
-__device__ __forceinline__ float nan_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
-
-__device__ __forceinline__ float box_area(const float4 b) {
-    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-}
-
-// Full reference arithmetic, NaN-propagating (slow path for malformed boxes / exotic thresholds).
-__device__ __forceinline__ float iou_generic(const float4 g, float ag, const float4 a, float aa) {
-    float w = __fsub_rn(nan_min(g.z, a.z), nan_max(g.x, a.x));
-    float h = __fsub_rn(nan_min(g.w, a.w), nan_max(g.y, a.y));
-    w = (w != w) ? w : fmaxf(w, 0.0f);
-    h = (h != h) ? h : fmaxf(h, 0.0f);
-    float inter = __fmul_rn(w, h);
-    float uni = __fsub_rn(__fadd_rn(ag, aa), inter);
-    return __fdiv_rn(inter, uni);
-}
-
-__device__ __forceinline__ bool box_well_formed(const float4 b) {
-    // finite coordinates and non-negative extent (NaN fails every comparison)
-    return (b.z >= b.x) && (b.w >= b.y) && (fabsf(b.x) <= 3.0e38f) && (fabsf(b.y) <= 3.0e38f) &&
-           (fabsf(b.z) <= 3.0e38f) && (fabsf(b.w) <= 3.0e38f);
-}
+using namespace rnmatch;
 
 template <bool FAST>
 __global__ void __launch_bounds__(MATCH_BLOCK)
@@ -76,95 +50,11 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
 
     float4 a = make_float4(0.f, 0.f, 1.f, 1.f);
     if (live) a = anchors[(long long)n * anchor_stride + ai];
-    const float aa = box_area(a);
+    const int m = match_block<FAST>(s_box, s_area, a, live, gt + g0, G, fg_thr, bg_thr, prune_c);
 
-    // warp-uniform: may this warp use culling / pruning / the non-NaN fast path?
-    bool warp_fast = FAST;
-    float bx1 = 0.f, by1 = 0.f, bx2 = 0.f, by2 = 0.f, ag_lo = 0.f, ag_hi = INFINITY;
-    if (FAST) {
-        // positive finite extents imply finite, ordered coordinates differences; NaN fails every test
-        bool ok = !live || ((a.z - a.x) > 0.0f && (a.w - a.y) > 0.0f && aa <= 3.0e38f && fabsf(a.x) <= 3.0e38f && fabsf(a.y) <= 3.0e38f);
-        warp_fast = __all_sync(0xffffffffu, ok);
-        bx1 = rn::warp_min(live ? a.x : INFINITY);
-        by1 = rn::warp_min(live ? a.y : INFINITY);
-        bx2 = rn::warp_max(live ? a.z : -INFINITY);
-        by2 = rn::warp_max(live ? a.w : -INFINITY);
-        const float amin = rn::warp_min(live ? aa : INFINITY), amax = rn::warp_max(live ? aa : 0.0f);
-        ag_lo = amin * prune_c * 0.999f;                 // GT areas outside [ag_lo, ag_hi] give IoU < bg_thr with
-        ag_hi = amax / (prune_c * 0.999f);               // every anchor of this warp (IoU <= area ratio)
-    }
-
-    float best = warp_fast ? 0.0f : -INFINITY;
-    int bi = 0;
-
-    for (int t0 = 0; t0 < G; t0 += GT_TILE) {
-        const int tn = min(GT_TILE, G - t0);
-        __syncthreads();
-        for (int j = threadIdx.x; j < tn; j += MATCH_BLOCK) {
-            float4 g = gt[g0 + t0 + j];
-            float ag = box_area(g);
-            s_box[j] = g;
-            s_area[j] = (box_well_formed(g) && ag <= 3.0e38f) ? ag : __int_as_float(0x7fc00000);
-        }
-        __syncthreads();
-
-        for (int base = 0; base < tn; base += 32) {
-            unsigned mask;
-            {
-                const int j = base + lane;
-                bool hit = j < tn;
-                if (hit && warp_fast) {
-                    float4 g = s_box[j];
-                    const float ag = s_area[j];
-                    float w = __fsub_rn(fminf(g.z, bx2), fmaxf(g.x, bx1));
-                    float h = __fsub_rn(fminf(g.w, by2), fmaxf(g.y, by1));
-                    hit = (ag != ag) || (w > 0.0f && h > 0.0f && ag >= ag_lo && ag <= ag_hi);
-                }
-                mask = __ballot_sync(0xffffffffu, hit);
-            }
-            while (mask) {
-                const int j = base + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float4 g = s_box[j];
-                const float ag = s_area[j];
-                const int gi = t0 + j;
-                if (warp_fast && ag == ag) {
-                    // well-formed pair: no NaN possible, IoU is +0 unless both extents are positive
-                    float w = __fsub_rn(fminf(g.z, a.z), fmaxf(g.x, a.x));
-                    float h = __fsub_rn(fminf(g.w, a.w), fmaxf(g.y, a.y));
-                    if (w > 0.0f && h > 0.0f) {
-                        float inter = __fmul_rn(w, h);
-                        float uni = __fsub_rn(__fadd_rn(ag, aa), inter);
-                        if (inter >= __fmul_rn(uni, prune_c)) {   // may reach bg_thr: exact quotient
-                            float v = __fdiv_rn(inter, uni);
-                            if (v > best) { best = v; bi = gi; }
-                        }
-                    }
-                } else {
-                    float v = iou_generic(g, box_area(g), a, aa);   // s_area holds the NaN marker for malformed boxes
-                    if (best == best) {                             // NaN, once taken, stays
-                        if (v != v || v > best) { best = v; bi = gi; }
-                    }
-                }
-            }
-        }
-    }
-
-    long long m = -2;
-    if (G > 0) {
-        if (best < bg_thr) m = -1;
-        if (best > fg_thr) m = bi;
-    }
     if (live) {
-        if (matches) matches[(long long)n * A + ai] = m;
-        if (codes) {
-            int code = (int)m;
-            if (m >= 0) {
-                int col = (int)labels[g0 + m] - 1;                  // labels are 1-based (README.md:132)
-                code = (int)m | (col << 20);
-            }
-            codes[(long long)n * A + ai] = code;
-        }
+        if (matches) matches[(long long)n * A + ai] = (long long)m;
+        if (codes) codes[(long long)n * A + ai] = pack_code(m, labels + g0);
     }
     if (fg_count) {
         unsigned fgm = __ballot_sync(0xffffffffu, live && m >= 0);

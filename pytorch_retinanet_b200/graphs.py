@@ -3,15 +3,15 @@
 The drop-in entry points (``RetinaNetLosses.forward``, ``process_detections``) cost ~0.9 ms of host
 time per batch of 16 images (torch allocations, autograd, ctypes marshalling) for ~0.6 ms of GPU
 work, and they run the training half and the inference half back to back.  ``HotPathGraph`` captures
-the SAME C-ABI calls (``rn_match`` -> ``rn_loss`` with gradients; ``rn_postprocess``) once, for fixed
+the SAME C-ABI calls (``rn_train_loss`` = matcher + loss with gradients; ``rn_postprocess``) once, for fixed
 shapes and static buffers, into a CUDA graph:
 
-    capture stream:   rn_match ---------> rn_loss (fwd + gradients) -> finalize ---.
+    capture stream:   rn_train_loss (matcher pipelined into loss fwd + gradients) --.
     side stream (hi): score filter -> lazy NMS -> status --------------------------+--> join
 
 so that a step is one ``cudaGraphLaunch`` (+ one ``rn_pack_targets`` launch for the ragged ground
-truth and one 4*(N+4)-byte D2H copy of the detection counts), and the ALU-bound matcher and the
-latency-bound NMS (one CTA per image) run in the shadow of the two HBM-bound streaming kernels.
+truth and one 4*(N+4)-byte D2H copy of the detection counts), and the
+latency-bound NMS (one CTA per image) runs in the shadow of the HBM-bound loss kernel.
 Results are bit-identical to the drop-in calls (tests/test_gpu_graph.py) — the kernels and their
 arguments are the same; only the launch mechanism differs.
 
@@ -164,7 +164,7 @@ class HotPathGraph:
             self.per_image = torch.zeros((N, 3), dtype=f32, device=dev)
             self.grad_cls_preds = torch.empty_like(cls_preds)
             self.grad_bbox_preds = torch.empty_like(bbox_preds)
-            self._loss_ws_bytes = lib.rn_loss_workspace_bytes(N, A, C)
+            self._loss_ws_bytes = lib.rn_train_loss_workspace_bytes(N, A, C)
             self._loss_ws = torch.empty((self._loss_ws_bytes,), dtype=torch.uint8, device=dev)
         else:
             self.total = self.per_image = self.grad_cls_preds = self.grad_bbox_preds = None
@@ -186,8 +186,15 @@ class HotPathGraph:
 
     # ---- raw C-ABI launches on the CURRENT stream (the same calls the drop-in path makes) ----
     def _enqueue_train(self):
-        self._enqueue_match()
-        self._enqueue_loss()
+        lib, N, A, C = self.lib, self.N, self.A, self.C
+        alpha, gamma, beta, match_thr, back_thr = self.hp
+        rc = lib.rn_train_loss(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(), self.anchor_stride,
+                               self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(), self.gt_off.data_ptr(), N, A, C, match_thr,
+                               back_thr, alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div, self.codes.data_ptr(),
+                               self.fg.data_ptr(), self.per_image.data_ptr(), self.total.data_ptr(),
+                               self.grad_cls_preds.data_ptr(), self.grad_bbox_preds.data_ptr(), self._loss_ws.data_ptr(),
+                               self._loss_ws_bytes, _native.stream_ptr(self.dev))
+        _native.check(rc, "rn_train_loss")
 
     def _enqueue_match(self):
         lib, N, A = self.lib, self.N, self.A

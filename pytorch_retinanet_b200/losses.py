@@ -36,7 +36,7 @@ def _shared_anchors(anchors: Sequence[Tensor]) -> Tuple[Tensor, int]:
 def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
                        packed: PackedTargets, alpha: float, gamma: float, beta: float, match_thr: float,
                        back_thr: float, batch_div: float, want_grad: bool):
-    """Launches rn_match + rn_loss.  Returns (out_total [4], out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
+    """Launches rn_train_loss (matcher + loss + gradients + reduction, one kernel).  Returns (out_total [4], out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
     lib = _native.load()
     dev = cls_preds.device
     N, A, C = cls_preds.shape
@@ -48,21 +48,26 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
     b = bbox_preds.detach()
     x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
     b = b if (b.dtype == torch.float32 and b.is_contiguous()) else b.to(torch.float32).contiguous()
-    _, codes, fg = match_batch(anchors, anchor_stride, packed, A, match_thr, back_thr, False, True)
+    assert match_thr > back_thr                    # box_utils.py:66
+    codes = torch.empty((N, A), dtype=torch.int32, device=dev)
+    fg = torch.empty((N,), dtype=torch.int32, device=dev)
     out_total = torch.empty((4,), dtype=torch.float32, device=dev)
     out_image = torch.empty((N, 3), dtype=torch.float32, device=dev)
     gl = torch.empty_like(x) if want_grad else None
     gb = torch.empty_like(b) if want_grad else None
-    ws_bytes = lib.rn_loss_workspace_bytes(N, A, C)
+    ws_bytes = lib.rn_train_loss_workspace_bytes(N, A, C)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     with _native.on_device(dev):
-        rc = lib.rn_loss(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
-                         _native.ptr(anchors, torch.float32, "anchors"), anchor_stride,
-                         _native.ptr(packed.boxes), _native.ptr(packed.offsets), _native.ptr(codes), _native.ptr(fg),
-                         N, A, C, float(alpha), float(gamma), float(beta), _REG_WEIGHTS_C,
-                         float(batch_div), _native.ptr(out_image), _native.ptr(out_total), _native.ptr(gl),
-                         _native.ptr(gb), _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
-    _native.check(rc, "rn_loss")
+        # matcher + loss + gradients + final reduction: one launch (two when the fused kernel's preconditions fail)
+        rc = lib.rn_train_loss(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
+                               _native.ptr(anchors, torch.float32, "anchors"), anchor_stride,
+                               _native.ptr(packed.boxes, torch.float32, "target boxes"),
+                               _native.ptr(packed.labels, torch.int64, "target labels"), _native.ptr(packed.offsets),
+                               N, A, C, float(match_thr), float(back_thr), float(alpha), float(gamma), float(beta),
+                               _REG_WEIGHTS_C, float(batch_div), _native.ptr(codes), _native.ptr(fg),
+                               _native.ptr(out_image), _native.ptr(out_total), _native.ptr(gl), _native.ptr(gb),
+                               _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+    _native.check(rc, "rn_train_loss")
     return out_total, out_image, gl, gb, codes
 
 

@@ -103,3 +103,67 @@ def test_graph_train_only_and_detect_only(P):
     from pytorch_retinanet_b200._native import NativeError
     with pytest.raises(NativeError):
         HotPathGraph(cfg.num_classes, x.cpu(), bb.cpu(), anc.cpu(), train=True, detect=False)
+
+
+@pytest.mark.parametrize("case", ["cfg1", "cfg2", "crowd_tiles", "odd_A"])
+def test_single_launch_training_kernel_equals_two_kernel_sequence(P, case):
+    """rn_train_loss's fused kernel (matcher software-pipelined into the loss, in-kernel final reduction) must be
+    bit-identical to rn_match + rn_loss: losses, per-image values, gradients, codes, foreground counts; with and
+    without gradients; run repeatedly (any inter-CTA ordering bug would show up as a difference)."""
+    from pytorch_retinanet_b200 import _native
+    from pytorch_retinanet_b200.box_utils import PackedTargets
+    from pytorch_retinanet_b200.losses import fused_loss_forward
+    lib = _native.load()
+    dev = torch.device("cuda")
+    if case == "cfg1":
+        cfg, n_img = S.CONFIGS[1], 3
+        b = S.make_batch(cfg, 11, n_img, clustered=True)
+    elif case == "cfg2":
+        cfg, n_img = S.CONFIGS[2], 5
+        b = S.make_batch(cfg, 11, n_img, clustered=True)
+    elif case == "crowd_tiles":               # G = 500 and one image with G > GT_TILE (512): two shared-memory tiles
+        cfg, n_img = S.CONFIGS[5], 3
+        b = S.make_batch(cfg, 2, n_img, clustered=True)
+        t0, t1 = b["targets"][0], b["targets"][1]
+        b["targets"][0] = {"boxes": torch.cat([t0["boxes"], t1["boxes"][:200]]), "labels": torch.cat([t0["labels"], t1["labels"][:200]])}
+    else:                                      # A not a multiple of the CTA span, C = 20 (vec4), an image without GT
+        cfg, n_img = S.CONFIGS[1], 4
+        b = S.make_batch(cfg, 30, n_img, clustered=True)
+        keep = 49104 - 77
+        b["anchors"] = b["anchors"][:keep].contiguous()
+        b["cls_preds"] = b["cls_preds"][:, :keep].contiguous()
+        b["bbox_preds"] = b["bbox_preds"][:, :keep].contiguous()
+        b["targets"][2] = {"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)}
+    anc = b["anchors"].to(dev)
+    x, bb = b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
+    tg = to_cuda_targets(b["targets"])
+    packed = PackedTargets([t["boxes"] for t in tg], [t["labels"] for t in tg], dev)
+
+    def run(want_grad):
+        out = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 2.0, 0.1, 0.5, 0.4, float(n_img), want_grad)
+        torch.cuda.synchronize()
+        return out
+
+    old = lib.rn_train_loss_set_fused(0)
+    try:
+        ref = run(True)
+        ref_ng = run(False)
+    finally:
+        lib.rn_train_loss_set_fused(1)
+    assert old == 1
+    for rep in range(4):
+        got = run(True)
+        for g, r, name in zip(got, ref, ("total", "per_image", "grad_logits", "grad_bbox", "codes")):
+            assert torch.equal(g, r), (case, rep, name)
+    got_ng = run(False)
+    assert torch.equal(got_ng[0], ref_ng[0]) and torch.equal(got_ng[1], ref_ng[1]) and got_ng[2] is None
+    assert torch.equal(got_ng[0], ref[0])                         # forward values do not depend on the gradient variant
+    # generic gamma goes through the other template instance
+    a = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 1.5, 0.1, 0.5, 0.4, float(n_img), True)
+    lib.rn_train_loss_set_fused(0)
+    try:
+        c = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 1.5, 0.1, 0.5, 0.4, float(n_img), True)
+    finally:
+        lib.rn_train_loss_set_fused(1)
+    for g, r in zip(a, c):
+        assert torch.equal(g, r)

@@ -21,30 +21,42 @@ def main(rep, kern, cubin, src=None):
     dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout.splitlines()
     # locate the kernel's text section
     start = next(i for i, l in enumerate(dis) if l.startswith("\t.section\t.text.") and kern in l)
-    line, off2line = 0, {}
+    line, off2line = (None, 0), {}
     for l in dis[start + 1:]:
         if l.startswith("\t.section"):
             break
-        m = re.search(r'//## File ".*", line (\d+)', l)
+        m = re.search(r'//## File "(.*)", line (\d+)', l)
         if m:
-            line = int(m.group(1))
+            line = (m.group(1), int(m.group(2)))
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/", l)
         if m:
             off2line[int(m.group(1), 16)] = line
     agg = {}
     for off, (s, ie, txt) in samples.items():
-        ln = off2line.get(off, -1)
+        ln = off2line.get(off, (None, -1))
         a = agg.setdefault(ln, [0, 0, 0])
         a[0] += s
         a[1] += ie
         a[2] += 1
     tot = sum(a[0] for a in agg.values())
-    srcl = open(src).read().splitlines() if src else None
+    cache = {}
+
+    def text_of(f, ln):
+        if f is None:
+            return ""
+        if f not in cache:
+            try:
+                cache[f] = open(f).read().splitlines()
+            except OSError:
+                cache[f] = []
+        L = cache[f]
+        return L[ln - 1].strip()[:90] if 0 < ln <= len(L) else ""
+
     print(f"total samples {tot}, instructions {len(samples)}")
-    for ln, (s, ie, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
-        text = srcl[ln - 1].strip()[:100] if srcl and 0 < ln <= len(srcl) else ""
-        print(f"line {ln:5d}: {s:6d} samples {100 * s / max(tot, 1):5.1f}%  warp-instr {ie:9d}  sass {n:4d} | {text}")
+    import os
+    for (f, ln), (s, ie, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+        print(f"{os.path.basename(f or '?'):16s}:{ln:5d}: {s:6d} samples {100 * s / max(tot, 1):5.1f}%  warp-instr {ie:9d}  sass {n:4d} | {text_of(f, ln)}")
 
 
 if __name__ == "__main__":
