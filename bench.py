@@ -346,15 +346,7 @@ def run_ours(args, rank, world, local_rank):
         return fused_loss_forward(d_cls, d_box, anc, 0, packed, 0.25, 2.0, 0.1, 0.5, 0.4, float(n_img), want_grad)
 
     kern = {}
-    def loss_two_kernels():
-        lib.rn_train_loss_set_fused(0)
-        try:
-            return loss_only(True)
-        finally:
-            lib.rn_train_loss_set_fused(1)
-
     for name, fn in (("loss_fwd_bwd", lambda: loss_only(True)), ("loss_fwd", lambda: loss_only(False)),
-                     ("loss_fwd_bwd_two_kernels", loss_two_kernels),  # rn_match, then rn_loss (+ finalize): the unfused sequence
                      ("loss_kernel_alone", graph._enqueue_loss),     # loss_kernel<4,grad> + finalize on precomputed codes
                      ("postprocess", lambda: postprocess_batch(d_cls, d_box, anc, 0, batch["im_szs"], 0.05, 0.5, 100))):
         for _ in range(3):
@@ -396,8 +388,8 @@ def run_ours(args, rank, world, local_rank):
     bytes_f = n_img * (4 * A * C + 16 * A) + 16 * A + 24 * gsum + 12 * n_img               # B_f
     bytes_p = n_img * (4 * A * C + 16 * A + 100 * 28) + 16 * A                             # B_p
     ach_fb = bytes_fb / (kern["loss_fwd_bwd"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "train_fused_kernel<grad> = rn_train_loss: matcher software-pipelined into the loss "
-                                          "fwd+grad stream, in-kernel final reduction (ONE launch)",
+    roofline = {"bound": "hbm", "kernel": "rn_train_loss = match_kernel + loss_kernel<4,grad> + finalize (training loss, "
+                                          "fwd+grad in one pass over the logits)",
                 "achieved": ach_fb, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach_fb / peak,
                 "traffic": 2.076e9 + 4.9e6, "traffic_note": "ncu --set full, loss_kernel 1.047 GB read + 1.029 GB write, "
                 "match_kernel 3.3 MB, finalize < 1 MB per launch (profiles/r01_notes.md)", "bytes_per_launch": bytes_fb, "ms_per_launch": kern["loss_fwd_bwd"],
@@ -405,10 +397,6 @@ def run_ours(args, rank, world, local_rank):
                                         "frac": bytes_f / (kern["loss_fwd"] * 1e-3) / 1e9 / peak},
                            "postprocess": {"GBps": bytes_p / (kern["postprocess"] * 1e-3) / 1e9, "ms": kern["postprocess"],
                                            "frac": bytes_p / (kern["postprocess"] * 1e-3) / 1e9 / peak},
-                           "loss_fwd_bwd_two_kernels": {"GBps": bytes_fb / (kern["loss_fwd_bwd_two_kernels"] * 1e-3) / 1e9,
-                                                        "ms": kern["loss_fwd_bwd_two_kernels"],
-                                                        "frac": bytes_fb / (kern["loss_fwd_bwd_two_kernels"] * 1e-3) / 1e9 / peak,
-                                                        "note": "rn_match + rn_loss + finalize as three launches (A/B of the fusion)"},
                            "loss_kernel_alone": {"GBps": bytes_fb / (kern["loss_kernel_alone"] * 1e-3) / 1e9,
                                                  "ms": kern["loss_kernel_alone"],
                                                  "frac": bytes_fb / (kern["loss_kernel_alone"] * 1e-3) / 1e9 / peak,
@@ -444,7 +432,7 @@ def run_ours(args, rank, world, local_rank):
                     "dropin_pipelined": {"value": total / (ms_pipe * 1e-3), "unit": "images/s", "ms_per_step": ms_pipe,
                                          "note": "drop-in calls with process_detections_async: results of step i read while "
                                                  "step i+1 is enqueued"}},
-            "gpu_launches": args.steps * 5,    # per graph step: pack_targets, train_fused, score filter, lazy NMS, status
+            "gpu_launches": args.steps * 7,    # per graph step: pack_targets, match, loss, finalize, score filter, lazy NMS, status
             "roofline": roofline, "cpu_baseline": cpu, "n1_levels": n1,
         }
         print(json.dumps(line), flush=True)

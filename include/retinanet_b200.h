@@ -110,14 +110,12 @@ int rn_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, cons
             float *out_total /*[4]*/, float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/,
             void *workspace, size_t workspace_bytes, rn_stream_t stream);
 
-/* The training half of the path in ONE launch: rn_match (codes + foreground counts) fused with rn_loss and its
- * final reduction — same arguments, same outputs, bit-identical results (retinanet/losses.py:113-145 with
- * box_utils.py:51-80 inside).  The matcher is ALU-bound and the loss HBM-bound; the kernel software-pipelines
- * them across images (CTAs match image r, then stream image r-1 once all of it is matched — the per-image
- * foreground count scales its gradients), so the matching hides under the streaming.  `codes` [N,A] and
- * `fg_count` [N] are outputs here (scratch for the caller, same contents as rn_match writes).  Falls back to
- * rn_match + rn_loss internally when C % 4 != 0, buffers are not 16-byte aligned, back_thr <= 0 or the PRECISE
- * test mode is on.  workspace: rn_train_loss_workspace_bytes(N, A, C).                                    */
+/* The training half of the path behind ONE call: rn_match (codes + foreground counts) followed by rn_loss and its
+ * final reduction on the same stream — same arguments, same outputs (retinanet/losses.py:113-145 with
+ * box_utils.py:51-80 inside).  `codes` [N,A] and `fg_count` [N] are outputs here (scratch for the caller, same
+ * contents as rn_match writes).  workspace: rn_train_loss_workspace_bytes(N, A, C).
+ * (Two single-launch fusions of the two kernels were measured slower than the sequence on B200 and are not shipped:
+ * see DESIGN.md 4.3b.)                                                                                     */
 size_t rn_train_loss_workspace_bytes(int N, int64_t A, int C);
 int rn_train_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, const float *anchors,
                   int64_t anchor_image_stride, const float *gt_boxes /*[sumG,4]*/, const int64_t *gt_labels /*[sumG]*/,
@@ -126,10 +124,6 @@ int rn_train_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/
                   int32_t *fg_count /*[N]*/, float *out_image /*[N,3]*/, float *out_total /*[4]*/,
                   float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/, void *workspace,
                   size_t workspace_bytes, rn_stream_t stream);
-
-/* Test / A-B hook: 0 makes rn_train_loss always run the rn_match + rn_loss sequence, 1 (default) lets it use the
- * single-launch kernel.  Returns the previous setting.  Process-global.                                   */
-int rn_train_loss_set_fused(int on);
 
 /* Dense element-wise losses, API parity with RetinaNetLosses.focal_loss (losses.py:29-47, arbitrary
  * float targets of the logits' shape, NO +1 shift) and RetinaNetLosses.smooth_l1_loss (losses.py:19-27).

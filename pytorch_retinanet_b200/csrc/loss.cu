@@ -26,7 +26,6 @@
 #include <cstring>
 
 #include "loss_math.cuh"
-#include "match_body.cuh"
 #include "rn_common.cuh"
 
 namespace {
@@ -36,7 +35,6 @@ constexpr int LOSS_SPAN = 256;   // anchors per CTA
 constexpr int LOSS_U = 4;        // 128-bit loads in flight per thread
 
 static int g_math_mode = 0;      // 0 fast, 1 precise
-static int g_train_fused = 1;    // 0: rn_train_loss always runs the rn_match + rn_loss sequence (test / A-B hook)
 
 struct LossParams {
     const float *logits;
@@ -60,15 +58,6 @@ struct LossParams {
 
 using namespace rnloss;
 
-// Barrier over the LOSS_BLOCK streaming threads: the whole CTA (NBAR = 0) or, in the warp-specialised training
-// kernel whose CTAs carry extra matcher warps, named barrier NBAR.
-template <int NBAR>
-__device__ __forceinline__ void loss_bar() {
-    if (NBAR == 0) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(NBAR), "r"(LOSS_BLOCK) : "memory");
-}
-
-template <int NBAR = 0>
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
     __shared__ double s[3][LOSS_BLOCK / 32];
     a = rn::warp_sum(a);
@@ -76,7 +65,7 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
     c = rn::warp_sum(c);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) { s[0][w] = a; s[1][w] = b; s[2][w] = c; }
-    loss_bar<NBAR>();
+    __syncthreads();
     if (threadIdx.x == 0) {
         a = b = c = 0.0;
 #pragma unroll
@@ -84,21 +73,16 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
     }
 }
 
-// Loads of the packed codes / foreground counts: read-only path when an earlier launch wrote them, L2
-// (ld.global.cg) when other CTAs of the SAME launch did (train_fused_kernel).
-template <bool SAME_LAUNCH>
-__device__ __forceinline__ int ld_code(const int *p) { return SAME_LAUNCH ? __ldcg(p) : __ldg(p); }
-
 // One CTA's share of the loss: LOSS_SPAN anchors of image n.  Writes the CTA's partial sums.
 // VEC = 4: C % 4 == 0 and 16-byte aligned rows (128-bit path); VEC = 1: any C (scalar path).
-template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE, bool SAME_LAUNCH>
+template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
 __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, const int chunk) {
     const long long a0 = (long long)chunk * LOSS_SPAN;
     const int span = (int)min((long long)LOSS_SPAN, P.A - a0);
     const long long row0 = (long long)n * P.A + a0;
     const int CV = P.C / VEC;                       // vectors per anchor row
     const int nvec = span * CV;
-    const int F = ld_code<SAME_LAUNCH>(P.fg_count + n);
+    const int F = __ldg(P.fg_count + n);
     const float inv = 1.0f / (fmaxf((float)F, 1.0f) * P.batch_div);   // gradient scale
     const float neg_gscale = P.alpha * inv;
     const float *src = P.logits + row0 * P.C;
@@ -128,7 +112,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
             if (valid[u]) {
                 const int al = P.magic ? (int)__umulhi((unsigned)f, P.magic) : f;   // f / CV
                 c0[u] = (f - al * CV) * VEC;
-                code[u] = ld_code<SAME_LAUNCH>(codes + al);
+                code[u] = __ldg(codes + al);
             }
         }
 #pragma unroll
@@ -190,7 +174,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     // ---- regression: one thread per anchor of the span (losses.py:66-71, 19-27) ----
     float reg = 0.0f;
     if (threadIdx.x < span) {
-        const int code = ld_code<SAME_LAUNCH>(codes + threadIdx.x);
+        const int code = __ldg(codes + threadIdx.x);
         float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (code >= 0) {
             const float4 gtb = P.gt[P.gt_off[n] + (code & 0xFFFFF)];
@@ -219,7 +203,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     }
 
     double s_neg = acc_neg, s_pos = acc_pos, s_reg = reg;
-    block_sum3<SAME_LAUNCH ? 1 : 0>(s_neg, s_pos, s_reg);
+    block_sum3(s_neg, s_pos, s_reg);
     if (threadIdx.x == 0) {
         double *o = P.partials + ((long long)n * P.chunks + chunk) * 2;
         o[0] = (double)P.alpha * s_neg + s_pos;
@@ -229,15 +213,14 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
 
 template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
 __global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : 5) loss_kernel(const LossParams P) {
-    loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE, false>(P, blockIdx.y, blockIdx.x);
+    loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE>(P, blockIdx.y, blockIdx.x);
 }
 
 // Fixed-order final reduction: block n reduces image n's chunk partials (thread-strided partial sums, then a
 // fixed tree), the last block to finish (ticket) sums the images in index order.  The summation order
 // depends only on (N, chunks) => bit-reproducible.  `tail` = [N][2] image sums + ticket, after the partials.
 constexpr int FIN_BLOCK = 256;
-// Called by all FIN_BLOCK threads of a CTA for image n (the partials may have been written by other CTAs of the
-// same launch: they are read through L2).
+// Called by all FIN_BLOCK threads of a CTA for image n.
 __device__ __forceinline__ void finalize_image(const double *partials, const int *fg_count, const int n, const int N,
                                                const int chunks, const float batch_div, float *__restrict__ out_image,
                                                float *__restrict__ out_total, double *tail) {
@@ -310,197 +293,6 @@ __global__ void __launch_bounds__(256) scale_kernel(float *__restrict__ buf, lon
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] *= s;
 }
 
-
-// ---- the whole training path in ONE launch: matcher + loss (+ gradients) + final reduction ----------------
-// rn_match is ALU-bound (no memory traffic to speak of) and the loss kernel HBM-bound, so run back to back they
-// leave each other's resource idle, and kernels of one stream do not overlap.  Fusing them naively is blocked by
-// a batch-wide dependency: the gradient of image n is scaled by 1 / max(1, F_n), the number of foreground
-// anchors of the WHOLE image (losses.py:108-109).
-// train_persistent_kernel: persistent, warp-specialised CTAs (one grid of SMs x TR_CTAS_PER_SM, all resident):
-//   * warps 0..7 ("streamers", 256 threads, named barrier 1) pull loss tiles (image n, chunk of 256 anchors) from
-//     an atomic ticket in image-major order and run exactly the loss_kernel body on them;
-//   * warp 8 ("matcher") pulls matching tasks (image r, 256 anchors = 8 groups of 32) from a second ticket, also in
-//     image-major order, with the image's GT staged in its private shared tile, writes codes, adds to F_r and
-//     releases done[r]; it never waits for anything, so it always makes progress and stays an image or more ahead
-//     (it needs ~1/3 of the streamers' time);
-//   * a streamer tile of image n first acquires done[n] == chunks (thread 0 polls; normally true long before).
-// The matcher's instructions fill issue slots the HBM-bound streamers leave empty, and none of its latencies
-// (ticket, GT staging, membar) sits in a barrier path of the streamers.
-// Final reduction without a second launch and without a fence in the streaming loop: the per-tile partial sums are
-// published into slots pre-set to a NaN sentinel (memset 0xFF); the CTA that takes the LAST ticket-ordered
-// increment of img_done[n] (relaxed atomic, its result is consumed one tile later) reduces the image's slots in the
-// fixed order of loss_finalize_kernel, spinning on any slot that is still the sentinel => bit-identical results.
-constexpr int TR_STREAM_THREADS = LOSS_BLOCK;             // 8 warps
-constexpr int TR_BLOCK = LOSS_BLOCK + 32;                 // + 1 matcher warp
-#ifndef TR_CTAS_PER_SM
-#define TR_CTAS_PER_SM 4
-#endif
-constexpr int TR_GROUPS = LOSS_SPAN / 32;                 // anchor groups per matching task
-
-struct TrainParams {
-    LossParams L;
-    const long long *labels;     // [sumG] 1-based class ids
-    int *codes_w;                // [N,A] written by the matcher warps (same buffer as L.codes)
-    int *fg_w;                   // [N]   zeroed by the host before the launch (same buffer as L.fg_count)
-    unsigned *ctrl;              // zeroed: [0] streamer ticket, [1] matcher ticket, [2..2+N) done, [2+N..2+2N) img_done
-    double *tail;                // [2N] image sums + finalize ticket
-    float *out_image, *out_total;
-    float fg_thr, bg_thr, prune_c;
-    int N;
-    int stream_only;             // experiment: codes / counts precomputed by rn_match, matcher warps idle
-};
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_volatile_f64(const double *p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Warp-level version of finalize_image with the SAME summation order (lane l plays threads l, l+32, .. of the
-// 256-thread reduction), reading sentinel-guarded slots.
-__device__ __forceinline__ void finalize_image_warp(const TrainParams &T, const int n) {
-    const LossParams &P = T.L;
-    const int lane = threadIdx.x & 31;
-    const double *p = P.partials + (long long)n * P.chunks * 2;
-    double cs = 0.0, rs = 0.0;
-#pragma unroll 1
-    for (int w = 0; w < FIN_BLOCK / 32; ++w) {
-        double c = 0.0, r = 0.0;
-        for (int k = w * 32 + lane; k < P.chunks; k += FIN_BLOCK) {
-            double vx, vy;
-            do {                                           // the slot's writer may still be in flight
-                vx = ld_volatile_f64(p + 2 * k);
-                vy = ld_volatile_f64(p + 2 * k + 1);
-            } while (__double_as_longlong(vx) == -1LL || __double_as_longlong(vy) == -1LL);
-            c += vx;
-            r += vy;
-        }
-        c = rn::warp_sum(c);
-        r = rn::warp_sum(r);
-        cs += c;
-        rs += r;
-    }
-    if (lane == 0) {
-        const int F = __ldcg(P.fg_count + n);
-        const double den = F > 0 ? (double)F : 1.0;             // clamp(F, min=1)  losses.py:108-109
-        cs /= den;
-        rs /= den;
-        T.tail[2 * n] = cs;
-        T.tail[2 * n + 1] = rs;
-        if (T.out_image) {
-            T.out_image[3 * n + 0] = (float)cs;
-            T.out_image[3 * n + 1] = (float)rs;
-            T.out_image[3 * n + 2] = (float)F;
-        }
-        __threadfence();
-        unsigned *ticket = (unsigned *)(T.tail + 2 * (long long)T.N);
-        if (atomicAdd(ticket, 1u) == (unsigned)(T.N - 1)) {    // last image: sum the batch in index order
-            __threadfence();
-            double c2 = 0.0, r2 = 0.0;
-            long long fsum = 0;
-            for (int i = 0; i < T.N; ++i) {
-                c2 += ld_volatile_f64(T.tail + 2 * i);
-                r2 += ld_volatile_f64(T.tail + 2 * i + 1);
-                fsum += __ldcg(P.fg_count + i);
-            }
-            T.out_total[0] = (float)(c2 / (double)P.batch_div);   // losses.py:138-140
-            T.out_total[1] = (float)(r2 / (double)P.batch_div);
-            T.out_total[2] = (float)fsum;
-            T.out_total[3] = (float)T.N;
-        }
-    }
-}
-
-template <bool WANT_GRAD, bool GAMMA2>
-__global__ void __launch_bounds__(TR_BLOCK, TR_CTAS_PER_SM) train_persistent_kernel(const __grid_constant__ TrainParams T) {
-    static_assert(rnmatch::MATCH_BLOCK == LOSS_SPAN, "a matching task covers one loss chunk");
-    __shared__ float4 s_box[rnmatch::GT_TILE];
-    __shared__ float s_area[rnmatch::GT_TILE];
-    __shared__ unsigned s_tile;
-    const LossParams &P = T.L;
-    const unsigned total = (unsigned)P.chunks * (unsigned)T.N;
-    unsigned *done = T.ctrl + 2, *img_done = T.ctrl + 2 + T.N;
-
-    if (threadIdx.x >= TR_STREAM_THREADS) {
-        // ================= matcher warp =================
-        if (T.stream_only) return;
-        const int lane = threadIdx.x & 31;
-        unsigned next = 0;
-        if (lane == 0) next = atomicAdd(T.ctrl + 1, 1u);
-        int staged_r = -1;
-        while (true) {
-            const unsigned t = __shfl_sync(0xffffffffu, next, 0);
-            if (t >= total) break;
-            if (lane == 0) next = atomicAdd(T.ctrl + 1, 1u);          // prefetch the next task
-            const int r = (int)(t / (unsigned)P.chunks), chunk = (int)(t - (unsigned)r * (unsigned)P.chunks);
-            const int g0 = P.gt_off[r], G = P.gt_off[r + 1] - g0;
-            const bool single = G <= rnmatch::GT_TILE;
-            if (single && staged_r != r) {
-                __syncwarp();
-                rnmatch::stage_gt_tile(s_box, s_area, P.gt + g0, G, lane, 32);
-                __syncwarp();
-            }
-            staged_r = single ? r : -1;
-            int fg = 0;
-#pragma unroll 1
-            for (int g = 0; g < TR_GROUPS; ++g) {
-                const long long ai = (long long)chunk * LOSS_SPAN + g * 32 + lane;
-                const bool live = ai < P.A;
-                float4 a = make_float4(0.f, 0.f, 1.f, 1.f);
-                if (live) a = P.anchors[(long long)r * P.anchor_stride + ai];
-                const int m = rnmatch::match_warp<true>(s_box, s_area, a, live, P.gt + g0, G, T.fg_thr, T.bg_thr, T.prune_c, single);
-                if (live) T.codes_w[(long long)r * P.A + ai] = rnmatch::pack_code(m, T.labels + g0);
-                fg += __popc(__ballot_sync(0xffffffffu, live && m >= 0));
-            }
-            __syncwarp();
-            if (lane == 0) {
-                if (fg) atomicAdd(T.fg_w + r, fg);
-                __threadfence();                                       // codes + count before the release
-                atomicAdd(done + r, 1u);
-            }
-        }
-        return;
-    }
-
-    // ================= streamers: 8 warps, named barrier 1 =================
-    unsigned next = 0, pending_old = 0;
-    int pending_n = -1, ready_n = -1;
-    if (threadIdx.x == 0) next = atomicAdd(T.ctrl, 1u);
-    while (true) {
-        if (threadIdx.x == 0) s_tile = next;
-        loss_bar<1>();
-        const unsigned t = s_tile;
-        if (t >= total) break;
-        const int n = (int)(t / (unsigned)P.chunks), chunk = (int)(t - (unsigned)n * (unsigned)P.chunks);
-        if (threadIdx.x == 0) {
-            next = atomicAdd(T.ctrl, 1u);                              // prefetch: consumed at the top of the next iteration
-            if (n > ready_n && !T.stream_only) {
-                while (ld_acquire_u32(done + n) < (unsigned)P.chunks) __nanosleep(200);
-                ready_n = n;
-            }
-        }
-        loss_bar<1>();                                                 // image n is matched; s_tile may be rewritten
-        loss_chunk<4, WANT_GRAD, GAMMA2, false, true>(P, n, chunk);   // thread 0 publishes the tile's partial sums
-        if (threadIdx.x < 32) {
-            // election of the image's finisher, one tile late so that the atomic's latency is off the critical path
-            const int fin_n = __shfl_sync(0xffffffffu, (pending_n >= 0 && pending_old == (unsigned)(P.chunks - 1)) ? pending_n : -1, 0);
-            if (fin_n >= 0) finalize_image_warp(T, fin_n);
-            if (threadIdx.x == 0) {
-                pending_old = atomicAdd(img_done + n, 1u);
-                pending_n = n;
-            }
-        }
-    }
-    if (threadIdx.x < 32) {
-        const int fin_n = __shfl_sync(0xffffffffu, (pending_n >= 0 && pending_old == (unsigned)(P.chunks - 1)) ? pending_n : -1, 0);
-        if (fin_n >= 0) finalize_image_warp(T, fin_n);
-    }
-}
 
 template <int VEC, bool WANT_GRAD, bool GAMMA2>
 void launch_loss(const LossParams &P, dim3 grid, cudaStream_t s, bool precise) {
@@ -580,18 +372,14 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     return 0;
 }
 
-// ---- rn_train_loss: rn_match + rn_loss in one launch (falls back to the two-call sequence when the fused
-// kernel's preconditions do not hold: C % 4, alignment, bg_thr <= 0, PRECISE test mode) ----
-extern "C" int rn_train_loss_set_fused(int on) {
-    int old = g_train_fused;
-    g_train_fused = on;
-    return old;
-}
-
-extern "C" size_t rn_train_loss_workspace_bytes(int N, int64_t A, int C) {
-    if (N <= 0 || A <= 0) return 64;
-    return rn_loss_workspace_bytes(N, A, C) + (size_t)(2 + 2 * (size_t)N + 2) * sizeof(unsigned);
-}
+// ---- rn_train_loss: the training half of the path behind ONE C call (rn_match, then rn_loss + final reduction on
+// the same stream).  Two single-launch fusions of the matcher into the loss stream were built and measured on
+// B200 (ticket-lagged CTAs; persistent warp-specialised CTAs with a dedicated matcher warp): both bit-identical,
+// both SLOWER than this sequence (427 / 473 us vs 392 us at config 2) because the loss kernel already runs at
+// ~0.95 of the measured HBM peak with 74 % of its issue slots busy — the matcher's instructions do not fit in the
+// remaining slots and every in-kernel dependency (ticket, acquire, election) costs the streamers a round trip.
+// See profiles/r01_notes.md ("single-launch training kernel") and the two ncu summaries next to it.
+extern "C" size_t rn_train_loss_workspace_bytes(int N, int64_t A, int C) { return rn_loss_workspace_bytes(N, A, C); }
 
 extern "C" int rn_train_loss(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
                              const float *gt_boxes, const int64_t *gt_labels, const int32_t *gt_off, int N, int64_t A, int C,
@@ -599,71 +387,12 @@ extern "C" int rn_train_loss(const float *logits, const float *bbox, const float
                              float batch_div, int32_t *codes, int32_t *fg_count, float *out_image, float *out_total,
                              float *grad_logits, float *grad_bbox, void *workspace, size_t workspace_bytes,
                              rn_stream_t stream) {
-    RN_CHECK_ARG(logits && bbox && anchors && gt_off && gt_boxes && gt_labels && codes && fg_count && out_total && weights_host,
-                 RN_E_BADARG, "rn_train_loss: null pointer");
-    RN_CHECK_ARG(N > 0 && A > 0 && C > 0, RN_E_BADARG, "rn_train_loss: N, A, C must be positive (got %d, %lld, %d)", N,
-                 (long long)A, C);
-    RN_CHECK_ARG(C <= 2048, RN_E_TOOLARGE, "rn_train_loss: C=%d exceeds 2048 classes", C);
-    RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_train_loss: N=%d exceeds 65535 images per call", N);
-    RN_CHECK_ARG(fg_thr > bg_thr, RN_E_BADARG, "rn_train_loss: match_thr (%g) must exceed back_thr (%g) (box_utils.py:66)",
-                 (double)fg_thr, (double)bg_thr);
-    RN_CHECK_ARG((grad_logits == nullptr) == (grad_bbox == nullptr), RN_E_BADARG,
-                 "rn_train_loss: grad_logits and grad_bbox must be given together");
-    RN_CHECK_ARG(batch_div > 0.0f, RN_E_BADARG, "rn_train_loss: batch_div must be positive");
-    RN_CHECK_ARG(workspace && workspace_bytes >= rn_train_loss_workspace_bytes(N, A, C), RN_E_WORKSPACE,
-                 "rn_train_loss: workspace too small (%zu < %zu)", workspace_bytes, rn_train_loss_workspace_bytes(N, A, C));
-    const bool vec4 = (C % 4 == 0) && (((uintptr_t)logits & 15) == 0) && (!grad_logits || ((uintptr_t)grad_logits & 15) == 0);
-    const int chunks = loss_chunks(A);
-    const bool fused = g_train_fused && vec4 && bg_thr > 0.0f && g_math_mode == 0 && (long long)chunks * N < 0x7fffffffLL;
-    if (!fused) {
-        int rc = rn_match(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, fg_thr, bg_thr, nullptr, codes,
-                          fg_count, stream);
-        if (rc) return rc;
-        return rn_loss(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma,
-                       beta, weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, workspace_bytes,
-                       stream);
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    TrainParams T;
-    LossParams &P = T.L;
-    P.logits = logits; P.bbox = (const float4 *)bbox; P.anchors = (const float4 *)anchors;
-    P.gt = (const float4 *)gt_boxes; P.gt_off = gt_off; P.codes = codes; P.fg_count = fg_count;
-    P.grad_logits = grad_logits; P.grad_bbox = (float4 *)grad_bbox; P.partials = (double *)workspace;
-    P.A = A; P.anchor_stride = anchor_image_stride; P.C = C; P.chunks = chunks;
-    P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
-    P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
-    const int CV = C / 4;
-    P.magic = CV == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)CV - 1) / (unsigned)CV);
-    T.codes_w = codes; T.fg_w = fg_count;
-    T.tail = (double *)workspace + (size_t)N * chunks * 2;
-    T.ctrl = (unsigned *)(T.tail + 2 * (size_t)N + 2);
-    T.labels = (const long long *)gt_labels;
-    T.out_image = out_image; T.out_total = out_total;
-    T.fg_thr = fg_thr; T.bg_thr = bg_thr; T.prune_c = bg_thr * (1.0f - 9.5367431640625e-07f);   // as rn_match
-    T.N = N;
-    // partial-sum slots <- NaN sentinel (0xFF..), tickets / counters / finalize ticket <- 0, foreground counts <- 0
-    cudaError_t e = cudaMemsetAsync(workspace, 0xFF, (size_t)N * chunks * 2 * sizeof(double), s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(T.tail + 2 * (size_t)N, 0, 2 * sizeof(double) + (size_t)(2 + 2 * (size_t)N) * sizeof(unsigned), s);
-    T.stream_only = g_train_fused == 2;
-    if (T.stream_only) {
-        int rc = rn_match(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, fg_thr, bg_thr, nullptr, codes, fg_count, stream);
-        if (rc) return rc;
-    } else if (e == cudaSuccess) e = cudaMemsetAsync(fg_count, 0, (size_t)N * sizeof(int32_t), s);
-    if (e != cudaSuccess) { rn_set_error("rn_train_loss: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
-    // persistent grid: every CTA resident (the matcher warps must all be able to run); fewer CTAs for tiny problems
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = RN_SM_COUNT_B200;
-    }
-    const long long tiles = (long long)chunks * N;
-    const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * TR_CTAS_PER_SM, tiles);
-    const bool g2 = gamma == 2.0f;
-    if (grad_logits) { if (g2) train_persistent_kernel<true, true><<<grid, TR_BLOCK, 0, s>>>(T); else train_persistent_kernel<true, false><<<grid, TR_BLOCK, 0, s>>>(T); }
-    else             { if (g2) train_persistent_kernel<false, true><<<grid, TR_BLOCK, 0, s>>>(T); else train_persistent_kernel<false, false><<<grid, TR_BLOCK, 0, s>>>(T); }
-    RN_CHECK_LAUNCH("rn_train_loss");
-    return 0;
+    RN_CHECK_ARG(gt_labels && codes && fg_count, RN_E_BADARG, "rn_train_loss: null pointer");
+    int rc = rn_match(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, fg_thr, bg_thr, nullptr, codes,
+                      fg_count, stream);
+    if (rc) return rc;
+    return rn_loss(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
+                   weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, workspace_bytes, stream);
 }
 
 // ---- per-level NCHW layout -----------------------------------------------------------

@@ -1,5 +1,5 @@
-// Device-side body of the fused anchor x GT matcher, shared by match.cu (rn_match) and loss.cu (the
-// single-launch training kernel rn_train_loss).  See match.cu for the design notes.
+// Device-side body of the fused anchor x GT matcher (rn_match, match.cu), split into reusable pieces: warp-level
+// culling set-up, GT tile staging, one warp x one staged tile, the final decision.  See match.cu for the design.
 #pragma once
 #include "rn_common.cuh"
 
@@ -145,30 +145,6 @@ __device__ __forceinline__ int match_block(float4 *s_box, float *s_area, const f
         __syncthreads();
         stage_gt_tile(s_box, s_area, gt + t0, tn, threadIdx.x, MATCH_BLOCK);
         __syncthreads();
-        match_tile(s_box, s_area, tn, t0, a, aa, w, prune_c, best, bi);
-    }
-    return match_decision(best, bi, G, fg_thr, bg_thr);
-}
-
-// The same for ONE WARP working alone (warp-specialised training kernel): 32 anchors (one per lane) against the
-// image's GT, staged in the warp's private shared tile.  `staged` tells that tile 0 of this image already sits in
-// shared memory (single-tile images are staged once per task, not once per anchor group).
-template <bool FAST>
-__device__ __forceinline__ int match_warp(float4 *s_box, float *s_area, const float4 a, const bool live,
-                                          const float4 *__restrict__ gt, const int G, const float fg_thr,
-                                          const float bg_thr, const float prune_c, const bool staged) {
-    const int lane = threadIdx.x & 31;
-    const float aa = box_area(a);
-    const WarpCull w = warp_cull_setup<FAST>(a, aa, live, prune_c);
-    float best = w.fast ? 0.0f : -INFINITY;
-    int bi = 0;
-    for (int t0 = 0; t0 < G; t0 += GT_TILE) {
-        const int tn = min(GT_TILE, G - t0);
-        if (!(staged && G <= GT_TILE)) {
-            __syncwarp();
-            stage_gt_tile(s_box, s_area, gt + t0, tn, lane, 32);
-            __syncwarp();
-        }
         match_tile(s_box, s_area, tn, t0, a, aa, w, prune_c, best, bi);
     }
     return match_decision(best, bi, G, fg_thr, bg_thr);

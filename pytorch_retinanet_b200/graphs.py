@@ -6,7 +6,7 @@ work, and they run the training half and the inference half back to back.  ``Hot
 the SAME C-ABI calls (``rn_train_loss`` = matcher + loss with gradients; ``rn_postprocess``) once, for fixed
 shapes and static buffers, into a CUDA graph:
 
-    capture stream:   rn_train_loss (matcher pipelined into loss fwd + gradients) --.
+    capture stream:   rn_train_loss: match -> loss (fwd + gradients) -> finalize ----.
     side stream (hi): score filter -> lazy NMS -> status --------------------------+--> join
 
 so that a step is one ``cudaGraphLaunch`` (+ one ``rn_pack_targets`` launch for the ragged ground

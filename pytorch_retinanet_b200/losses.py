@@ -36,7 +36,7 @@ def _shared_anchors(anchors: Sequence[Tensor]) -> Tuple[Tensor, int]:
 def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
                        packed: PackedTargets, alpha: float, gamma: float, beta: float, match_thr: float,
                        back_thr: float, batch_div: float, want_grad: bool):
-    """Launches rn_train_loss (matcher + loss + gradients + reduction, one kernel).  Returns (out_total [4], out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
+    """One C call (rn_train_loss): matcher, then loss + gradients + final reduction.  Returns (out_total [4], out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
     lib = _native.load()
     dev = cls_preds.device
     N, A, C = cls_preds.shape
@@ -58,7 +58,6 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
     ws_bytes = lib.rn_train_loss_workspace_bytes(N, A, C)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     with _native.on_device(dev):
-        # matcher + loss + gradients + final reduction: one launch (two when the fused kernel's preconditions fail)
         rc = lib.rn_train_loss(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
                                _native.ptr(anchors, torch.float32, "anchors"), anchor_stride,
                                _native.ptr(packed.boxes, torch.float32, "target boxes"),

@@ -106,12 +106,12 @@ def test_graph_train_only_and_detect_only(P):
 
 
 @pytest.mark.parametrize("case", ["cfg1", "cfg2", "crowd_tiles", "odd_A"])
-def test_single_launch_training_kernel_equals_two_kernel_sequence(P, case):
-    """rn_train_loss's fused kernel (matcher software-pipelined into the loss, in-kernel final reduction) must be
-    bit-identical to rn_match + rn_loss: losses, per-image values, gradients, codes, foreground counts; with and
-    without gradients; run repeatedly (any inter-CTA ordering bug would show up as a difference)."""
+def test_train_loss_call_equals_match_then_loss(P, case):
+    """rn_train_loss (one C call) must equal rn_match followed by rn_loss called separately — losses, per-image
+    values, gradients, codes — and be bit-reproducible run to run; covers G > GT_TILE (two shared-memory tiles),
+    A not a multiple of the CTA span, an image without GT, generic gamma."""
     from pytorch_retinanet_b200 import _native
-    from pytorch_retinanet_b200.box_utils import PackedTargets
+    from pytorch_retinanet_b200.box_utils import _REG_WEIGHTS_C, PackedTargets, match_batch
     from pytorch_retinanet_b200.losses import fused_loss_forward
     lib = _native.load()
     dev = torch.device("cuda")
@@ -138,32 +138,29 @@ def test_single_launch_training_kernel_equals_two_kernel_sequence(P, case):
     x, bb = b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
     tg = to_cuda_targets(b["targets"])
     packed = PackedTargets([t["boxes"] for t in tg], [t["labels"] for t in tg], dev)
+    N, A, C = x.shape
 
-    def run(want_grad):
-        out = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 2.0, 0.1, 0.5, 0.4, float(n_img), want_grad)
-        torch.cuda.synchronize()
-        return out
+    def separate(gamma, want_grad):
+        _, codes, fg = match_batch(anc, 0, packed, A, 0.5, 0.4, False, True)
+        total = torch.empty((4,), device=dev)
+        image = torch.empty((N, 3), device=dev)
+        gl = torch.empty_like(x) if want_grad else None
+        gb = torch.empty_like(bb) if want_grad else None
+        nb = lib.rn_loss_workspace_bytes(N, A, C)
+        ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+        rc = lib.rn_loss(x.data_ptr(), bb.data_ptr(), anc.data_ptr(), 0, packed.boxes.data_ptr(), packed.offsets.data_ptr(),
+                         codes.data_ptr(), fg.data_ptr(), N, A, C, 0.25, gamma, 0.1, _REG_WEIGHTS_C, float(n_img), image.data_ptr(),
+                         total.data_ptr(), None if gl is None else gl.data_ptr(), None if gb is None else gb.data_ptr(),
+                         ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "rn_loss")
+        return total, image, gl, gb, codes
 
-    old = lib.rn_train_loss_set_fused(0)
-    try:
-        ref = run(True)
-        ref_ng = run(False)
-    finally:
-        lib.rn_train_loss_set_fused(1)
-    assert old == 1
-    for rep in range(4):
-        got = run(True)
-        for g, r, name in zip(got, ref, ("total", "per_image", "grad_logits", "grad_bbox", "codes")):
-            assert torch.equal(g, r), (case, rep, name)
-    got_ng = run(False)
+    for gamma in (2.0, 1.5):
+        ref = separate(gamma, True)
+        for rep in range(3):
+            got = fused_loss_forward(x, bb, anc, 0, packed, 0.25, gamma, 0.1, 0.5, 0.4, float(n_img), True)
+            for g, r, name in zip(got, ref, ("total", "per_image", "grad_logits", "grad_bbox", "codes")):
+                assert torch.equal(g, r), (case, gamma, rep, name)
+    got_ng = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 2.0, 0.1, 0.5, 0.4, float(n_img), False)
+    ref_ng = separate(2.0, False)
     assert torch.equal(got_ng[0], ref_ng[0]) and torch.equal(got_ng[1], ref_ng[1]) and got_ng[2] is None
-    assert torch.equal(got_ng[0], ref[0])                         # forward values do not depend on the gradient variant
-    # generic gamma goes through the other template instance
-    a = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 1.5, 0.1, 0.5, 0.4, float(n_img), True)
-    lib.rn_train_loss_set_fused(0)
-    try:
-        c = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 1.5, 0.1, 0.5, 0.4, float(n_img), True)
-    finally:
-        lib.rn_train_loss_set_fused(1)
-    for g, r in zip(a, c):
-        assert torch.equal(g, r)
