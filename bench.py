@@ -169,7 +169,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(world):
@@ -435,7 +435,19 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": args.steps * 7,    # per graph step: pack_targets, match, loss, finalize, score filter, lazy NMS, status
             "roofline": roofline, "cpu_baseline": cpu, "n1_levels": n1,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
+
+
+def _emit(line: dict) -> None:
+    """The ONE JSON line, written to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Libraries (NCCL's version banner, torchrun) print to fd 1: keep the real stdout for the JSON line only and send
+# everything else to stderr.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
