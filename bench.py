@@ -256,6 +256,12 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ms_step = timed(step_graph, args.steps)
+    if args.only_step:
+        if rank == 0:
+            sampler.stop()
+            _emit({"metric": METRIC, "value": n_img * world / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world,
+                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "only_step": True})
+        return
     t0 = time.perf_counter()
     for _ in range(20):
         graph.step(targets)
@@ -458,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-levels", action="store_true", help="skip the row-N1 (per-level NCHW) timing leg")
+    ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the warm-up and the timed graph steps "
+                                                                "(what `value` measures) and print a reduced line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
