@@ -146,10 +146,10 @@ def run_reference(args, rank, world):
         return
     torch.set_num_threads(os.cpu_count() or 1)              # every host thread the box has
     cfg = S.CONFIGS[WORKLOAD_CFG]
-    sample = 2
+    sample = cfg.batch                                      # the whole 16-image batch of the workload: ~3 s per step
     batch = S.make_batch(cfg, 0, sample)
     for _ in range(args.warmup_ref):
-        cpu_reference_step(batch, 1)
+        cpu_reference_step(batch, 2)
     times = []
     for _ in range(args.steps_ref):
         t0 = time.perf_counter()
@@ -398,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
                                           "fwd+grad in one pass over the logits)",
                 "achieved": ach_fb, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach_fb / peak,
                 "traffic": 2.076e9 + 4.9e6, "traffic_note": "ncu --set full, loss_kernel 1.047 GB read + 1.029 GB write, "
-                "match_kernel 3.3 MB, finalize < 1 MB per launch (profiles/r01_notes.md)", "bytes_per_launch": bytes_fb, "ms_per_launch": kern["loss_fwd_bwd"],
+                "match_kernel 3.3 MB, finalize < 1 MB per launch (profiles/r01_ncu_graph_step_summary.txt)", "bytes_per_launch": bytes_fb, "ms_per_launch": kern["loss_fwd_bwd"],
                 "others": {"loss_fwd": {"GBps": bytes_f / (kern["loss_fwd"] * 1e-3) / 1e9, "ms": kern["loss_fwd"],
                                         "frac": bytes_f / (kern["loss_fwd"] * 1e-3) / 1e9 / peak},
                            "postprocess": {"GBps": bytes_p / (kern["postprocess"] * 1e-3) / 1e9, "ms": kern["postprocess"],
@@ -415,10 +415,10 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = 2
-        v, dt = time_cpu_reference(batch, sample, repeats=2)
+        sample = n_img                                      # the whole batch, 3 passes: ~10 s of CPU work
+        v, dt = time_cpu_reference(batch, sample, repeats=3)
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{sample} images of the same batch, best of 2 ({dt:.2f} s per pass), torch CPU eager port of the "
+               "sample": f"the same {sample}-image batch, best of 3 passes ({dt:.2f} s per pass), torch CPU eager port of the "
                          f"reference (oracle/torch_oracle.py), os.cpu_count={os.cpu_count()}"}
     if rank == 0:
         total = n_img * world
