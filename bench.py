@@ -7,8 +7,10 @@ match + focal/smooth-L1 loss + decode + NMS).
 
 One "step" = one pass of the whole hot path over one batch of synthetic COCO-shaped inputs
 (BASELINE.json configs[1]: 800x1333 -> A=201,600 anchors, 80 classes, batch 16 per GPU, <=100 GT/img):
-  anchors -> process_detections (sigmoid/threshold/decode/clip/NMS/top-100) -> RetinaNetLosses.forward (fused
-  matcher + focal + smooth-L1, gradients produced in the same pass) -> backward.
+  matcher + focal + smooth-L1 loss with gradients (rn_train_loss) and post-processing (sigmoid/threshold/decode/
+  clip/NMS/top-100, rn_postprocess) of the same batch.  `value` runs it as HotPathGraph.step (one CUDA graph, double
+  buffered); `api.*` holds the same step through the drop-in calls (RetinaNetLosses.forward + backward +
+  process_detections) and the unpipelined graph.
 N > 1: every rank owns its own 16 images (weak scaling; 8 GPUs = configs[2], batch 128) and the
 ranks exchange one 16-byte all-reduce per step.
 
@@ -240,28 +242,50 @@ def run_ours(args, rank, world, local_rank):
             ms = float(t.item())
         return ms / steps
 
-    # ---- device-resident throughput: the step as ONE CUDA graph (same C-ABI calls, two concurrent branches) ----
+    # ---- device-resident throughput: the step as ONE CUDA graph (same C-ABI calls, two concurrent branches).
+    # Two graphs on two input buffers alternate (double buffering): step i+1 is launched, then the losses, gradients
+    # and detections of step i are read — every step's results are consumed, one step late, so the host work of a
+    # step (GT packing, graph launch, count copy, slicing) overlaps with the GPU work of the other buffer. ----
     from pytorch_retinanet_b200.graphs import HotPathGraph
     gsum_max = sum(int(t["boxes"].shape[0]) for t in targets)
-    graph = HotPathGraph(C, d_cls, d_box, gen(images, fmaps)[0], batch["im_szs"], max_targets=max(4096, gsum_max),
-                         global_batch=(n_img * world) if world > 1 else None)
+    gb = (n_img * world) if world > 1 else None
+    anc0 = gen(images, fmaps)[0]
+    graph = HotPathGraph(C, d_cls, d_box, anc0, batch["im_szs"], max_targets=max(4096, gsum_max), global_batch=gb)
+    d_cls2, d_box2 = d_cls.clone(), d_box.clone()
+    graph2 = HotPathGraph(C, d_cls2, d_box2, anc0, batch["im_szs"], max_targets=max(4096, gsum_max), global_batch=gb)
+    gpend = []
 
-    def step_graph():
-        r = graph.step(targets)                             # pack GT + graph launch (+ 16-byte all-reduce at N > 1)
-        return r.losses, r.detections(), r.grads            # detections() waits for the counts: one sync per step
+    def step_graph_pipelined():
+        g = graph if (len(gpend) == 0 or gpend[-1][0] is graph2) else graph2
+        gpend.append((g, g.step(targets)))                  # pack GT + graph launch (+ 16-byte all-reduce at N > 1)
+        if len(gpend) > 1:
+            r = gpend.pop(0)[1]
+            return r.losses, r.detections(), r.grads        # detections() waits for that step's counts
 
-    for _ in range(args.warmup):
-        step_graph()
+    for _ in range(max(args.warmup, 4)):
+        step_graph_pipelined()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step = timed(step_graph, args.steps)
+    ms_step = timed(step_graph_pipelined, args.steps)
+    while gpend:
+        gpend.pop(0)[1].detections()
     if args.only_step:
         if rank == 0:
             sampler.stop()
             _emit({"metric": METRIC, "value": n_img * world / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world,
                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "only_step": True})
         return
+    del graph2, d_cls2, d_box2
+
+    # ---- one graph, results read in the same step (one host sync per step) ----
+    def step_graph():
+        r = graph.step(targets)
+        return r.losses, r.detections(), r.grads
+
+    for _ in range(3):
+        step_graph()
+    ms_graph_sync = timed(step_graph, args.steps)
     t0 = time.perf_counter()
     for _ in range(20):
         graph.step(targets)
@@ -272,6 +296,20 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(d_cls, d_box)
     ms_dropin = timed(lambda: step(d_cls, d_box), args.steps)
+
+    # ---- drop-in calls, inference half enqueued first and collected at the END OF THE SAME STEP (no host sync between
+    # the halves; nothing is carried over to the next step) ----
+    def step_overlapped():
+        anchors = gen(images, fmaps)
+        handle = P.process_detections_async(stub, {"cls_preds": d_cls, "bbox_preds": d_box}, anchors, batch["im_szs"])
+        x, b = d_cls.detach().requires_grad_(True), d_box.detach().requires_grad_(True)
+        out = losses(targets, {"cls_preds": x, "bbox_preds": b}, anchors)
+        (out["classification_loss"] + out["regression_loss"]).backward()
+        return out, handle.detections(), x.grad
+
+    for _ in range(3):
+        step_overlapped()
+    ms_overlapped = timed(step_overlapped, args.steps)
 
     # ---- same work, software-pipelined: detections of step i are collected while step i+1 is enqueued ----
     pending = []
@@ -409,8 +447,8 @@ def run_ours(args, rank, world, local_rank):
                                                  "note": "loss_kernel<4,grad> + finalize, codes precomputed by rn_match"},
                            "graph_step": {"GBps": (bytes_fb + bytes_p) / (ms_step * 1e-3) / 1e9, "ms": ms_step,
                                           "frac": (bytes_fb + bytes_p) / (ms_step * 1e-3) / 1e9 / peak,
-                                          "note": "B_fb + B_p over the whole timed step (both branches of the graph, host "
-                                                  "sync and target packing included); the logits are counted once per branch"}}}
+                                          "note": "B_fb + B_p over the whole timed step (both branches of the graph, target "
+                                                  "packing and result read-back included); the logits are counted once per branch"}}}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----
     cpu = None
@@ -426,15 +464,23 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": total / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks,
+            "config": dict(workload_config(world), pipeline="2 input buffers x 2 CUDA graphs alternate; results of step i are "
+                                                            "read after step i+1 is launched (api.graph_sync = no pipelining)"),
+            "clocks": clocks,
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps},
-            "api": {"value_through": "HotPathGraph.step: one CUDA graph of rn_train_loss (match+loss fwd+grad) || rn_postprocess, "
-                                     "detections read every step",
+            "api": {"value_through": "HotPathGraph.step: one CUDA graph of rn_train_loss (match+loss fwd+grad) || rn_postprocess; two "
+                                     "graphs / input buffers alternate, every step's losses, gradients and detections are read "
+                                     "one step late",
+                    "graph_sync": {"value": total / (ms_graph_sync * 1e-3), "unit": "images/s", "ms_per_step": ms_graph_sync,
+                                   "note": "one graph, results read in the same step (one host sync per step)"},
                     "graph_host_enqueue_us": host_us_graph,
                     "dropin_sync": {"value": total / (ms_dropin * 1e-3), "unit": "images/s", "ms_per_step": ms_dropin,
                                     "note": "RetinaNetLosses.forward + backward + process_detections (reference signatures, "
                                             "autograd), one host sync per step"},
+                    "dropin_overlapped": {"value": total / (ms_overlapped * 1e-3), "unit": "images/s", "ms_per_step": ms_overlapped,
+                                          "note": "drop-in calls, process_detections_async enqueued before the training half and "
+                                                  "collected at the end of the same step"},
                     "dropin_pipelined": {"value": total / (ms_pipe * 1e-3), "unit": "images/s", "ms_per_step": ms_pipe,
                                          "note": "drop-in calls with process_detections_async: results of step i read while "
                                                  "step i+1 is enqueued"}},

@@ -159,10 +159,21 @@ class PendingDetections:
         return out
 
     def detections(self) -> List[Dict[str, Tensor]]:
-        ob, os_, ol, counts = self.result()
-        # one unbind per tensor + one slice per field (half the view ops of ob[i, :k])
-        return [{"boxes": b[:k], "scores": s[:k], "labels": l[:k]}
-                for b, s, l, k in zip(ob.unbind(0), os_.unbind(0), ol.unbind(0), counts)]
+        return slice_detections(*self.result())
+
+
+def slice_detections(ob: Tensor, os_: Tensor, ol: Tensor, counts: Sequence[int]) -> List[Dict[str, Tensor]]:
+    """Padded slabs [N,M,*] + per-image counts -> the reference's ``List[Dict]`` (models.py:236-242) with THREE view
+    calls for the whole batch: every image contributes the sizes (k, M-k) to one ``split_with_sizes`` per field."""
+    N, M = ob.shape[0], ob.shape[1]
+    sizes = []
+    for k in counts:
+        sizes.append(k)
+        sizes.append(M - k)
+    b = ob.view(N * M, -1).split_with_sizes(sizes)
+    s = os_.view(N * M).split_with_sizes(sizes)
+    l = ol.view(N * M).split_with_sizes(sizes)
+    return [{"boxes": b[2 * i], "scores": s[2 * i], "labels": l[2 * i]} for i in range(N)]
 
 
 def postprocess_batch_async(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,

@@ -31,7 +31,7 @@ from .box_utils import _REG_WEIGHTS_C
 from .config import (FOCAL_LOSS_ALPHA, FOCAL_LOSS_GAMMA, IOU_THRESHOLDS_BACKGROUND, IOU_THRESHOLDS_FOREGROUND,
                      MAX_DETECTIONS_PER_IMAGE, NMS_THRES, SCORE_THRES, SMOOTH_L1_LOSS_BETA)
 from .detections import (_FORMATS, _image_sizes_tensor, _resize_ratio_tensor, default_candidate_capacity,
-                         postprocess_batch)
+                         postprocess_batch, slice_detections)
 
 _vp = ctypes.c_void_p
 
@@ -84,16 +84,7 @@ class GraphStepResult:
 
     def detections(self) -> List[Dict[str, Tensor]]:
         """The reference's ``List[Dict]`` (models.py:236-242): three ``split_with_sizes`` calls for the batch."""
-        ob, os_, ol, counts = self.result()
-        N, M = ob.shape[0], ob.shape[1]
-        sizes = []
-        for k in counts:
-            sizes.append(k)
-            sizes.append(M - k)
-        b = ob.view(N * M, -1).split_with_sizes(sizes)
-        s = os_.view(N * M).split_with_sizes(sizes)
-        l = ol.view(N * M).split_with_sizes(sizes)
-        return [{"boxes": b[2 * i], "scores": s[2 * i], "labels": l[2 * i]} for i in range(N)]
+        return slice_detections(*self.result())
 
 
 class HotPathGraph:
