@@ -52,6 +52,14 @@ def _worker(rank, world, port, ret):
     want = O.postprocess(x.detach(), bb.detach(), [anc] * (hi - lo), b["im_szs"][lo:hi])
     for d, w in zip(dets, want):
         ok &= torch.equal(d["labels"], w["labels"]) and torch.equal(d["boxes"], w["boxes"])
+    # the graph form of the sharded step: bit-identical to the sharded drop-in calls on every rank
+    from pytorch_retinanet_b200.graphs import HotPathGraph
+    res = HotPathGraph(cfg.num_classes, x.detach(), bb.detach(), anc, b["im_szs"][lo:hi], global_batch=n_total).step(tg)
+    ok &= torch.equal(res.losses["classification_loss"], out["classification_loss"].detach())
+    ok &= torch.equal(res.losses["regression_loss"], out["regression_loss"].detach())
+    ok &= torch.equal(res.grads[0], x.grad) and torch.equal(res.grads[1], bb.grad)
+    for d, w in zip(res.detections(), dets):
+        ok &= torch.equal(d["labels"], w["labels"]) and torch.equal(d["boxes"], w["boxes"]) and torch.equal(d["scores"], w["scores"])
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
