@@ -409,7 +409,7 @@ namespace {
 #define LV_PU 1      // 128-position chunks of one plane in flight per lane
 #endif
 #ifndef LV_CU
-#define LV_CU 4      // channel planes in flight per warp
+#define LV_CU 2      // channel planes in flight per warp (2 planes x 8 CTAs/SM measured best: 0.43 vs 0.56 ms with 4 x 4)
 #endif
 constexpr int LV_TILE = 128 * LV_PU;
 constexpr int LV_BLOCK = 256;
@@ -450,7 +450,6 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
     const long long anchor0 = D.lvl_off + (long long)p0 * D.na + a;   // anchor of position p: anchor0 + p*na
     const int *codes = P.codes + (long long)n * P.A + anchor0;
     // per-lane constants of the 4 positions this lane owns in every class plane
-    int posc[LV_PU][4];        // positive class of the position's anchor, or -1
     bool ign[LV_PU][4];        // ignore anchor (or out of range): logit replaced by -100 -> p = sp = grad = 0 exactly
     bool ok[LV_PU];            // lane's vector lies inside the tile (VEC == 4)
 #pragma unroll
@@ -461,7 +460,6 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
             const int p = VEC == 4 ? pu * 128 + lane * 4 + k : pu * 128 + k * 32 + lane;
             const int cd = p < np ? __ldg(codes + (long long)p * D.na) : -2;
             ign[pu][k] = cd == -2;
-            posc[pu][k] = cd >= 0 ? (cd >> 20) : -1;
         }
     }
     const int F = P.fg_count[n];
@@ -511,23 +509,19 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
                 const float vmax = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
                 const bool small = __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
                 float local = 0.0f;
+                float pk[4], spk[4];
+                if (small) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float pk, spk;
-                    if (small) sigmoid_softplus_small(x[k], pk, spk);
-                    else sigmoid_softplus<false>(x[k] + 1.0f, pk, spk);
-                    const float w = pow_gamma<GAMMA2>(pk, P.gamma);
-                    local = fmaf(w, spk, local);
-                    g[k] = w * pk * neg_gscale;
-                    if (posc[pu][k] == c) {                            // this element is its anchor's positive (rare)
-                        const float xx = x[k] + 1.0f;
-                        float p, sp;
-                        sigmoid_softplus<false>(xx, p, sp);
-                        const float wn = pow_gamma<GAMMA2>(p, P.gamma);
-                        const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
-                        acc_pos += wp * (sp - xx) - P.alpha * wn * sp;
-                        g[k] = wp * (p - 1.0f) * inv;
-                    }
+                    for (int k = 0; k < 4; ++k) sigmoid_softplus_small(x[k], pk[k], spk[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sigmoid_softplus<false>(x[k] + 1.0f, pk[k], spk[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {      // every element as a negative; the (rare) positives are patched after the walk
+                    const float w = pow_gamma<GAMMA2>(pk[k], P.gamma);
+                    local = fmaf(w, spk[k], local);
+                    g[k] = w * pk[k] * neg_gscale;
                 }
                 acc_neg += local;
                 if (WANT_GRAD) {
@@ -546,13 +540,26 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
         }
     }
 
-    // ---- regression: the tile's positions for this anchor index; box channel (a*4 + k) plane, stride HW ----
+    // ---- per position: regression (box channel (a*4 + k) plane, stride HW) and, for a foreground anchor, the patch
+    // of its ONE positive class element — its logit is re-read (L2), the negative term the walk added is taken back
+    // and the gradient element the walk wrote is overwritten (hence the barrier) ----
+    if (WANT_GRAD) __syncthreads();
     float reg = 0.0f;
     for (int p = t; p < np; p += LV_BLOCK) {
         const int cd = __ldg(codes + (long long)p * D.na);
         const long long b0 = ((long long)(n * D.na + a) * 4) * D.HW + p0 + p;
         float gr[4] = {0.f, 0.f, 0.f, 0.f};
         if (cd >= 0) {
+            {
+                const long long e = (((long long)n * D.na + a) * P.C + (cd >> 20)) * D.HW + p0 + p;
+                const float xx = __ldg(D.cls + e) + 1.0f;
+                float pp, sp;
+                sigmoid_softplus<false>(xx, pp, sp);
+                const float wn = pow_gamma<GAMMA2>(pp, P.gamma);
+                const float wp = pow_gamma<GAMMA2>(1.0f - pp, P.gamma) * (1.0f - P.alpha);
+                acc_pos += wp * (sp - xx) - P.alpha * wn * sp;
+                if (WANT_GRAD) D.gcls[e] = wp * (pp - 1.0f) * inv;
+            }
             const long long anchor = anchor0 + (long long)p * D.na;
             const float4 gtb = P.gt[P.gt_off[n] + (cd & 0xFFFFF)];
             const float4 an = P.anchors[(long long)n * P.anchor_stride + anchor];
@@ -591,8 +598,11 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
 
 // All pyramid levels in ONE launch: blockIdx.x enumerates the tiles of every level (the small P5-P7 levels
 // would otherwise be latency-bound launches of their own), blockIdx.y = image, blockIdx.z = cell anchor.
+#ifndef LV_MINB
+#define LV_MINB 8    // resident CTAs per SM asked of ptxas: 32 registers/thread, full occupancy (8 bytes of spills)
+#endif
 template <bool WANT_GRAD, bool GAMMA2>
-__global__ void __launch_bounds__(LV_BLOCK) loss_levels_kernel(const __grid_constant__ LvlLossParams P) {
+__global__ void __launch_bounds__(LV_BLOCK, LV_MINB) loss_levels_kernel(const __grid_constant__ LvlLossParams P) {
     int l = 0;
 #pragma unroll
     for (int k = 1; k < RN_MAX_LEVELS; ++k)

@@ -91,12 +91,36 @@ PPWorkspace carve(void *base, int N, int C, int64_t cap) {
     return w;
 }
 
+// Where the box activations live: the reference head's [N,A,4] tensor, or (row N1) the raw per-level conv outputs
+// [N, na*4, H, W] — only the few thousand candidates that reach NMS are ever read, so the level layout is indexed
+// in place (4 strided loads per candidate) instead of being re-laid out.
+struct BoxSource {
+    const float4 *nac;                    // [N,A,4] or null
+    const float *lvl[RN_MAX_LEVELS];      // level l: [N, na_l*4, HW_l]
+    long long off[RN_MAX_LEVELS + 1];     // anchor offsets of the levels
+    int HW[RN_MAX_LEVELS], na[RN_MAX_LEVELS];
+    int nlev;
+};
+
+__device__ __forceinline__ float4 load_activation(const BoxSource &B, const int n, const long long A, const long long anchor) {
+    if (B.nac) return __ldg(B.nac + (long long)n * A + anchor);
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < RN_MAX_LEVELS; ++k)
+        if (k < B.nlev && anchor >= B.off[k]) l = k;
+    const int na = B.na[l], HW = B.HW[l];
+    const int r = (int)(anchor - B.off[l]);
+    const int pos = r / na, a = r - pos * na;
+    const float *b0 = B.lvl[l] + ((long long)(n * na + a) * 4) * HW + pos;
+    return make_float4(__ldg(b0), __ldg(b0 + HW), __ldg(b0 + 2LL * HW), __ldg(b0 + 3LL * HW));
+}
+
 // decode + clip of one anchor: activ_2_bbox (box_utils.py:37-48) then clip_boxes_to_image
 // (tv:ops/boxes.py:149-182: x in [0,w], y in [0,h]).
-__device__ __noinline__ float4 decode_clip(const float4 *__restrict__ bbox, const float4 *__restrict__ anchors,
-                                              long long row, long long anchor_row, float4 wts, float imw,
-                                              float imh) {
-    float4 b = rn::decode_box(__ldg(bbox + row), __ldg(anchors + anchor_row), wts);
+__device__ __noinline__ float4 decode_clip(const BoxSource &box, const int n, const long long A, const long long anchor,
+                                           const float4 *__restrict__ anchors, long long anchor_row, float4 wts, float imw,
+                                           float imh) {
+    float4 b = rn::decode_box(load_activation(box, n, A, anchor), __ldg(anchors + anchor_row), wts);
     b.x = rn::clampf(b.x, 0.0f, imw);
     b.z = rn::clampf(b.z, 0.0f, imw);
     b.y = rn::clampf(b.y, 0.0f, imh);
@@ -316,7 +340,7 @@ __device__ __forceinline__ float nms_area(const float4 b) {
 }
 
 struct NmsParams {
-    const float4 *bbox;      // DECODE mode: [N,A,4] activations
+    BoxSource box;           // DECODE mode: box activations
     const float4 *anchors;
     const int *im_hw;
     const float4 *boxes;     // RAW mode: [K,4] boxes already sorted per segment
@@ -334,7 +358,7 @@ struct NmsParams {
 };
 
 template <bool RAW>
-__global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
+__global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const __grid_constant__ NmsParams P) {
     __shared__ u64 s_keys[RAW ? 1 : SORT_SMEM];
     __shared__ float4 s_box[NMS_CHUNK];
     __shared__ float s_area[NMS_CHUNK];
@@ -350,12 +374,12 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
         return;
     }
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    long long img_row = 0, anc_row = 0;
+    long long anc_row = 0;
+    int n = 0;
     float imw = 0.f, imh = 0.f;
     u64 *keys = nullptr;
     if (!RAW) {
-        const int n = seg / P.C;
-        img_row = (long long)n * P.A;
+        n = seg / P.C;
         anc_row = (long long)n * P.anchor_stride;
         imh = (float)P.im_hw[2 * n];
         imw = (float)P.im_hw[2 * n + 1];
@@ -383,7 +407,7 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_kernel(const NmsParams P) {
             } else {
                 key = keys[c0 + t];
                 const long long anchor = (long long)(u32)key;
-                b = decode_clip(P.bbox, P.anchors, img_row + anchor, anc_row + anchor, P.wts, imw, imh);
+                b = decode_clip(P.box, n, P.A, anchor, P.anchors, anc_row + anchor, P.wts, imw, imh);
             }
         }
         const float area = nms_area(b);
@@ -501,7 +525,7 @@ __device__ __forceinline__ float4 finish_box(float4 b, const float *__restrict__
 
 // ------------------------------------------------------------------------------------------- LAZY
 struct LazyParams {
-    const float4 *bbox;
+    BoxSource box;
     const float4 *anchors;
     const int *im_hw;
     long long A;
@@ -580,7 +604,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     const u64 *cand = cached ? s_cand : g_cand;
     LZ_TICK(0);
     const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
-    const long long img_row = (long long)n * P.A, anc_row = (long long)n * P.anchor_stride;
+    const long long anc_row = (long long)n * P.anchor_stride;
     const u32 A32 = (u32)P.A;
 
     int kept = 0, processed = 0;
@@ -689,7 +713,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
                     const u32 lo = (u32)S.sel[c0 + t];
                     cls = (int)(lo / A32);
                     const long long anchor = (long long)(lo - (u32)cls * A32);
-                    b = decode_clip(P.bbox, P.anchors, img_row + anchor, anc_row + anchor, P.wts, imw, imh);
+                    b = decode_clip(P.box, n, P.A, anchor, P.anchors, anc_row + anchor, P.wts, imw, imh);
                     // remove_small_boxes(min_size=1e-2), models.py:203
                     alive = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);
                     if (P.topk > 0) {
@@ -1081,7 +1105,7 @@ extern "C" size_t rn_postprocess_workspace_bytes(int N, int64_t A, int C, int64_
 }
 
 // Everything after the streaming filter (shared by the [N,A,C] and the per-level entry points).
-static int pp_tail(const PPWorkspace &w, const FilterParams &F, const float *bbox, const float *anchors,
+static int pp_tail(const PPWorkspace &w, const FilterParams &F, const BoxSource &box, const float *anchors,
                    int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A, int C, double nms_thr,
                    int max_det, int pre_nms_topk, const int64_t *level_off_host, int num_levels, bool lazy,
                    int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
@@ -1092,7 +1116,7 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const float *bbo
 
     if (lazy) {
         LazyParams Z;
-        Z.bbox = (const float4 *)bbox; Z.anchors = (const float4 *)anchors; Z.im_hw = im_hw; Z.A = A;
+        Z.box = box; Z.anchors = (const float4 *)anchors; Z.im_hw = im_hw; Z.A = A;
         Z.anchor_stride = anchor_image_stride; Z.C = C; Z.N = N; Z.thr = thr_f; Z.wts = F.wts; Z.max_det = max_det;
         Z.cand_key = w.pool_key; Z.img_count = w.img_count; Z.cap_n = F.cap_n; Z.out_boxes = out_boxes;
         Z.out_scores = out_scores; Z.out_labels = (long long *)out_labels; Z.out_count = out_count; Z.status = out_status;
@@ -1118,7 +1142,7 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const float *bbo
     RN_CHECK_LAUNCH("rn_postprocess/scatter");
 
     NmsParams M;
-    M.bbox = (const float4 *)bbox; M.anchors = (const float4 *)anchors; M.im_hw = im_hw; M.boxes = nullptr;
+    M.box = box; M.anchors = (const float4 *)anchors; M.im_hw = im_hw; M.boxes = nullptr;
     M.keep_flags = nullptr; M.A = A; M.anchor_stride = anchor_image_stride; M.C = C; M.thr = thr_f; M.wts = F.wts; M.seg_off = w.seg_off;
     M.sorted_key = w.sorted_key; M.kept_key = w.kept_key; M.kept_box = w.kept_box; M.kept_count = w.kept_count;
     nms_kernel<false><<<S, NMS_CHUNK, 0, s>>>(M);
@@ -1197,7 +1221,10 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
     }
     RN_CHECK_LAUNCH("rn_postprocess/score_filter");
 
-    return pp_tail(w, F, bbox, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
+    BoxSource box;
+    memset(&box, 0, sizeof(box));
+    box.nac = (const float4 *)bbox;
+    return pp_tail(w, F, box, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
                    level_off_host, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count,
                    out_status, out_ratio_hw, out_format, s);
 }
@@ -1205,8 +1232,7 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
 // ---- per-level NCHW inputs ------------------------------------------------------------
 // The filter streams each level's conv output [N, na*C, H, W] as the flat array it is (a 128-bit load
 // may straddle two channel planes: only the rare survivors decompose their flat index into
-// (anchor, class)); the box activations (1/20 of the bytes) are gathered once into [N,A,4] for the
-// NMS kernels' random access.
+// (anchor, class)); the box activations are read in place by the NMS kernels (BoxSource), candidates only.
 struct LevelFilterParams {
     const float *cls;        // one level, [N, na*C*HW] flat
     long long len;           // na*C*HW (< 2^31)
@@ -1253,23 +1279,19 @@ __device__ __noinline__ void emit_candidates_level(const FilterParams &P, const 
 
 constexpr int LVF_SPAN = 8192;     // floats per warp task
 
+struct AllLevelsFilterParams {
+    LevelFilterParams lv[RN_MAX_LEVELS];
+    int task_base[RN_MAX_LEVELS + 1];   // first warp task of each level (prefix sums), [num_levels] = total
+    int vec4[RN_MAX_LEVELS];
+    int num_levels;
+};
+
 template <int VEC, bool LAZY>
-__global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_levels_kernel(const __grid_constant__ FilterParams P,
-                                                                          const __grid_constant__ LevelFilterParams Q) {
-    __shared__ u64 s_key[PP_BLOCK / 32][PP_WSTAGE];
-    __shared__ u32 s_seg[LAZY ? 1 : PP_BLOCK / 32][LAZY ? 1 : PP_WSTAGE];
-    __shared__ int s_n[PP_BLOCK / 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.y;
-    const long long e_begin = ((long long)blockIdx.x * (PP_BLOCK / 32) + warp) * LVF_SPAN;
-    if (e_begin >= Q.len) return;
+__device__ __forceinline__ void filter_level_span(const FilterParams &P, const LevelFilterParams &Q, const int n,
+                                                  const long long e_begin, u64 *st_key, u32 *st_seg, int *st_n) {
+    const int lane = threadIdx.x & 31;
     const int span = (int)min((long long)LVF_SPAN, Q.len - e_begin);
     const float *src = Q.cls + (long long)n * Q.len + e_begin;
-    u64 *st_key = s_key[warp];
-    u32 *st_seg = LAZY ? nullptr : s_seg[warp];
-    int *st_n = &s_n[warp];
-    if (lane == 0) *st_n = 0;
-    __syncwarp();
     const int nvec = span / VEC;
     for (int base = 0; base < nvec; base += 32 * PP_U) {
         float4 v[PP_U];
@@ -1290,6 +1312,33 @@ __global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_levels_kernel(const 
                                             st_seg, st_n);
         }
     }
+}
+
+// ALL pyramid levels in one launch: blockIdx.x enumerates the warp tasks (LVF_SPAN floats each) of every level, so the
+// small P5-P7 levels — 20 us launches of their own, latency-bound on 16..200 CTAs — stream in the shadow of P3.
+template <bool LAZY>
+__global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_levels_kernel(const __grid_constant__ FilterParams P,
+                                                                          const __grid_constant__ AllLevelsFilterParams L) {
+    __shared__ u64 s_key[PP_BLOCK / 32][PP_WSTAGE];
+    __shared__ u32 s_seg[LAZY ? 1 : PP_BLOCK / 32][LAZY ? 1 : PP_WSTAGE];
+    __shared__ int s_n[PP_BLOCK / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.y;
+    const int task = blockIdx.x * (PP_BLOCK / 32) + warp;
+    if (task >= L.task_base[L.num_levels]) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < RN_MAX_LEVELS; ++k)
+        if (k < L.num_levels && task >= L.task_base[k]) l = k;
+    const LevelFilterParams &Q = L.lv[l];
+    const long long e_begin = (long long)(task - L.task_base[l]) * LVF_SPAN;
+    u64 *st_key = s_key[warp];
+    u32 *st_seg = LAZY ? nullptr : s_seg[warp];
+    int *st_n = &s_n[warp];
+    if (lane == 0) *st_n = 0;
+    __syncwarp();
+    if (L.vec4[l]) filter_level_span<4, LAZY>(P, Q, n, e_begin, st_key, st_seg, st_n);
+    else filter_level_span<1, LAZY>(P, Q, n, e_begin, st_key, st_seg, st_n);
     __syncwarp();
     const int staged = min(*st_n, PP_WSTAGE);
     if (staged == 0) return;
@@ -1308,21 +1357,8 @@ __global__ void __launch_bounds__(PP_BLOCK, 4) score_filter_levels_kernel(const 
     }
 }
 
-// box level [N, na*4, H, W] -> rows lvl_off.. of [N, A, 4]
-__global__ void __launch_bounds__(256) gather_bbox_level_kernel(const float *__restrict__ box, int HW, int na, long long A,
-                                                                long long lvl_off, float4 *__restrict__ out) {
-    const int n = blockIdx.y;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;     // idx = a*HW + pos (pos fastest: coalesced reads)
-    if (idx >= (long long)na * HW) return;
-    const int a = (int)(idx / HW), pos = (int)(idx - (long long)a * HW);
-    const float *b0 = box + ((long long)(n * na + a) * 4) * HW + pos;
-    out[(long long)n * A + lvl_off + (long long)pos * na + a] =
-        make_float4(__ldg(b0), __ldg(b0 + HW), __ldg(b0 + 2LL * HW), __ldg(b0 + 3LL * HW));
-}
-
 extern "C" size_t rn_postprocess_levels_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det) {
-    const size_t base = rn_postprocess_workspace_bytes(N, A, C, cand_capacity, max_det);
-    return base ? align_up(base, 256) + (size_t)N * (size_t)A * 16 : 0;
+    return rn_postprocess_workspace_bytes(N, A, C, cand_capacity, max_det);   // the box levels are indexed in place
 }
 
 extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const float *const *bbox_levels_host,
@@ -1357,9 +1393,7 @@ extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const 
     RN_CHECK_ARG(level_off[num_levels] == A, RN_E_BADARG, "rn_postprocess_levels: levels hold %lld anchors, A = %lld",
                  (long long)level_off[num_levels], (long long)A);
     PPWorkspace w = carve(workspace, N, C, cand_capacity);
-    const size_t box_off = align_up(w.total_bytes, 256);
-    RN_CHECK_ARG(workspace_bytes >= box_off + (size_t)N * (size_t)A * 16, RN_E_WORKSPACE, "rn_postprocess_levels: workspace too small");
-    float4 *bbox_nac = (float4 *)((char *)workspace + box_off);
+    RN_CHECK_ARG(workspace_bytes >= w.total_bytes, RN_E_WORKSPACE, "rn_postprocess_levels: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(workspace, 0, w.zero_bytes, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(out_status, 0, 4 * sizeof(int32_t), s);
@@ -1374,36 +1408,39 @@ extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const 
     }
     const bool lazy = algo == RN_PP_LAZY;
     FilterParams F;
-    F.logits = nullptr; F.bbox = bbox_nac; F.anchors = (const float4 *)anchors; F.im_hw = im_hw;
+    F.logits = nullptr; F.bbox = nullptr; F.anchors = (const float4 *)anchors; F.im_hw = im_hw;
     F.A = A; F.anchor_stride = anchor_image_stride; F.C = C; F.magic = 0; F.x_lo = x_lo; F.thr = thr; F.cap = (u32)cand_capacity;
     F.cap_n = (u32)max((int64_t)1, cand_capacity / N); F.w = w;
     F.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
+    AllLevelsFilterParams L;
+    BoxSource box;
+    memset(&L, 0, sizeof(L));
+    memset(&box, 0, sizeof(box));
+    L.num_levels = box.nlev = num_levels;
+    long long tasks = 0;
     for (int l = 0; l < num_levels; ++l) {
         const int32_t *d = level_desc_host + 3 * l;
         const int HW = d[0] * d[1], na = d[2];
-        if (HW == 0) continue;
-        RN_CHECK_ARG(cls_levels_host[l] && bbox_levels_host[l], RN_E_BADARG, "rn_postprocess_levels: null level %d", l);
-        dim3 gg((unsigned)(((long long)na * HW + 255) / 256), (unsigned)N);
-        gather_bbox_level_kernel<<<gg, 256, 0, s>>>(bbox_levels_host[l], HW, na, A, level_off[l], bbox_nac);
-        RN_CHECK_LAUNCH("rn_postprocess_levels/gather_bbox");
-        LevelFilterParams Q;
+        RN_CHECK_ARG(HW == 0 || (cls_levels_host[l] && bbox_levels_host[l]), RN_E_BADARG, "rn_postprocess_levels: null level %d", l);
+        LevelFilterParams &Q = L.lv[l];
         Q.cls = cls_levels_host[l]; Q.len = (long long)na * C * HW; Q.HW = HW; Q.na = na; Q.C = C; Q.lvl_off = level_off[l];
         RN_CHECK_ARG(Q.len < (1LL << 31), RN_E_TOOLARGE, "rn_postprocess_levels: level %d has more than 2^31 elements per image", l);
-        Q.magicHW = HW == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)HW - 1) / (unsigned)HW);
+        Q.magicHW = HW <= 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)HW - 1) / (unsigned)HW);
         Q.magicC = C == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)C - 1) / (unsigned)C);
-        const bool vec4 = (Q.len % 4 == 0) && (((uintptr_t)Q.cls & 15) == 0);
-        const long long tasks = (Q.len + LVF_SPAN - 1) / LVF_SPAN;
+        L.vec4[l] = (Q.len % 4 == 0) && (((uintptr_t)Q.cls & 15) == 0);
+        L.task_base[l] = (int)tasks;
+        tasks += (Q.len + LVF_SPAN - 1) / LVF_SPAN;
+        box.lvl[l] = bbox_levels_host[l]; box.off[l] = level_off[l]; box.HW[l] = HW; box.na[l] = na;
+        RN_CHECK_ARG(tasks < 0x7fffffffLL, RN_E_TOOLARGE, "rn_postprocess_levels: too many tasks");
+    }
+    for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) { L.task_base[l] = (int)tasks; box.off[l] = A; }
+    if (tasks > 0) {
         dim3 grid((unsigned)((tasks + PP_BLOCK / 32 - 1) / (PP_BLOCK / 32)), (unsigned)N);
-        if (lazy) {
-            if (vec4) score_filter_levels_kernel<4, true><<<grid, PP_BLOCK, 0, s>>>(F, Q);
-            else score_filter_levels_kernel<1, true><<<grid, PP_BLOCK, 0, s>>>(F, Q);
-        } else {
-            if (vec4) score_filter_levels_kernel<4, false><<<grid, PP_BLOCK, 0, s>>>(F, Q);
-            else score_filter_levels_kernel<1, false><<<grid, PP_BLOCK, 0, s>>>(F, Q);
-        }
+        if (lazy) score_filter_levels_kernel<true><<<grid, PP_BLOCK, 0, s>>>(F, L);
+        else score_filter_levels_kernel<false><<<grid, PP_BLOCK, 0, s>>>(F, L);
         RN_CHECK_LAUNCH("rn_postprocess_levels/score_filter");
     }
-    return pp_tail(w, F, (const float *)bbox_nac, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
+    return pp_tail(w, F, box, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
                    level_off, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count, out_status,
                    out_ratio_hw, out_format, s);
 }
@@ -1418,7 +1455,7 @@ extern "C" int rn_nms_segments(const float *boxes, const int32_t *seg_off, int n
     float thr_f = (float)nms_thr;
     if ((double)thr_f > nms_thr) thr_f = nextafterf(thr_f, -INFINITY);
     NmsParams M;
-    M.bbox = nullptr; M.anchors = nullptr; M.im_hw = nullptr; M.boxes = (const float4 *)boxes;
+    memset(&M.box, 0, sizeof(M.box)); M.anchors = nullptr; M.im_hw = nullptr; M.boxes = (const float4 *)boxes;
     M.keep_flags = keep_flags; M.A = 0; M.anchor_stride = 0; M.C = 1; M.thr = thr_f; M.wts = make_float4(1.f, 1.f, 1.f, 1.f);
     M.seg_off = seg_off; M.sorted_key = nullptr; M.kept_key = nullptr; M.kept_box = (float4 *)workspace;
     M.kept_count = nullptr;
