@@ -422,7 +422,18 @@ def run_ours(args, rank, world, local_rank):
             for _ in range(3):
                 fn()
             lv[name] = timed(fn, max(5, args.steps))
-        n1 = {"ms": lv, "note": "loss / post-processing on raw [N, 9*C, H_l, W_l] conv outputs (no permute+cat); "
+        glv = HotPathGraph(C, cls_lv, box_lv, anc, batch["im_szs"], max_targets=max(4096, gsum_max))
+
+        def step_graph_levels():
+            r = glv.step(targets)
+            return r.losses, r.detections(), r.grads
+
+        for _ in range(3):
+            step_graph_levels()
+        lv["graph_step_sync"] = timed(step_graph_levels, max(5, args.steps))
+        del glv
+        n1 = {"ms": lv, "note": "loss / post-processing on raw [N, 9*C, H_l, W_l] conv outputs (no permute+cat); graph_step_sync = "
+                                "HotPathGraph on the level lists, results read in the same step; "
                                 "reference_head_relayout_cls_fwd = torch time of the re-layout pass this removes (forward only; "
                                 "its backward costs the same again)"}
         del cls_lv, box_lv

@@ -32,7 +32,13 @@ namespace {
 
 constexpr int LOSS_BLOCK = 256;
 constexpr int LOSS_SPAN = 256;   // anchors per CTA
-constexpr int LOSS_U = 4;        // 128-bit loads in flight per thread
+#ifndef LOSS_U_DEF
+#define LOSS_U_DEF 4
+#endif
+#ifndef LOSS_MINB
+#define LOSS_MINB 5
+#endif
+constexpr int LOSS_U = LOSS_U_DEF;   // 128-bit loads in flight per thread
 
 static int g_math_mode = 0;      // 0 fast, 1 precise
 
@@ -212,7 +218,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
 }
 
 template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
-__global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : 5) loss_kernel(const LossParams P) {
+__global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : LOSS_MINB) loss_kernel(const LossParams P) {
     loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE>(P, blockIdx.y, blockIdx.x);
 }
 

@@ -31,7 +31,8 @@ from .box_utils import _REG_WEIGHTS_C
 from .config import (FOCAL_LOSS_ALPHA, FOCAL_LOSS_GAMMA, IOU_THRESHOLDS_BACKGROUND, IOU_THRESHOLDS_FOREGROUND,
                      MAX_DETECTIONS_PER_IMAGE, NMS_THRES, SCORE_THRES, SMOOTH_L1_LOSS_BETA)
 from .detections import (_FORMATS, _image_sizes_tensor, _resize_ratio_tensor, default_candidate_capacity,
-                         postprocess_batch, slice_detections)
+                         postprocess_batch, postprocess_levels_async, slice_detections)
+from .losses import _level_desc, _ptr_array
 
 _vp = ctypes.c_void_p
 
@@ -75,9 +76,13 @@ class GraphStepResult:
             if found > capacity or fallback:
                 # rare: candidate pool overflow / an image needs more rounds than the lazy budget -> eager re-run of the
                 # same inputs through the drop-in call, which knows how to grow the pool and switch algorithm
-                self._dets = postprocess_batch(o.cls_preds, o.bbox_preds, o.anchors, o.anchor_stride, o.im_szs, o.score_thres,
-                                               o.nms_thres, o.max_det, cand_capacity=max(found, o.cap),
-                                               original_image_sizes=o.original_image_sizes, box_format=o.box_format)
+                kw = dict(cand_capacity=max(found, o.cap), original_image_sizes=o.original_image_sizes, box_format=o.box_format)
+                if o.levels:
+                    self._dets = postprocess_levels_async(o.cls_preds, o.bbox_preds, o.C, o.anchors, o.anchor_stride, o.im_szs,
+                                                          o.score_thres, o.nms_thres, o.max_det, **kw).result()
+                else:
+                    self._dets = postprocess_batch(o.cls_preds, o.bbox_preds, o.anchors, o.anchor_stride, o.im_szs,
+                                                   o.score_thres, o.nms_thres, o.max_det, **kw)
             else:
                 self._dets = (o.out_boxes, o.out_scores, o.out_labels, host[:N])
         return self._dets
@@ -92,7 +97,9 @@ class HotPathGraph:
 
     ``cls_preds [N,A,C]`` / ``bbox_preds [N,A,4]`` are the STATIC inputs: pass the tensors the head writes into
     (or copy into ``graph.cls_preds`` / ``graph.bbox_preds``); ``anchors`` is the shared ``[A,4]`` tensor of
-    :class:`AnchorGenerator`.  ``max_targets`` bounds the total number of GT boxes of a batch (static packed
+    :class:`AnchorGenerator`.  Both may instead be LISTS of the head's raw per-level conv outputs
+    ``[N, na*C, H_l, W_l]`` / ``[N, na*4, H_l, W_l]`` (row N1: no permute/cat pass); gradients then come back as lists
+    in the same layout.  ``max_targets`` bounds the total number of GT boxes of a batch (static packed
     buffers).  ``global_batch`` / ``group``: image-sharded multi-GPU use — the loss is divided by the global
     batch and ``step`` all-reduces the 16-byte loss vector (NCCL), exactly as ``ShardedRetinaNetLosses``.
     """
@@ -109,15 +116,24 @@ class HotPathGraph:
         if not (train or detect):
             raise ValueError("HotPathGraph: nothing to do (train=False, detect=False)")
         lib = _native.load()
-        for t, name, dt in ((cls_preds, "cls_preds", torch.float32), (bbox_preds, "bbox_preds", torch.float32),
-                            (anchors, "anchors", torch.float32)):
-            _native.ptr(t, dt, name)                      # CUDA + dtype + contiguity, or NativeError (no CPU path)
-        dev = cls_preds.device
-        N, A, C = cls_preds.shape
-        if C != num_classes:
-            raise ValueError(f"cls_preds has {C} classes, expected {num_classes}")
-        if bbox_preds.shape != (N, A, 4):
-            raise ValueError(f"bbox_preds must be [{N},{A},4], got {tuple(bbox_preds.shape)}")
+        self.levels = isinstance(cls_preds, (list, tuple))
+        _native.ptr(anchors, torch.float32, "anchors")    # CUDA + dtype + contiguity, or NativeError (no CPU path)
+        if self.levels:
+            cls_preds, bbox_preds = list(cls_preds), list(bbox_preds)
+            for t in cls_preds + bbox_preds:
+                _native.ptr(t, torch.float32, "level tensor")
+            self._desc, A, N = _level_desc(cls_preds, bbox_preds, num_classes)
+            self._cls_ptrs, self._box_ptrs = _ptr_array(cls_preds), _ptr_array(bbox_preds)
+            dev, C = cls_preds[0].device, num_classes
+        else:
+            _native.ptr(cls_preds, torch.float32, "cls_preds")
+            _native.ptr(bbox_preds, torch.float32, "bbox_preds")
+            dev = cls_preds.device
+            N, A, C = cls_preds.shape
+            if C != num_classes:
+                raise ValueError(f"cls_preds has {C} classes, expected {num_classes}")
+            if bbox_preds.shape != (N, A, 4):
+                raise ValueError(f"bbox_preds must be [{N},{A},4], got {tuple(bbox_preds.shape)}")
         if anchors.dim() == 2:
             stride = 0
         elif anchors.dim() == 3 and anchors.shape[0] == N:
@@ -153,9 +169,15 @@ class HotPathGraph:
             self.fg = torch.empty((N,), dtype=i32, device=dev)
             self.total = torch.zeros((4,), dtype=f32, device=dev)
             self.per_image = torch.zeros((N, 3), dtype=f32, device=dev)
-            self.grad_cls_preds = torch.empty_like(cls_preds)
-            self.grad_bbox_preds = torch.empty_like(bbox_preds)
-            self._loss_ws_bytes = lib.rn_train_loss_workspace_bytes(N, A, C)
+            if self.levels:
+                self.grad_cls_preds = [torch.empty_like(t) for t in cls_preds]
+                self.grad_bbox_preds = [torch.empty_like(t) for t in bbox_preds]
+                self._gcls_ptrs, self._gbox_ptrs = _ptr_array(self.grad_cls_preds), _ptr_array(self.grad_bbox_preds)
+                self._loss_ws_bytes = lib.rn_loss_levels_workspace_bytes(N, self._desc, len(cls_preds))
+            else:
+                self.grad_cls_preds = torch.empty_like(cls_preds)
+                self.grad_bbox_preds = torch.empty_like(bbox_preds)
+                self._loss_ws_bytes = lib.rn_train_loss_workspace_bytes(N, A, C)
             self._loss_ws = torch.empty((self._loss_ws_bytes,), dtype=torch.uint8, device=dev)
         else:
             self.total = self.per_image = self.grad_cls_preds = self.grad_bbox_preds = None
@@ -169,7 +191,8 @@ class HotPathGraph:
             self._host = torch.empty((N + 4,), dtype=i32, pin_memory=True)
             self._hw = _image_sizes_tensor(self.im_szs, dev)
             self._ratio = _resize_ratio_tensor(self.im_szs, original_image_sizes, dev)
-            self._pp_ws_bytes = lib.rn_postprocess_workspace_bytes(N, A, C, self.cap, M)
+            self._pp_ws_bytes = (lib.rn_postprocess_levels_workspace_bytes if self.levels else
+                                 lib.rn_postprocess_workspace_bytes)(N, A, C, self.cap, M)
             self._pp_ws = torch.empty((self._pp_ws_bytes,), dtype=torch.uint8, device=dev)
         self._side = torch.cuda.Stream(device=dev, priority=-1) if (train and detect and concurrent) else None
         self.graph = torch.cuda.CUDAGraph()
@@ -179,6 +202,15 @@ class HotPathGraph:
     def _enqueue_train(self):
         lib, N, A, C = self.lib, self.N, self.A, self.C
         alpha, gamma, beta, match_thr, back_thr = self.hp
+        if self.levels:
+            self._enqueue_match()
+            rc = lib.rn_loss_levels(self._cls_ptrs, self._box_ptrs, self._desc, len(self.cls_preds), self.anchors.data_ptr(),
+                                    self.anchor_stride, self.gt_boxes.data_ptr(), self.gt_off.data_ptr(), self.codes.data_ptr(),
+                                    self.fg.data_ptr(), N, A, C, alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div,
+                                    self.per_image.data_ptr(), self.total.data_ptr(), self._gcls_ptrs, self._gbox_ptrs,
+                                    self._loss_ws.data_ptr(), self._loss_ws_bytes, _native.stream_ptr(self.dev))
+            _native.check(rc, "rn_loss_levels")
+            return
         rc = lib.rn_train_loss(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(), self.anchor_stride,
                                self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(), self.gt_off.data_ptr(), N, A, C, match_thr,
                                back_thr, alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div, self.codes.data_ptr(),
@@ -209,6 +241,15 @@ class HotPathGraph:
     def _enqueue_detect(self):
         lib, N, A, C = self.lib, self.N, self.A, self.C
         meta = self.meta.data_ptr()
+        if self.levels:
+            rc = lib.rn_postprocess_levels(self._cls_ptrs, self._box_ptrs, self._desc, len(self.cls_preds), self.anchors.data_ptr(),
+                                           self.anchor_stride, self._hw.data_ptr(), N, A, C, self.score_thres, self.nms_thres,
+                                           self.max_det, _REG_WEIGHTS_C, 0, 0, self.cap, self.out_boxes.data_ptr(),
+                                           self.out_scores.data_ptr(), self.out_labels.data_ptr(), meta, meta + 4 * N,
+                                           self._pp_ws.data_ptr(), self._pp_ws_bytes, _native.stream_ptr(self.dev),
+                                           None if self._ratio is None else self._ratio.data_ptr(), _FORMATS[self.box_format])
+            _native.check(rc, "rn_postprocess_levels")
+            return
         rc = lib.rn_postprocess(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(),
                                 self.anchor_stride, self._hw.data_ptr(), N, A, C, self.score_thres, self.nms_thres, self.max_det,
                                 _REG_WEIGHTS_C, 0, None, 0, 0, self.cap, self.out_boxes.data_ptr(), self.out_scores.data_ptr(),

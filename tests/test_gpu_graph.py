@@ -164,3 +164,34 @@ def test_train_loss_call_equals_match_then_loss(P, case):
     got_ng = fused_loss_forward(x, bb, anc, 0, packed, 0.25, 2.0, 0.1, 0.5, 0.4, float(n_img), False)
     ref_ng = separate(2.0, False)
     assert torch.equal(got_ng[0], ref_ng[0]) and torch.equal(got_ng[1], ref_ng[1]) and got_ng[2] is None
+
+
+def test_graph_on_raw_level_outputs(P):
+    """HotPathGraph on the head's raw per-level conv outputs (row N1) equals the drop-in calls on the same lists
+    (bit-identical) and the [N,A,C] path (losses 1e-6, detections bit-identical)."""
+    from pytorch_retinanet_b200.graphs import HotPathGraph
+    cfg = S.CONFIGS[1]
+    dev = torch.device("cuda")
+    n_img = 3
+    b = S.make_batch(cfg, 21, n_img, clustered=True)
+    anc = b["anchors"].to(dev)
+    tg = to_cuda_targets(b["targets"])
+    xs = [t.to(dev) for t in S.nac_to_levels(b["cls_preds"], cfg.padded_hw)]
+    bs = [t.to(dev) for t in S.nac_to_levels(b["bbox_preds"], cfg.padded_hw)]
+    g = HotPathGraph(cfg.num_classes, xs, bs, anc, b["im_szs"])
+    res = g.step(tg)
+    L = P.RetinaNetLosses(cfg.num_classes)
+    xg, bg = [t.clone().requires_grad_(True) for t in xs], [t.clone().requires_grad_(True) for t in bs]
+    out = L(tg, {"cls_levels": xg, "bbox_levels": bg}, [anc] * n_img)
+    (out["classification_loss"] + out["regression_loss"]).backward()
+    for k in out:
+        assert torch.equal(res.losses[k], out[k].detach()), k
+    for got, want in zip(res.grads[0] + res.grads[1], xg + bg):
+        assert torch.equal(got, want.grad)
+    stub = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100, num_classes=cfg.num_classes)
+    dets = P.process_detections(stub, {"cls_levels": xs, "bbox_levels": bs}, [anc] * n_img, b["im_szs"])
+    _assert_same_dets(res.detections(), dets)
+    want_out, _, _, _, want_dets = _dropin(P, cfg, b["cls_preds"].to(dev), b["bbox_preds"].to(dev), anc, tg, b["im_szs"])
+    for k in want_out:
+        assert rel_close(res.losses[k], want_out[k].detach(), 1e-6), k
+    _assert_same_dets(res.detections(), want_dets)
