@@ -76,13 +76,15 @@ class GraphStepResult:
             if found > capacity or fallback:
                 # rare: candidate pool overflow / an image needs more rounds than the lazy budget -> eager re-run of the
                 # same inputs through the drop-in call, which knows how to grow the pool and switch algorithm
-                kw = dict(cand_capacity=max(found, o.cap), original_image_sizes=o.original_image_sizes, box_format=o.box_format)
+                kw = dict(cand_capacity=max(found, o.cap), original_image_sizes=o.original_image_sizes, box_format=o.box_format,
+                          pre_nms_topk=o.topk or None)
                 if o.levels:
                     self._dets = postprocess_levels_async(o.cls_preds, o.bbox_preds, o.C, o.anchors, o.anchor_stride, o.im_szs,
                                                           o.score_thres, o.nms_thres, o.max_det, **kw).result()
                 else:
                     self._dets = postprocess_batch(o.cls_preds, o.bbox_preds, o.anchors, o.anchor_stride, o.im_szs,
-                                                   o.score_thres, o.nms_thres, o.max_det, **kw)
+                                                   o.score_thres, o.nms_thres, o.max_det,
+                                                   level_offsets=o.level_offsets if o.topk else None, **kw)
             else:
                 self._dets = (o.out_boxes, o.out_scores, o.out_labels, host[:N])
         return self._dets
@@ -112,7 +114,8 @@ class HotPathGraph:
                  original_image_sizes: Optional[Sequence[Tuple[int, int]]] = None, box_format: str = "xyxy",
                  alpha: float = FOCAL_LOSS_ALPHA, gamma: float = FOCAL_LOSS_GAMMA, beta: float = SMOOTH_L1_LOSS_BETA,
                  match_thr: float = IOU_THRESHOLDS_FOREGROUND, back_thr: float = IOU_THRESHOLDS_BACKGROUND,
-                 cand_capacity: Optional[int] = None, concurrent: bool = True):
+                 cand_capacity: Optional[int] = None, concurrent: bool = True, pre_nms_topk: Optional[int] = None,
+                 level_offsets: Optional[Sequence[int]] = None):
         if not (train or detect):
             raise ValueError("HotPathGraph: nothing to do (train=False, detect=False)")
         lib = _native.load()
@@ -151,6 +154,15 @@ class HotPathGraph:
         self.im_szs = list(im_szs) if im_szs is not None else None
         self.original_image_sizes, self.box_format = original_image_sizes, box_format
         self.score_thres, self.nms_thres, self.max_det = float(score_thres), float(nms_thres), int(detections_per_img)
+        self.topk = int(pre_nms_topk) if pre_nms_topk else 0        # extension: top-k per (image, pyramid level) before NMS
+        self._lvl = None
+        if self.topk and not self.levels:
+            if level_offsets is None:
+                raise ValueError("pre_nms_topk requires level_offsets (anchor offsets of the pyramid levels)")
+            self.level_offsets = [int(v) for v in level_offsets]
+            self._lvl = (ctypes.c_int64 * len(self.level_offsets))(*self.level_offsets)
+        if self.topk and A * C >= (1 << 32):
+            raise ValueError("pre_nms_topk needs A*C < 2^32")
         self.group = group
         self.world = 1
         if global_batch is not None:
@@ -244,7 +256,7 @@ class HotPathGraph:
         if self.levels:
             rc = lib.rn_postprocess_levels(self._cls_ptrs, self._box_ptrs, self._desc, len(self.cls_preds), self.anchors.data_ptr(),
                                            self.anchor_stride, self._hw.data_ptr(), N, A, C, self.score_thres, self.nms_thres,
-                                           self.max_det, _REG_WEIGHTS_C, 0, 0, self.cap, self.out_boxes.data_ptr(),
+                                           self.max_det, _REG_WEIGHTS_C, self.topk, 0, self.cap, self.out_boxes.data_ptr(),
                                            self.out_scores.data_ptr(), self.out_labels.data_ptr(), meta, meta + 4 * N,
                                            self._pp_ws.data_ptr(), self._pp_ws_bytes, _native.stream_ptr(self.dev),
                                            None if self._ratio is None else self._ratio.data_ptr(), _FORMATS[self.box_format])
@@ -252,7 +264,8 @@ class HotPathGraph:
             return
         rc = lib.rn_postprocess(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(),
                                 self.anchor_stride, self._hw.data_ptr(), N, A, C, self.score_thres, self.nms_thres, self.max_det,
-                                _REG_WEIGHTS_C, 0, None, 0, 0, self.cap, self.out_boxes.data_ptr(), self.out_scores.data_ptr(),
+                                _REG_WEIGHTS_C, self.topk, self._lvl, (len(self.level_offsets) - 1) if self._lvl is not None else 0, 0,
+                                self.cap, self.out_boxes.data_ptr(), self.out_scores.data_ptr(),
                                 self.out_labels.data_ptr(), meta, meta + 4 * N, self._pp_ws.data_ptr(), self._pp_ws_bytes,
                                 _native.stream_ptr(self.dev), None if self._ratio is None else self._ratio.data_ptr(),
                                 _FORMATS[self.box_format])

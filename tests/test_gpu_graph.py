@@ -195,3 +195,27 @@ def test_graph_on_raw_level_outputs(P):
     for k in want_out:
         assert rel_close(res.losses[k], want_out[k].detach(), 1e-6), k
     _assert_same_dets(res.detections(), want_dets)
+
+
+def test_graph_pre_nms_topk_extension(P):
+    """pre_nms_topk (per-level top-k before NMS, an opt-in extension) through the graph equals the drop-in call."""
+    from pytorch_retinanet_b200.detections import postprocess_batch, slice_detections
+    from pytorch_retinanet_b200.graphs import HotPathGraph
+    cfg = S.CONFIGS[1]
+    dev = torch.device("cuda")
+    b = S.make_batch(cfg, 5, 2, clustered=True)
+    anc, x, bb = b["anchors"].to(dev), b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
+    offs = [0]
+    for h, w in S.grid_sizes(cfg.padded_hw):
+        offs.append(offs[-1] + 9 * h * w)
+    want = slice_detections(*postprocess_batch(x, bb, anc, 0, b["im_szs"], 0.05, 0.5, 100, pre_nms_topk=50, level_offsets=offs))
+    plain = slice_detections(*postprocess_batch(x, bb, anc, 0, b["im_szs"], 0.05, 0.5, 100))
+    g = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"], train=False, pre_nms_topk=50, level_offsets=offs)
+    got = g.step().detections()
+    _assert_same_dets(got, want)
+    assert any(not torch.equal(a["scores"], p["scores"]) for a, p in zip(got, plain) if a["scores"].shape == p["scores"].shape) or \
+        any(a["scores"].shape != p["scores"].shape for a, p in zip(got, plain))      # the filter is active
+    xs = [t.to(dev) for t in S.nac_to_levels(b["cls_preds"], cfg.padded_hw)]
+    bs = [t.to(dev) for t in S.nac_to_levels(b["bbox_preds"], cfg.padded_hw)]
+    gl = HotPathGraph(cfg.num_classes, xs, bs, anc, b["im_szs"], train=False, pre_nms_topk=50)
+    _assert_same_dets(gl.step().detections(), want)
