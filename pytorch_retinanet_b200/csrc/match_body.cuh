@@ -33,15 +33,16 @@ __device__ __forceinline__ bool box_well_formed(const float4 b) {
            (fabsf(b.z) <= 3.0e38f) && (fabsf(b.w) <= 3.0e38f);
 }
 
-// Per-warp matching state of one group of 32 anchors (one per lane).
+// Per-warp matching state of one group of 32*K anchors (K per lane).
 struct WarpCull {
     bool fast;                       // warp-uniform: culling / pruning / non-NaN fast path allowed
     float bx1, by1, bx2, by2;        // bounding box of the warp's anchors
     float ag_lo, ag_hi;              // GT areas outside this range cannot reach bg_thr with any anchor of the warp
 };
 
-template <bool FAST>
-__device__ __forceinline__ WarpCull warp_cull_setup(const float4 a, const float aa, const bool live, const float prune_c) {
+template <bool FAST, int K>
+__device__ __forceinline__ WarpCull warp_cull_setup(const float4 (&a)[K], const float (&aa)[K], const bool (&live)[K],
+                                                    const float prune_c) {
     WarpCull w;
     w.fast = FAST;
     w.bx1 = w.by1 = w.bx2 = w.by2 = 0.f;
@@ -49,13 +50,25 @@ __device__ __forceinline__ WarpCull warp_cull_setup(const float4 a, const float 
     w.ag_hi = INFINITY;
     if (FAST) {
         // positive finite extents imply finite, ordered coordinates differences; NaN fails every test
-        bool ok = !live || ((a.z - a.x) > 0.0f && (a.w - a.y) > 0.0f && aa <= 3.0e38f && fabsf(a.x) <= 3.0e38f && fabsf(a.y) <= 3.0e38f);
+        bool ok = true;
+        float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY, amin = INFINITY, amax = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            ok = ok && (!live[k] || ((a[k].z - a[k].x) > 0.0f && (a[k].w - a[k].y) > 0.0f && aa[k] <= 3.0e38f &&
+                                     fabsf(a[k].x) <= 3.0e38f && fabsf(a[k].y) <= 3.0e38f));
+            if (live[k]) {
+                x1 = fminf(x1, a[k].x); y1 = fminf(y1, a[k].y);
+                x2 = fmaxf(x2, a[k].z); y2 = fmaxf(y2, a[k].w);
+                amin = fminf(amin, aa[k]); amax = fmaxf(amax, aa[k]);
+            }
+        }
         w.fast = __all_sync(0xffffffffu, ok);
-        w.bx1 = rn::warp_min(live ? a.x : INFINITY);
-        w.by1 = rn::warp_min(live ? a.y : INFINITY);
-        w.bx2 = rn::warp_max(live ? a.z : -INFINITY);
-        w.by2 = rn::warp_max(live ? a.w : -INFINITY);
-        const float amin = rn::warp_min(live ? aa : INFINITY), amax = rn::warp_max(live ? aa : 0.0f);
+        w.bx1 = rn::warp_min(x1);
+        w.by1 = rn::warp_min(y1);
+        w.bx2 = rn::warp_max(x2);
+        w.by2 = rn::warp_max(y2);
+        amin = rn::warp_min(amin);
+        amax = rn::warp_max(amax);
         w.ag_lo = amin * prune_c * 0.999f;               // GT areas outside [ag_lo, ag_hi] give IoU < bg_thr with
         w.ag_hi = amax / (prune_c * 0.999f);             // every anchor of this warp (IoU <= area ratio)
     }
@@ -73,10 +86,12 @@ __device__ __forceinline__ void stage_gt_tile(float4 *s_box, float *s_area, cons
     }
 }
 
-// One warp x one staged tile of `tn` GT boxes (global indices t0..t0+tn): cull, then evaluate the surviving pairs.
+// One warp x one staged tile of `tn` GT boxes (global indices t0..t0+tn): cull against the warp's bounding box and
+// area range, then evaluate the surviving GT boxes against the K anchors of every lane.
+template <int K>
 __device__ __forceinline__ void match_tile(const float4 *s_box, const float *s_area, const int tn, const int t0,
-                                           const float4 a, const float aa, const WarpCull &w, const float prune_c,
-                                           float &best, int &bi) {
+                                           const float4 (&a)[K], const float (&aa)[K], const WarpCull &w,
+                                           const float prune_c, float (&best)[K], int (&bi)[K]) {
     const int lane = threadIdx.x & 31;
     for (int base = 0; base < tn; base += 32) {
         unsigned mask;
@@ -99,21 +114,27 @@ __device__ __forceinline__ void match_tile(const float4 *s_box, const float *s_a
             const float ag = s_area[j];
             const int gi = t0 + j;
             if (w.fast && ag == ag) {
-                // well-formed pair: no NaN possible, IoU is +0 unless both extents are positive
-                float ww = __fsub_rn(fminf(g.z, a.z), fmaxf(g.x, a.x));
-                float hh = __fsub_rn(fminf(g.w, a.w), fmaxf(g.y, a.y));
-                if (ww > 0.0f && hh > 0.0f) {
-                    float inter = __fmul_rn(ww, hh);
-                    float uni = __fsub_rn(__fadd_rn(ag, aa), inter);
-                    if (inter >= __fmul_rn(uni, prune_c)) {   // may reach bg_thr: exact quotient
-                        float v = __fdiv_rn(inter, uni);
-                        if (v > best) { best = v; bi = gi; }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    // well-formed pair: no NaN possible, IoU is +0 unless both extents are positive
+                    float ww = __fsub_rn(fminf(g.z, a[k].z), fmaxf(g.x, a[k].x));
+                    float hh = __fsub_rn(fminf(g.w, a[k].w), fmaxf(g.y, a[k].y));
+                    if (ww > 0.0f && hh > 0.0f) {
+                        float inter = __fmul_rn(ww, hh);
+                        float uni = __fsub_rn(__fadd_rn(ag, aa[k]), inter);
+                        if (inter >= __fmul_rn(uni, prune_c)) {   // may reach bg_thr: exact quotient
+                            float v = __fdiv_rn(inter, uni);
+                            if (v > best[k]) { best[k] = v; bi[k] = gi; }
+                        }
                     }
                 }
             } else {
-                float v = iou_generic(g, box_area(g), a, aa);   // s_area holds the NaN marker for malformed boxes
-                if (best == best) {                             // NaN, once taken, stays
-                    if (v != v || v > best) { best = v; bi = gi; }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float v = iou_generic(g, box_area(g), a[k], aa[k]);   // s_area holds the NaN marker for malformed boxes
+                    if (best[k] == best[k]) {                             // NaN, once taken, stays
+                        if (v != v || v > best[k]) { best[k] = v; bi[k] = gi; }
+                    }
                 }
             }
         }
@@ -129,25 +150,31 @@ __device__ __forceinline__ int match_decision(const float best, const int bi, co
     return m;
 }
 
-// Matches anchor `a` (this thread's; `live` = it exists) against the G boxes gt[0..G) of one image.  Must be
-// called by ALL MATCH_BLOCK threads of the CTA (barriers inside); s_box / s_area are GT_TILE-sized shared
-// buffers.  Returns -2 ignore, -1 background, g >= 0 matched GT index (box_utils.py:51-80).
-template <bool FAST>
-__device__ __forceinline__ int match_block(float4 *s_box, float *s_area, const float4 a, const bool live,
-                                           const float4 *__restrict__ gt, const int G, const float fg_thr,
-                                           const float bg_thr, const float prune_c) {
-    const float aa = box_area(a);
-    const WarpCull w = warp_cull_setup<FAST>(a, aa, live, prune_c);
-    float best = w.fast ? 0.0f : -INFINITY;
-    int bi = 0;
+// Matches the K anchors a[] of this thread (`live[k]` = it exists) against the G boxes gt[0..G) of one image.  Must
+// be called by ALL MATCH_BLOCK threads of the CTA (barriers inside); s_box / s_area are GT_TILE-sized shared
+// buffers.  m[k] = -2 ignore, -1 background, g >= 0 matched GT index (box_utils.py:51-80).  K > 1 amortises the
+// per-warp work (bounding-box reductions, the cull loop over all GT boxes, staging) over 32*K anchors.
+template <bool FAST, int K>
+__device__ __forceinline__ void match_block(float4 *s_box, float *s_area, const float4 (&a)[K], const bool (&live)[K],
+                                            const float4 *__restrict__ gt, const int G, const float fg_thr,
+                                            const float bg_thr, const float prune_c, int (&m)[K]) {
+    float aa[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) aa[k] = box_area(a[k]);
+    const WarpCull w = warp_cull_setup<FAST, K>(a, aa, live, prune_c);
+    float best[K];
+    int bi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { best[k] = w.fast ? 0.0f : -INFINITY; bi[k] = 0; }
     for (int t0 = 0; t0 < G; t0 += GT_TILE) {
         const int tn = min(GT_TILE, G - t0);
         __syncthreads();
         stage_gt_tile(s_box, s_area, gt + t0, tn, threadIdx.x, MATCH_BLOCK);
         __syncthreads();
-        match_tile(s_box, s_area, tn, t0, a, aa, w, prune_c, best, bi);
+        match_tile<K>(s_box, s_area, tn, t0, a, aa, w, prune_c, best, bi);
     }
-    return match_decision(best, bi, G, fg_thr, bg_thr);
+#pragma unroll
+    for (int k = 0; k < K; ++k) m[k] = match_decision(best[k], bi[k], G, fg_thr, bg_thr);
 }
 
 // Packed per-anchor target of the loss kernels: -2 / -1 / (g | (label-1) << 20); labels are 1-based (README.md:132).

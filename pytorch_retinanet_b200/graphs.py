@@ -239,14 +239,16 @@ class HotPathGraph:
                           self.gt_off.data_ptr(), N, match_thr, back_thr, None, self.codes.data_ptr(), self.fg.data_ptr(), s)
         _native.check(rc, "rn_match")
 
-    def _enqueue_loss(self):
+    def _enqueue_loss(self, want_grad: bool = True):
+        """rn_loss alone on the codes of the last step (bench.py times the streaming kernel by itself with it)."""
         lib, N, A, C = self.lib, self.N, self.A, self.C
         alpha, gamma, beta = self.hp[:3]
         s = _native.stream_ptr(self.dev)
         rc = lib.rn_loss(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(), self.anchor_stride,
                          self.gt_boxes.data_ptr(), self.gt_off.data_ptr(), self.codes.data_ptr(), self.fg.data_ptr(), N, A, C,
                          alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div, self.per_image.data_ptr(), self.total.data_ptr(),
-                         self.grad_cls_preds.data_ptr(), self.grad_bbox_preds.data_ptr(), self._loss_ws.data_ptr(),
+                         self.grad_cls_preds.data_ptr() if want_grad else None,
+                         self.grad_bbox_preds.data_ptr() if want_grad else None, self._loss_ws.data_ptr(),
                          self._loss_ws_bytes, s)
         _native.check(rc, "rn_loss")
 
