@@ -37,8 +37,11 @@ using namespace rnmatch;
 #endif
 constexpr int MATCH_SPAN = MATCH_BLOCK * MATCH_K;   // anchors per CTA
 
+#ifndef MATCH_MINB
+#define MATCH_MINB 5    // 48 registers: 30.5 us; unconstrained (64 regs) 31.2 us, 6 CTAs (40 regs, spills) 31.1 us at config 2
+#endif
 template <bool FAST>
-__global__ void __launch_bounds__(MATCH_BLOCK)
+__global__ void __launch_bounds__(MATCH_BLOCK, MATCH_MINB)
 match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_stride,
              const float4 *__restrict__ gt,
              const long long *__restrict__ labels, const int *__restrict__ gt_off, float fg_thr, float bg_thr,
