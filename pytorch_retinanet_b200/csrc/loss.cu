@@ -407,9 +407,10 @@ extern "C" int rn_train_loss(const float *logits, const float *bbox, const float
 // right before this path.  loss_levels_kernel consumes the conv outputs directly (index math only) and
 // writes the gradients back in NCHW, so that pass disappears.  Element (n, a, c, y, x) of a level lives
 // at ((n*na + a)*C + c)*H*W + y*W + x and belongs to anchor lvl_off + (y*W + x)*na + a.
-// One CTA = 128 consecutive positions of one level x one cell-anchor index a x its C class planes; the
-// tile's packed codes (one per position) are staged in shared memory; each warp walks class planes, four
-// in flight, each lane owning 4 positions (a 128-bit load when H*W % 4 == 0, else coalesced scalar loads).
+// One CTA = 128 consecutive positions of one level x one cell-anchor index a x its C class planes; each warp
+// walks class planes, LV_CU in flight, each lane owning 4 positions (a 128-bit load when H*W % 4 == 0, else
+// coalesced scalar loads).  32 registers per thread -> 8 CTAs per SM (full occupancy), which is worth more here
+// than loads in flight per thread: the CTAs are short (C/8 planes per warp) and many.
 namespace {
 #ifndef LV_PU
 #define LV_PU 1      // 128-position chunks of one plane in flight per lane
@@ -445,9 +446,10 @@ struct LvlLossParams {
 };
 
 // One CTA = (tile of 128 positions of one level, image n, cell-anchor index a): C class planes of 512 B.
-// No shared memory and no barrier before the streaming loop: each lane keeps the packed codes of its 4
+// No shared memory and no barrier before the streaming loop: each lane keeps the ignore flags of its 4
 // positions in registers (they are the same for all C planes) and the first plane loads are issued together
-// with the code loads.
+// with the code loads.  The plane walk treats every element as a negative; the one positive class element of a
+// foreground anchor is patched afterwards, in the per-position regression loop.
 template <int VEC, bool WANT_GRAD, bool GAMMA2>
 __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const LvlDesc &D, int tile, int n, int a) {
     const int p0 = tile * LV_TILE;

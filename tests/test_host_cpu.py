@@ -139,3 +139,22 @@ def test_sharded_loss_two_ranks_gloo():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_graph_api_rejects_cpu_tensors_and_bad_arguments():
+    """HotPathGraph validates its arguments before touching the GPU: CPU tensors are refused (no CPU path)."""
+    import pytest
+    import torch
+    from pytorch_retinanet_b200 import _native
+    from pytorch_retinanet_b200.graphs import HotPathGraph
+    x, b, a = torch.zeros((2, 9, 4)), torch.zeros((2, 9, 4)), torch.zeros((9, 4))
+    with pytest.raises(ValueError):
+        HotPathGraph(4, x, b, a, train=False, detect=False)
+    try:
+        _native.load()
+    except _native.NativeError:
+        pytest.skip("CUDA library not built on this machine")
+    with pytest.raises(_native.NativeError):
+        HotPathGraph(4, x, b, a, [(8, 8), (8, 8)])
+    with pytest.raises(_native.NativeError):
+        HotPathGraph(4, [x.view(2, 36, 1, 1)], [b.view(2, 36, 1, 1)], a, [(8, 8), (8, 8)])
