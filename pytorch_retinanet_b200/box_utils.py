@@ -73,6 +73,9 @@ class PackedTargets:
         self.total = sum(counts)
         self.counts = counts
         device = torch.device(device)
+        if device.type == "cuda" and self.total and all(not b.is_cuda for b, c in zip(boxes, counts) if c) and \
+                self._pack_from_host(boxes, labels, counts, device, ratios_hw):
+            return
         if device.type == "cuda" and self._pack_native(boxes, labels, counts, device, ratios_hw):
             return
         # generic path (dtype/device conversions needed, or host-side use in the CPU tests): torch ops
@@ -107,6 +110,40 @@ class PackedTargets:
             # <= a few hundred bytes: the driver embeds a pageable copy of this size in the command stream and
             # returns without waiting for the GPU, which is cheaper than allocating pinned staging memory
             self.offsets = torch.tensor(offs, dtype=torch.int32, device=device)
+
+    def _pack_from_host(self, boxes, labels, counts, device, ratios_hw) -> bool:
+        """Targets still on the HOST (what ``collate_fn`` hands over, utils/detection_utils.py:7-9): instead of one
+        small pageable host->device copy per tensor (2N per batch), offsets, boxes and labels are laid out in ONE
+        pinned staging buffer and shipped with ONE asynchronous copy; the packed tensors are views of the device
+        copy.  The optional box resize is the same fp32 multiply torchvision's ``resize_boxes`` performs."""
+        N, total = len(counts), self.total
+        if labels is not None:
+            for l, c in zip(labels, counts):
+                if l.numel() != c:
+                    raise ValueError("targets: number of labels does not match number of boxes")
+        off_bytes = ((N + 1) * 4 + 15) // 16 * 16
+        box_bytes = total * 16
+        lab_bytes = total * 8 if labels is not None else 0
+        stage = torch.empty((off_bytes + box_bytes + lab_bytes,), dtype=torch.uint8, pin_memory=True)
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        stage[:(N + 1) * 4].view(torch.int32).copy_(torch.tensor(offs, dtype=torch.int32))
+        hb = stage[off_bytes:off_bytes + box_bytes].view(torch.float32).view(total, 4)
+        live = [b.reshape(-1, 4).to(torch.float32) for b, c in zip(boxes, counts) if c]
+        if ratios_hw is not None:
+            live = [b * torch.tensor([rw, rh, rw, rh], dtype=torch.float32)
+                    for b, (rh, rw) in zip(live, [r for r, c in zip(ratios_hw, counts) if c])]
+        torch.cat(live, out=hb)
+        if labels is not None:
+            hl = stage[off_bytes + box_bytes:].view(torch.int64)
+            torch.cat([l.reshape(-1).to(torch.int64) for l, c in zip(labels, counts) if c], out=hl)
+        dev_buf = stage.to(device, non_blocking=True)               # the one H2D copy
+        self._staging = stage                                       # keep the pinned block alive until the copy ran
+        self.offsets = dev_buf[:(N + 1) * 4].view(torch.int32)
+        self.boxes = dev_buf[off_bytes:off_bytes + box_bytes].view(torch.float32).view(total, 4)
+        self.labels = dev_buf[off_bytes + box_bytes:].view(torch.int64) if labels is not None else None
+        return True
 
     def _pack_native(self, boxes, labels, counts, device, ratios_hw) -> bool:
         """One ``rn_pack_targets`` launch (row N3) when every tensor already is a contiguous fp32 / int64 tensor

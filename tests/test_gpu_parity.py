@@ -656,3 +656,32 @@ def test_no_cpu_fallback(P):
         P.matcher(anc, anc[:3])
     with pytest.raises(_native.NativeError):
         P.AnchorGenerator().grid_anchors(S.grid_sizes((64, 64)), torch.device("cpu"))
+
+
+def test_pack_targets_from_host_single_copy(P):
+    """Targets still on the host (the reference's collate_fn output) are packed into one pinned buffer and shipped
+    with ONE H2D copy: same packed tensors as the device-side packer, with and without the GT-box resize, and the
+    loss accepts them directly."""
+    from pytorch_retinanet_b200.box_utils import PackedTargets
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    boxes = [torch.rand((k, 4), generator=g) * 300 for k in (5, 0, 17, 1)]
+    boxes[1] = torch.zeros((0, 4))
+    labels = [torch.randint(1, 21, (b.shape[0],), generator=g) for b in boxes]
+    ratios = [(1.5, 0.75), (1.0, 1.0), (0.5, 2.0), (1.25, 1.25)]
+    for rat in (None, ratios):
+        host = PackedTargets(boxes, labels, dev, ratios_hw=rat)
+        devp = PackedTargets([b.to(dev) for b in boxes], [l.to(dev) for l in labels], dev, ratios_hw=rat)
+        assert hasattr(host, "_staging") and not hasattr(devp, "_staging")
+        assert host.total == devp.total == 23 and host.counts == devp.counts
+        assert torch.equal(host.offsets, devp.offsets) and host.offsets.dtype == torch.int32
+        assert torch.equal(host.boxes, devp.boxes[:23]) and torch.equal(host.labels, devp.labels[:23])
+    cfg = S.CONFIGS[1]
+    b = S.make_batch(cfg, 9, 2, clustered=True)
+    anc = b["anchors"].to(dev)
+    L = P.RetinaNetLosses(cfg.num_classes)
+    x, bb = b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
+    a = L(b["targets"], {"cls_preds": x, "bbox_preds": bb}, [anc] * 2)                        # CPU targets
+    c = L(to_cuda_targets(b["targets"]), {"cls_preds": x, "bbox_preds": bb}, [anc] * 2)       # CUDA targets
+    for k in a:
+        assert torch.equal(a[k], c[k]), k
