@@ -174,9 +174,15 @@ class HotPathGraph:
 
         f32, i32, i64 = torch.float32, torch.int32, torch.int64
         if train:
-            self.gt_boxes = torch.zeros((max(self.max_targets, 1), 4), dtype=f32, device=dev)
-            self.gt_labels = torch.ones((max(self.max_targets, 1),), dtype=i64, device=dev)
-            self.gt_off = torch.zeros((N + 1,), dtype=i32, device=dev)
+            # static packed targets: ONE byte buffer [offsets | boxes | labels] so that host-resident targets can be
+            # uploaded with a single copy; the three tensors the kernels see are views of it
+            cap = max(self.max_targets, 1)
+            self._off_bytes = ((N + 1) * 4 + 15) // 16 * 16
+            self._tgt_buf = torch.zeros((self._off_bytes + cap * 24,), dtype=torch.uint8, device=dev)
+            self.gt_off = self._tgt_buf[:(N + 1) * 4].view(i32)
+            self.gt_boxes = self._tgt_buf[self._off_bytes:self._off_bytes + cap * 16].view(f32).view(cap, 4)
+            self.gt_labels = self._tgt_buf[self._off_bytes + cap * 16:].view(i64)
+            self.gt_labels.fill_(1)
             self.codes = torch.empty((N, A), dtype=i32, device=dev)
             self.fg = torch.empty((N,), dtype=i32, device=dev)
             self.total = torch.zeros((4,), dtype=f32, device=dev)
@@ -311,6 +317,8 @@ class HotPathGraph:
         if sum(counts) > self.max_targets:
             raise ValueError(f"{sum(counts)} GT boxes exceed max_targets={self.max_targets} of this graph")
         dev = self.dev
+        if sum(counts) and all(not b.is_cuda for b, c in zip(boxes, counts) if c):
+            return self._load_targets_from_host(boxes, labels, counts)
         for b, l, c in zip(boxes, labels, counts):
             if c and not (b.dtype == torch.float32 and b.device == dev and b.is_contiguous() and l.dtype == torch.int64
                           and l.device == dev and l.is_contiguous() and l.numel() == c and b.dim() == 2 and b.shape[1] == 4):
@@ -323,6 +331,27 @@ class HotPathGraph:
             rc = self.lib.rn_pack_targets(bp, lp, cnt, N, None, self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(),
                                           self.gt_off.data_ptr(), _native.stream_ptr(dev))
         _native.check(rc, "rn_pack_targets")
+
+    def _load_targets_from_host(self, boxes, labels, counts) -> None:
+        """Host-resident targets (the reference's ``collate_fn`` output): one pinned image of the static target buffer,
+        one asynchronous H2D copy (no per-tensor copies, no packing launch)."""
+        N, total, cap = self.N, sum(counts), max(self.max_targets, 1)
+        stage = torch.empty((self._off_bytes + cap * 24,), dtype=torch.uint8, pin_memory=True)
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        stage[:(N + 1) * 4].view(torch.int32).copy_(torch.tensor(offs, dtype=torch.int32))
+        hb = stage[self._off_bytes:self._off_bytes + total * 16].view(torch.float32).view(total, 4)
+        torch.cat([b.reshape(-1, 4).to(torch.float32) for b, c in zip(boxes, counts) if c], out=hb)
+        lab0 = self._off_bytes + cap * 16
+        hl = stage[lab0:lab0 + total * 8].view(torch.int64)
+        live = [l.reshape(-1).to(torch.int64) for l, c in zip(labels, counts) if c]
+        if sum(l.numel() for l in live) != total:
+            raise ValueError("targets: number of labels does not match number of boxes")
+        torch.cat(live, out=hl)
+        # only the used prefix of each section matters; three slices of one pinned block, stream-ordered before the graph
+        self._tgt_buf[:self._off_bytes + total * 16].copy_(stage[:self._off_bytes + total * 16], non_blocking=True)
+        self._tgt_buf[lab0:lab0 + total * 8].copy_(stage[lab0:lab0 + total * 8], non_blocking=True)
 
     def step(self, targets: Optional[Sequence[Dict[str, Tensor]]] = None) -> GraphStepResult:
         """One pass of the path over the current contents of ``cls_preds`` / ``bbox_preds``.  ``targets=None`` keeps the

@@ -91,6 +91,11 @@ def test_graph_train_only_and_detect_only(P):
     r = gt.step(tg)
     assert torch.equal(r.losses["classification_loss"], want_out["classification_loss"].detach())
     assert torch.equal(r.grads[0], want_gx)
+    gt.grad_cls_preds.zero_()
+    r = gt.step(b["targets"])                 # host-resident targets: uploaded with the pinned single-buffer route
+    assert torch.equal(r.losses["classification_loss"], want_out["classification_loss"].detach())
+    assert torch.equal(r.losses["regression_loss"], want_out["regression_loss"].detach())
+    assert torch.equal(r.grads[0], want_gx)
     with pytest.raises(RuntimeError):
         r.detections()
     gd = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"], train=False, detect=True)
