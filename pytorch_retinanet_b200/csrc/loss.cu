@@ -558,7 +558,7 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
         const long long b0 = ((long long)(n * D.na + a) * 4) * D.HW + p0 + p;
         float gr[4] = {0.f, 0.f, 0.f, 0.f};
         if (cd >= 0) {
-            {
+            if ((cd >> 20) < P.C) {               // a label outside 1..C matches no class plane (as in loss_kernel)
                 const long long e = (((long long)n * D.na + a) * P.C + (cd >> 20)) * D.HW + p0 + p;
                 const float xx = __ldg(D.cls + e) + 1.0f;
                 float pp, sp;
