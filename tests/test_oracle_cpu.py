@@ -151,3 +151,42 @@ def test_oracle_matches_live_reference():
         for a, b_ in zip(dr, do):
             assert torch.equal(a["scores"], b_["scores"]) and torch.equal(a["labels"], b_["labels"])
             assert torch.equal(a["boxes"], b_["boxes"])
+
+
+def test_degenerate_inputs_both_oracles_agree():
+    """Adversarial inputs for the two restatements (torch op-for-op and plain C): exact-threshold IoUs, ties, duplicate
+    and zero-area boxes, NaN / inf coordinates, equal NMS scores.  The torch oracle is the reference's own op
+    sequence (bit-identical to it, see test_oracle_matches_live_reference); the C oracle must agree with it."""
+    g = torch.Generator().manual_seed(11)
+    base = torch.tensor([[0., 0., 10., 10.], [100., 100., 110., 110.], [0., 0., 10., 20.], [5., 5., 5., 5.],
+                         [0., 0., 10., 12.5], [2., 2., 8., 8.]])
+    extra = torch.rand((40, 2), generator=g) * 50
+    wh = torch.rand((40, 2), generator=g) * 30 + 1
+    anchors = torch.cat([base, torch.cat([extra, extra + wh], 1), base[:2]])            # duplicates at the end
+    cases = [
+        torch.tensor([[0., 0., 10., 10.], [0., 0., 10., 10.]]),                         # tie -> first GT
+        torch.tensor([[0., 0., 10., 8.], [0., 0., 10., 25.]]),                          # IoU 0.8 / exactly 0.4 with anchor 0
+        torch.tensor([[3., 3., 3., 3.], [0., 0., 10., 10.]]),                           # zero-area GT
+        torch.tensor([[float("nan"), 0., 10., 10.], [0., 0., 10., 10.]]),               # NaN propagates through max
+        torch.tensor([[0., 0., float("inf"), 10.], [20., 20., 40., 45.]]),              # inf extent
+        torch.tensor([[10., 10., 0., 0.], [0., 0., 10., 10.]]),                         # inverted box (negative extent)
+        torch.zeros((0, 4)),                                                            # no GT -> all ignore
+        torch.cat([extra[:25], extra[:25] + wh[:25]], 1),                               # GT identical to some anchors
+    ]
+    for k, gt in enumerate(cases):
+        want = O.match(anchors, gt).numpy()
+        got = CO.match(anchors, gt)
+        assert np.array_equal(got, want), (k, got[:12], want[:12])
+    # NMS: equal scores keep the lower index, strict threshold, many exact duplicates
+    boxes = torch.cat([base[[0, 0, 2, 4, 5]], torch.cat([extra[:20], extra[:20] + wh[:20]], 1)])
+    for scores in (torch.ones(boxes.shape[0]), torch.linspace(1, 0.1, boxes.shape[0]).round(decimals=1),
+                   torch.rand(boxes.shape[0], generator=g)):
+        for thr in (0.5, 0.4, 0.0, 1.0):
+            want = O.nms_keep(boxes, scores, thr).numpy()
+            got = CO.nms(boxes, scores, thr)
+            assert np.array_equal(np.asarray(got), want), (thr, got, want)
+            try:
+                import torchvision
+                assert np.array_equal(torchvision.ops.nms(boxes, scores, thr).numpy(), want), thr
+            except ImportError:
+                pass
