@@ -158,3 +158,24 @@ def test_graph_api_rejects_cpu_tensors_and_bad_arguments():
         HotPathGraph(4, x, b, a, [(8, 8), (8, 8)])
     with pytest.raises(_native.NativeError):
         HotPathGraph(4, [x.view(2, 36, 1, 1)], [b.view(2, 36, 1, 1)], a, [(8, 8), (8, 8)])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the reference's CPU path on the host cores) must print exactly ONE JSON line on
+    stdout with the contract's keys — it runs without a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"].startswith("images/sec") and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
