@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RN_ABI_VERSION 1
+#define RN_ABI_VERSION 2
 
 #define RN_E_BADARG   (-1)  /* null pointer / negative size / unsupported combination          */
 #define RN_E_TOOLARGE (-2)  /* size exceeds a documented limit (levels, cell anchors, classes) */
@@ -42,6 +42,35 @@ extern "C" {
 #define RN_PP_GENERAL 1
 
 typedef void *rn_stream_t; /* cudaStream_t */
+
+/* ---- image-sharded multi-GPU exchange ----------------------------------------------
+ * The reference computes the loss per image and averages over the batch (retinanet/losses.py:126-140); with the
+ * batch sharded by image over the GPUs of one NVLink/NVSwitch box the ONLY exchange of the path is the sum of the
+ * 16-byte vector out_total = {cls, reg, sum F, N_local} over the ranks.  It is folded into the loss's final
+ * reduction kernel: the block that finishes the local sum stores its four values, each paired with a step
+ * sequence number in one 8-byte word, straight into every peer's receive slots over NVLink (peer-mapped memory),
+ * then reads the slots the peers filled for it and adds them in rank order — every rank ends with the same bits,
+ * no separate collective launch, no host involvement, CUDA-graph capturable.
+ * A receive buffer (rn_comm_bytes() bytes, zero-initialised, allocated with rn_comm_alloc so that it can be
+ * exported) lives on every rank; peers[r] is rank r's buffer as mapped into THIS process (peers[rank] = the local
+ * one).  Every rank must run the same sequence of exchanging calls (as with any collective).  A rank that does not
+ * hear from a peer within ~2 s writes NaN into out_total and sets the error word (rn_comm_error) instead of hanging. */
+#define RN_MAX_PEERS 16
+typedef struct {
+    void *peers[RN_MAX_PEERS]; /* device pointers: receive buffer of every rank, mapped into this process */
+    int32_t rank, world;
+} rn_exchange_t;
+size_t rn_comm_bytes(void);
+int rn_comm_alloc(void **out_ptr);                                 /* cudaMalloc + zero (current device)        */
+int rn_comm_free(void *ptr);
+int rn_comm_export(void *ptr, void *handle_out_host /*64 bytes*/); /* cudaIpcGetMemHandle                         */
+int rn_comm_import(const void *handle_host /*64 bytes*/, void **out_ptr); /* cudaIpcOpenMemHandle (peer access)   */
+int rn_comm_unmap(void *imported_ptr);                             /* cudaIpcCloseMemHandle                       */
+int rn_comm_error(const void *local_buf, int32_t *out_host);       /* synchronous read of the error word (tests) */
+/* The exchange by itself: total[4] <- sum over the ranks (one 32-thread launch).  For a rank whose shard is empty
+ * (it launches no loss kernel but must take part) and for tests; rn_loss / rn_train_loss / rn_loss_levels do the
+ * same inside their final reduction when given `exchange_host`.                                               */
+int rn_exchange_total(float *total /*[4] in/out*/, const rn_exchange_t *exchange_host, rn_stream_t stream);
 
 int rn_abi_version(void);
 const char *rn_last_error(void);
@@ -72,12 +101,16 @@ int rn_pack_targets(const float *const *boxes_host, const int64_t *const *labels
  * -1 background, g >= 0 index of the matched GT box inside image n.  Images with zero GT boxes
  * get -2 everywhere (box_utils.py:70-71).
  * Optional outputs (may be NULL):
- *   codes   [N,A] int32 — packed per-anchor target used by rn_loss: -2 / -1 / (g | (label-1) << 20)
- *                         (requires gt_labels; G per image < 2^20, classes < 2^11)
+ *   codes   [N,A] int32 — packed per-anchor target used by rn_loss: -2 / -1 / (g | cls << 20), cls = label-1 for
+ *                         labels 1..2047 and 2047 ("no class column") otherwise — a label 0 keeps the regression term
+ *                         and gets all-zero class targets like the reference (losses.py:96-103); a label > C, for
+ *                         which the reference's one_hot raises, trains as background here.  Requires gt_labels,
+ *                         sumG < 2^20 and C <= 2047.
  *   fg_count[N]   int32 — number of foreground anchors per image (zeroed by the call itself).       */
 int rn_match(const float *anchors /*[A,4] or [N,A,4]*/, int64_t A, int64_t anchor_image_stride,
              const float *gt_boxes /*[sumG,4]*/,
              const int64_t *gt_labels /*[sumG] or NULL*/, const int32_t *gt_off /*[N+1]*/, int N,
+             int64_t gt_total /* sumG; codes need every G_n <= sumG < 2^20, else RN_E_TOOLARGE */,
              float fg_thr, float bg_thr, int64_t *matches /*[N,A] or NULL*/, int32_t *codes /*[N,A] or NULL*/,
              int32_t *fg_count /*[N] or NULL*/, rn_stream_t stream);
 
@@ -108,7 +141,8 @@ int rn_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, cons
             const int32_t *fg_count /*[N]*/, int N, int64_t A, int C, float alpha, float gamma, float beta,
             const float *weights_host /*[4]*/, float batch_div, float *out_image /*[N,3]*/,
             float *out_total /*[4]*/, float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/,
-            void *workspace, size_t workspace_bytes, rn_stream_t stream);
+            void *workspace, size_t workspace_bytes, rn_stream_t stream,
+            const rn_exchange_t *exchange_host /* NULL = single GPU; else out_total is summed over the ranks */);
 
 /* The training half of the path behind ONE call: rn_match (codes + foreground counts) followed by rn_loss and its
  * final reduction on the same stream — same arguments, same outputs (retinanet/losses.py:113-145 with
@@ -119,11 +153,11 @@ int rn_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, cons
 size_t rn_train_loss_workspace_bytes(int N, int64_t A, int C);
 int rn_train_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/, const float *anchors,
                   int64_t anchor_image_stride, const float *gt_boxes /*[sumG,4]*/, const int64_t *gt_labels /*[sumG]*/,
-                  const int32_t *gt_off /*[N+1]*/, int N, int64_t A, int C, float fg_thr, float bg_thr, float alpha,
+                  const int32_t *gt_off /*[N+1]*/, int N, int64_t gt_total, int64_t A, int C, float fg_thr, float bg_thr, float alpha,
                   float gamma, float beta, const float *weights_host /*[4]*/, float batch_div, int32_t *codes /*[N,A]*/,
                   int32_t *fg_count /*[N]*/, float *out_image /*[N,3]*/, float *out_total /*[4]*/,
                   float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/, void *workspace,
-                  size_t workspace_bytes, rn_stream_t stream);
+                  size_t workspace_bytes, rn_stream_t stream, const rn_exchange_t *exchange_host /*or NULL*/);
 
 /* Dense element-wise losses, API parity with RetinaNetLosses.focal_loss (losses.py:29-47, arbitrary
  * float targets of the logits' shape, NO +1 shift) and RetinaNetLosses.smooth_l1_loss (losses.py:19-27).
@@ -185,7 +219,8 @@ int rn_loss_levels(const float *const *cls_levels_host, const float *const *bbox
                    const int32_t *fg_count, int N, int64_t A, int C, float alpha, float gamma, float beta,
                    const float *weights_host, float batch_div, float *out_image /*[N,3]*/, float *out_total /*[4]*/,
                    float *const *grad_cls_levels_host /*or NULL*/, float *const *grad_bbox_levels_host /*or NULL*/,
-                   void *workspace, size_t workspace_bytes, rn_stream_t stream);
+                   void *workspace, size_t workspace_bytes, rn_stream_t stream,
+                   const rn_exchange_t *exchange_host /*or NULL*/);
 size_t rn_postprocess_levels_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
 int rn_postprocess_levels(const float *const *cls_levels_host, const float *const *bbox_levels_host,
                           const int32_t *level_desc_host /*[L][3]*/, int num_levels, const float *anchors,

@@ -65,7 +65,7 @@ class AnchorGenerator(nn.Module):
         self.aspect_ratios = _broadcast_params(aspect_ratios, self.num_features, "aspect_ratios")
         self.offset = offset
         self.cell_anchors = self._calculate_cell_anchors(self.sizes, self.aspect_ratios)
-        self._cache: Dict[Tuple, Tensor] = {}
+        self._cache: Dict[Tuple, Tuple] = {}     # key -> (anchors, ready event, producing stream)
         self.last_level_offsets: List[int] = []   # anchor offsets of the pyramid levels of the last grid
 
     def _calculate_cell_anchors(self, sizes, ratios):
@@ -109,12 +109,22 @@ class AnchorGenerator(nn.Module):
         for (h, w), n in zip(grid_sizes, self.num_anchors):
             offs.append(offs[-1] + h * w * n)
         self.last_level_offsets = offs
-        key = (tuple(grid_sizes), device.index if device.index is not None else torch.cuda.current_device())
+        cells = [b for b in self.cell_anchors]
+        # the key covers everything the grid depends on: a load_state_dict into the cell_anchors buffers bumps their
+        # version counters, strides / offset are compared by value — a stale grid is never served
+        key = (tuple(grid_sizes), device.index if device.index is not None else torch.cuda.current_device(),
+               tuple((c.data_ptr(), c._version, tuple(c.shape)) for c in cells),
+               tuple(int(s) for s in self.strides), float(self.offset))
+        stream = torch.cuda.current_stream(device)
         hit = self._cache.get(key)
         if hit is not None:
-            return hit
+            anchors, ready, made_on = hit
+            if made_on != stream.cuda_stream:                  # first use on another stream: order after the producer
+                stream.wait_event(ready)
+            return anchors
+        if len(self._cache) > 16:
+            self._cache.clear()
         assert len(grid_sizes) == self.num_features, "one feature map per stride expected"
-        cells = [b for b in self.cell_anchors]
         cells_dev = torch.cat([c.to(device=device, dtype=torch.float32) for c in cells]).contiguous()
         desc = []
         total = 0
@@ -127,7 +137,9 @@ class AnchorGenerator(nn.Module):
             rc = lib.rn_anchor_grid(_native.ptr(cells_dev), (ctypes.c_int32 * len(desc))(*desc), len(grid_sizes),
                                     float(self.offset), _native.ptr(out), total, _native.stream_ptr(device))
         _native.check(rc, "rn_anchor_grid")
-        self._cache[key] = out
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        self._cache[key] = (out, ready, stream.cuda_stream)
         return out
 
     def grid_anchors(self, grid_sizes, device) -> List[Tensor]:

@@ -192,7 +192,7 @@ def match_batch(anchors: Tensor, anchor_stride: int, packed: PackedTargets, num_
         rc = lib.rn_match(_native.ptr(anchors, torch.float32, "anchors"), A, anchor_stride,
                           _native.ptr(packed.boxes, torch.float32, "target boxes"),
                           _native.ptr(packed.labels, torch.int64, "target labels") if want_codes else None,
-                          _native.ptr(packed.offsets), N, float(match_thr), float(back_thr),
+                          _native.ptr(packed.offsets), N, packed.total, float(match_thr), float(back_thr),
                           _native.ptr(matches), _native.ptr(codes), _native.ptr(fg), _native.stream_ptr(dev))
     _native.check(rc, "rn_match")
     return matches, codes, fg

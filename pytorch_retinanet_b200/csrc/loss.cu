@@ -226,12 +226,85 @@ __global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : LOSS_MINB) loss_kern
 // fixed tree), the last block to finish (ticket) sums the images in index order.  The summation order
 // depends only on (N, chunks) => bit-reproducible.  `tail` = [N][2] image sums + ticket, after the partials.
 constexpr int FIN_BLOCK = 256;
+
+// Image-sharded multi-GPU exchange folded into the final reduction (include/retinanet_b200.h,
+// rn_exchange_t).  Receive buffer of a rank, in 8-byte words: slot[parity][sender][4] = (seq << 32) | float bits,
+// then the rank's own step counter and error word.  An aligned 8-byte store is single-copy atomic, so a word whose
+// upper half equals the expected sequence number carries a complete value (the LL idea: no flag, no fence).
+// Two parities: a rank can run at most one step ahead of the slowest reader of its previous values.
+constexpr int XCH_SLOT_WORDS = 2 * RN_MAX_PEERS * 4;
+constexpr long long XCH_TIMEOUT_CYCLES = 4000000000LL;         // ~2 s at 1.9 GHz
+struct ExchangeDev {
+    unsigned long long *peers[RN_MAX_PEERS];
+    int rank, world;
+};
+__device__ __forceinline__ void st_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by ALL threads of a block (>= 32 threads) after s_v / s_seq were written and a barrier: thread r stores the
+// local vector into rank r's slots and collects rank r's vector from the local slots; out_total = sum in rank order.
+__device__ __forceinline__ void peer_exchange(const float *s_v, const unsigned seq, float (*s_all)[4],
+                                              float *__restrict__ out_total, const ExchangeDev &X) {
+    const int t = threadIdx.x;
+    if (t < X.world) {                                          // thread t talks to rank t
+        const int par = (int)(seq & 1u);
+        unsigned long long *dst = X.peers[t] + (par * RN_MAX_PEERS + X.rank) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_sys_u64(dst + k, ((unsigned long long)seq << 32) | __float_as_uint(s_v[k]));
+        const unsigned long long *src = X.peers[X.rank] + (par * RN_MAX_PEERS + t) * 4;
+        const long long t0 = clock64();
+        bool ok = true;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long w = 0;
+            while (ok) {
+                w = ld_sys_u64(src + k);
+                if ((unsigned)(w >> 32) == seq) break;
+                if (clock64() - t0 > XCH_TIMEOUT_CYCLES) ok = false;
+            }
+            s_all[t][k] = ok ? __uint_as_float((unsigned)w) : __int_as_float(0x7fc00000);
+        }
+        if (!ok) *((unsigned *)(X.peers[X.rank] + XCH_SLOT_WORDS) + 1) = 1u;    // error word: a peer never arrived
+    }
+    __syncthreads();
+    if (t < 4) {                                                // rank order: the same bits on every rank
+        double acc = 0.0;
+        for (int rk = 0; rk < X.world; ++rk) acc += (double)s_all[rk][t];
+        out_total[t] = (float)acc;
+    }
+}
+
+// The exchange by itself (a rank whose shard is empty launches no loss kernel but must still take part).
+__global__ void __launch_bounds__(32) exchange_kernel(float *__restrict__ total, const __grid_constant__ ExchangeDev X) {
+    __shared__ float s_v[4];
+    __shared__ unsigned s_seq;
+    __shared__ float s_all[RN_MAX_PEERS][4];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_v[k] = total[k];
+        unsigned *seqp = (unsigned *)(X.peers[X.rank] + XCH_SLOT_WORDS);
+        s_seq = *seqp + 1u;
+        *seqp = s_seq;
+    }
+    __syncthreads();
+    peer_exchange(s_v, s_seq, s_all, total, X);
+}
+
 // Called by all FIN_BLOCK threads of a CTA for image n.
 __device__ __forceinline__ void finalize_image(const double *partials, const int *fg_count, const int n, const int N,
                                                const int chunks, const float batch_div, float *__restrict__ out_image,
-                                               float *__restrict__ out_total, double *tail) {
+                                               float *__restrict__ out_total, double *tail, const ExchangeDev &X) {
     __shared__ double s_c[FIN_BLOCK / 32], s_r[FIN_BLOCK / 32];
     __shared__ bool s_last;
+    __shared__ float s_v[4];
+    __shared__ unsigned s_seq;
+    __shared__ float s_all[RN_MAX_PEERS][4];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const double2 *p = (const double2 *)partials + (long long)n * chunks;
     double c = 0.0, r = 0.0;
@@ -264,25 +337,53 @@ __device__ __forceinline__ void finalize_image(const double *partials, const int
         s_last = atomicAdd(ticket, 1u) == (unsigned)(N - 1);
     }
     __syncthreads();
-    if (s_last && t == 0) {
+    if (!s_last) return;                                        // block-uniform
+    if (t == 0) {
         __threadfence();
         double cs = 0.0, rs = 0.0;
         long long fsum = 0;
         const volatile double *vt = tail;
         for (int i = 0; i < N; ++i) { cs += vt[2 * i]; rs += vt[2 * i + 1]; fsum += __ldcg(fg_count + i); }
-        out_total[0] = (float)(cs / (double)batch_div);         // losses.py:138-140
-        out_total[1] = (float)(rs / (double)batch_div);
-        out_total[2] = (float)fsum;                             // sum_n F_n   } carried for the image-sharded
-        out_total[3] = (float)N;                                // local images } all-reduce
+        s_v[0] = (float)(cs / (double)batch_div);               // losses.py:138-140
+        s_v[1] = (float)(rs / (double)batch_div);
+        s_v[2] = (float)fsum;                                   // sum_n F_n   } carried for the image-sharded
+        s_v[3] = (float)N;                                      // local images } exchange
         *ticket = 0u;
+        if (X.world <= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out_total[k] = s_v[k];
+        } else {
+            unsigned *seqp = (unsigned *)(X.peers[X.rank] + XCH_SLOT_WORDS);
+            s_seq = *seqp + 1u;                                 // this rank's step counter (same on every rank)
+            *seqp = s_seq;
+        }
     }
+    if (X.world <= 1) return;
+    __syncthreads();
+    peer_exchange(s_v, s_seq, s_all, out_total, X);
 }
 
 __global__ void __launch_bounds__(FIN_BLOCK) loss_finalize_kernel(const double *__restrict__ partials,
                                                                   const int *__restrict__ fg_count, int N, int chunks,
                                                                   float batch_div, float *__restrict__ out_image,
-                                                                  float *__restrict__ out_total, double *__restrict__ tail) {
-    finalize_image(partials, fg_count, blockIdx.x, N, chunks, batch_div, out_image, out_total, tail);
+                                                                  float *__restrict__ out_total, double *__restrict__ tail,
+                                                                  const __grid_constant__ ExchangeDev X) {
+    finalize_image(partials, fg_count, blockIdx.x, N, chunks, batch_div, out_image, out_total, tail, X);
+}
+
+// host rn_exchange_t -> kernel parameter; returns false on a malformed descriptor
+inline bool make_exchange(const rn_exchange_t *x, ExchangeDev &X) {
+    memset(&X, 0, sizeof(X));
+    X.world = 1;
+    if (!x || x->world <= 1) return true;
+    if (x->world > RN_MAX_PEERS || x->rank < 0 || x->rank >= x->world) return false;
+    for (int r = 0; r < x->world; ++r) {
+        if (!x->peers[r]) return false;
+        X.peers[r] = (unsigned long long *)x->peers[r];
+    }
+    X.rank = x->rank;
+    X.world = x->world;
+    return true;
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(float *__restrict__ buf, long long n, const float *__restrict__ scale) {
@@ -315,6 +416,7 @@ void launch_loss_g(const LossParams &P, dim3 grid, cudaStream_t s, bool precise)
         launch_loss<VEC, WANT_GRAD, false>(P, grid, s, precise);
 }
 
+// (host helpers)
 inline int loss_chunks(int64_t A) { return (int)((A + LOSS_SPAN - 1) / LOSS_SPAN); }
 
 }  // namespace
@@ -323,6 +425,16 @@ extern "C" int rn_loss_set_math_mode(int mode) {
     int old = g_math_mode;
     g_math_mode = mode ? 1 : 0;
     return old;
+}
+
+extern "C" int rn_exchange_total(float *total, const rn_exchange_t *exchange_host, rn_stream_t stream) {
+    RN_CHECK_ARG(total && exchange_host, RN_E_BADARG, "rn_exchange_total: null pointer");
+    ExchangeDev X;
+    RN_CHECK_ARG(make_exchange(exchange_host, X), RN_E_BADARG, "rn_exchange_total: malformed exchange descriptor");
+    if (X.world <= 1) return 0;
+    exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(total, X);
+    RN_CHECK_LAUNCH("rn_exchange_total");
+    return 0;
 }
 
 extern "C" size_t rn_loss_workspace_bytes(int N, int64_t A, int C) {
@@ -336,12 +448,14 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
                        const int32_t *gt_off, const int32_t *codes, const int32_t *fg_count, int N, int64_t A, int C,
                        float alpha, float gamma, float beta, const float *weights_host, float batch_div,
                        float *out_image, float *out_total, float *grad_logits, float *grad_bbox, void *workspace,
-                       size_t workspace_bytes, rn_stream_t stream) {
+                       size_t workspace_bytes, rn_stream_t stream, const rn_exchange_t *exchange_host) {
     RN_CHECK_ARG(logits && bbox && anchors && gt_off && codes && fg_count && out_total && weights_host, RN_E_BADARG,
                  "rn_loss: null pointer");
+    ExchangeDev X;
+    RN_CHECK_ARG(make_exchange(exchange_host, X), RN_E_BADARG, "rn_loss: malformed exchange descriptor");
     RN_CHECK_ARG(N > 0 && A > 0 && C > 0, RN_E_BADARG, "rn_loss: N, A, C must be positive (got %d, %lld, %d)", N,
                  (long long)A, C);
-    RN_CHECK_ARG(C <= 2048, RN_E_TOOLARGE, "rn_loss: C=%d exceeds 2048 classes", C);
+    RN_CHECK_ARG(C <= 2047, RN_E_TOOLARGE, "rn_loss: C=%d exceeds 2047 classes", C);
     RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_loss: N=%d exceeds 65535 images per call", N);
     RN_CHECK_ARG((grad_logits == nullptr) == (grad_bbox == nullptr), RN_E_BADARG,
                  "rn_loss: grad_logits and grad_bbox must be given together");
@@ -372,7 +486,7 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
         cudaError_t e = cudaMemsetAsync(tail + 2 * (size_t)N, 0, sizeof(unsigned), s);
         if (e != cudaSuccess) { rn_set_error("rn_loss: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
         loss_finalize_kernel<<<N, FIN_BLOCK, 0, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
-                                                     out_total, tail);
+                                                     out_total, tail, X);
     }
     RN_CHECK_LAUNCH("rn_loss_finalize");
     return 0;
@@ -388,17 +502,19 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
 extern "C" size_t rn_train_loss_workspace_bytes(int N, int64_t A, int C) { return rn_loss_workspace_bytes(N, A, C); }
 
 extern "C" int rn_train_loss(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
-                             const float *gt_boxes, const int64_t *gt_labels, const int32_t *gt_off, int N, int64_t A, int C,
+                             const float *gt_boxes, const int64_t *gt_labels, const int32_t *gt_off, int N,
+                             int64_t gt_total, int64_t A, int C,
                              float fg_thr, float bg_thr, float alpha, float gamma, float beta, const float *weights_host,
                              float batch_div, int32_t *codes, int32_t *fg_count, float *out_image, float *out_total,
                              float *grad_logits, float *grad_bbox, void *workspace, size_t workspace_bytes,
-                             rn_stream_t stream) {
+                             rn_stream_t stream, const rn_exchange_t *exchange_host) {
     RN_CHECK_ARG(gt_labels && codes && fg_count, RN_E_BADARG, "rn_train_loss: null pointer");
-    int rc = rn_match(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, fg_thr, bg_thr, nullptr, codes,
-                      fg_count, stream);
+    int rc = rn_match(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, nullptr,
+                      codes, fg_count, stream);
     if (rc) return rc;
     return rn_loss(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
-                   weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, workspace_bytes, stream);
+                   weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, workspace_bytes, stream,
+                   exchange_host);
 }
 
 // ---- per-level NCHW layout -----------------------------------------------------------
@@ -640,11 +756,14 @@ extern "C" int rn_loss_levels(const float *const *cls_levels_host, const float *
                               const int32_t *codes, const int32_t *fg_count, int N, int64_t A, int C, float alpha,
                               float gamma, float beta, const float *weights_host, float batch_div, float *out_image,
                               float *out_total, float *const *grad_cls_levels_host, float *const *grad_bbox_levels_host,
-                              void *workspace, size_t workspace_bytes, rn_stream_t stream) {
+                              void *workspace, size_t workspace_bytes, rn_stream_t stream,
+                              const rn_exchange_t *exchange_host) {
+    ExchangeDev X;
+    RN_CHECK_ARG(make_exchange(exchange_host, X), RN_E_BADARG, "rn_loss_levels: malformed exchange descriptor");
     RN_CHECK_ARG(cls_levels_host && bbox_levels_host && level_desc_host && anchors && gt_off && codes && fg_count &&
                      out_total && weights_host, RN_E_BADARG, "rn_loss_levels: null pointer");
     RN_CHECK_ARG(num_levels >= 1 && num_levels <= RN_MAX_LEVELS, RN_E_TOOLARGE, "rn_loss_levels: bad num_levels %d", num_levels);
-    RN_CHECK_ARG(N > 0 && A > 0 && C > 0 && N <= 65535 && C <= 2048, RN_E_BADARG, "rn_loss_levels: bad N/A/C");
+    RN_CHECK_ARG(N > 0 && A > 0 && C > 0 && N <= 65535 && C <= 2047, RN_E_BADARG, "rn_loss_levels: bad N/A/C");
     RN_CHECK_ARG((grad_cls_levels_host == nullptr) == (grad_bbox_levels_host == nullptr), RN_E_BADARG,
                  "rn_loss_levels: gradient level arrays must be given together");
     RN_CHECK_ARG(batch_div > 0.0f, RN_E_BADARG, "rn_loss_levels: batch_div must be positive");
@@ -690,7 +809,7 @@ extern "C" int rn_loss_levels(const float *const *cls_levels_host, const float *
         cudaError_t e = cudaMemsetAsync(tail + 2 * (size_t)N, 0, sizeof(unsigned), s);
         if (e != cudaSuccess) { rn_set_error("rn_loss_levels: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
         loss_finalize_kernel<<<N, FIN_BLOCK, 0, s>>>((const double *)workspace, fg_count, N, chunks, batch_div, out_image,
-                                                     out_total, tail);
+                                                     out_total, tail, X);
     }
     RN_CHECK_LAUNCH("rn_loss_levels/finalize");
     return 0;

@@ -83,14 +83,18 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
 }  // namespace
 
 extern "C" int rn_match(const float *anchors, int64_t A, int64_t anchor_image_stride, const float *gt_boxes, const int64_t *gt_labels,
-                        const int32_t *gt_off, int N, float fg_thr, float bg_thr, int64_t *matches, int32_t *codes,
-                        int32_t *fg_count, rn_stream_t stream) {
+                        const int32_t *gt_off, int N, int64_t gt_total, float fg_thr, float bg_thr, int64_t *matches,
+                        int32_t *codes, int32_t *fg_count, rn_stream_t stream) {
     RN_CHECK_ARG(anchors && gt_off, RN_E_BADARG, "rn_match: null anchors/gt_off");
     RN_CHECK_ARG(A >= 0 && N >= 0, RN_E_BADARG, "rn_match: negative size");
     RN_CHECK_ARG(anchor_image_stride == 0 || anchor_image_stride >= A, RN_E_BADARG, "rn_match: bad anchor_image_stride");
     RN_CHECK_ARG(fg_thr > bg_thr, RN_E_BADARG, "rn_match: match_thr (%g) must exceed back_thr (%g) (box_utils.py:66)",
                  (double)fg_thr, (double)bg_thr);
     RN_CHECK_ARG(!codes || gt_labels, RN_E_BADARG, "rn_match: codes requested without gt_labels");
+    RN_CHECK_ARG(gt_total >= 0, RN_E_BADARG, "rn_match: negative gt_total");
+    // the packed code keeps the GT index in 20 bits: every G_n <= sumG must fit (silent corruption otherwise)
+    RN_CHECK_ARG(!codes || gt_total < (1LL << 20), RN_E_TOOLARGE,
+                 "rn_match: %lld GT boxes in the batch; the packed codes need fewer than 2^20", (long long)gt_total);
     RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_match: N=%d exceeds 65535 images per call", N);
     if (A == 0 || N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;

@@ -177,9 +177,17 @@ __device__ __forceinline__ void match_block(float4 *s_box, float *s_area, const 
     for (int k = 0; k < K; ++k) m[k] = match_decision(best[k], bi[k], G, fg_thr, bg_thr);
 }
 
-// Packed per-anchor target of the loss kernels: -2 / -1 / (g | (label-1) << 20); labels are 1-based (README.md:132).
+// Packed per-anchor target of the loss kernels: -2 / -1 / (g | cls << 20); labels are 1-based (README.md:132), cls =
+// label-1 for labels 1..2047.  Any other label gets cls = 2047, "no class column" (C <= 2047 is enforced by rn_loss):
+// label 0 is the reference's class id 0, whose one-hot row is all zeros after the [:,1:] slice (losses.py:96-103) —
+// the anchor stays foreground (regression term, F count) with all-negative class targets; labels the 11 bits cannot
+// hold no longer corrupt the GT index or alias the -1 / -2 codes.
+constexpr int kNoClass = 2047;
 __device__ __forceinline__ int pack_code(int m, const long long *__restrict__ labels) {
-    return m >= 0 ? (m | (((int)labels[m] - 1) << 20)) : m;
+    if (m < 0) return m;
+    const long long lab = labels[m];
+    const int cls = (lab >= 1 && lab <= (long long)kNoClass) ? (int)lab - 1 : kNoClass;
+    return m | (cls << 20);
 }
 
 }  // namespace rnmatch

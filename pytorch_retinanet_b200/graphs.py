@@ -102,8 +102,10 @@ class HotPathGraph:
     :class:`AnchorGenerator`.  Both may instead be LISTS of the head's raw per-level conv outputs
     ``[N, na*C, H_l, W_l]`` / ``[N, na*4, H_l, W_l]`` (row N1: no permute/cat pass); gradients then come back as lists
     in the same layout.  ``max_targets`` bounds the total number of GT boxes of a batch (static packed
-    buffers).  ``global_batch`` / ``group``: image-sharded multi-GPU use — the loss is divided by the global
-    batch and ``step`` all-reduces the 16-byte loss vector (NCCL), exactly as ``ShardedRetinaNetLosses``.
+    buffers).  ``global_batch`` / ``group`` / ``exchange``: image-sharded multi-GPU use — the loss is divided by the
+    global batch and the 16-byte loss vector is summed over the ranks exactly as in ``ShardedRetinaNetLosses``:
+    inside the captured final reduction kernel over peer-mapped memory (``exchange="peer"``, default — the graph
+    launch is then the whole step), or by one NCCL ``all_reduce`` issued after the graph (``"nccl"``).
     """
 
     def __init__(self, num_classes: int, cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor,
@@ -115,7 +117,7 @@ class HotPathGraph:
                  alpha: float = FOCAL_LOSS_ALPHA, gamma: float = FOCAL_LOSS_GAMMA, beta: float = SMOOTH_L1_LOSS_BETA,
                  match_thr: float = IOU_THRESHOLDS_FOREGROUND, back_thr: float = IOU_THRESHOLDS_BACKGROUND,
                  cand_capacity: Optional[int] = None, concurrent: bool = True, pre_nms_topk: Optional[int] = None,
-                 level_offsets: Optional[Sequence[int]] = None):
+                 level_offsets: Optional[Sequence[int]] = None, exchange="peer"):
         if not (train or detect):
             raise ValueError("HotPathGraph: nothing to do (train=False, detect=False)")
         lib = _native.load()
@@ -165,12 +167,19 @@ class HotPathGraph:
             raise ValueError("pre_nms_topk needs A*C < 2^32")
         self.group = group
         self.world = 1
+        self._xch = None
         if global_batch is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            if self.world > 1 and train:
+                from .distributed import PeerExchange, get_exchange
+                self._xch = exchange if isinstance(exchange, PeerExchange) else get_exchange(group, exchange)
+        self._xref = None if self._xch is None else self._xch.ref
         self.batch_div = float(global_batch if global_batch is not None else N)
         self.hp = (float(alpha), float(gamma), float(beta), float(match_thr), float(back_thr))
         self.max_targets = int(max_targets)
+        if train and self.max_targets >= (1 << 20):
+            raise ValueError("max_targets must stay below 2^20 (GT index field of the packed match codes)")
 
         f32, i32, i64 = torch.float32, torch.int32, torch.int64
         if train:
@@ -226,15 +235,16 @@ class HotPathGraph:
                                     self.anchor_stride, self.gt_boxes.data_ptr(), self.gt_off.data_ptr(), self.codes.data_ptr(),
                                     self.fg.data_ptr(), N, A, C, alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div,
                                     self.per_image.data_ptr(), self.total.data_ptr(), self._gcls_ptrs, self._gbox_ptrs,
-                                    self._loss_ws.data_ptr(), self._loss_ws_bytes, _native.stream_ptr(self.dev))
+                                    self._loss_ws.data_ptr(), self._loss_ws_bytes, _native.stream_ptr(self.dev), self._xref)
             _native.check(rc, "rn_loss_levels")
             return
         rc = lib.rn_train_loss(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(), self.anchor_stride,
-                               self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(), self.gt_off.data_ptr(), N, A, C, match_thr,
+                               self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(), self.gt_off.data_ptr(), N,
+                               self.max_targets, A, C, match_thr,
                                back_thr, alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div, self.codes.data_ptr(),
                                self.fg.data_ptr(), self.per_image.data_ptr(), self.total.data_ptr(),
                                self.grad_cls_preds.data_ptr(), self.grad_bbox_preds.data_ptr(), self._loss_ws.data_ptr(),
-                               self._loss_ws_bytes, _native.stream_ptr(self.dev))
+                               self._loss_ws_bytes, _native.stream_ptr(self.dev), self._xref)
         _native.check(rc, "rn_train_loss")
 
     def _enqueue_match(self):
@@ -242,11 +252,13 @@ class HotPathGraph:
         match_thr, back_thr = self.hp[3], self.hp[4]
         s = _native.stream_ptr(self.dev)
         rc = lib.rn_match(self.anchors.data_ptr(), A, self.anchor_stride, self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(),
-                          self.gt_off.data_ptr(), N, match_thr, back_thr, None, self.codes.data_ptr(), self.fg.data_ptr(), s)
+                          self.gt_off.data_ptr(), N, self.max_targets, match_thr, back_thr, None, self.codes.data_ptr(),
+                          self.fg.data_ptr(), s)
         _native.check(rc, "rn_match")
 
     def _enqueue_loss(self, want_grad: bool = True):
-        """rn_loss alone on the codes of the last step (bench.py times the streaming kernel by itself with it)."""
+        """rn_loss alone on the codes of the last step (bench.py times the streaming kernel by itself with it; no
+        exchange — a timing aid must not desynchronise the ranks' step counters)."""
         lib, N, A, C = self.lib, self.N, self.A, self.C
         alpha, gamma, beta = self.hp[:3]
         s = _native.stream_ptr(self.dev)
@@ -255,7 +267,7 @@ class HotPathGraph:
                          alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div, self.per_image.data_ptr(), self.total.data_ptr(),
                          self.grad_cls_preds.data_ptr() if want_grad else None,
                          self.grad_bbox_preds.data_ptr() if want_grad else None, self._loss_ws.data_ptr(),
-                         self._loss_ws_bytes, s)
+                         self._loss_ws_bytes, s, None)
         _native.check(rc, "rn_loss")
 
     def _enqueue_detect(self):
@@ -359,9 +371,9 @@ class HotPathGraph:
         if self.train and targets is not None:
             self.load_targets(targets)
         self.graph.replay()
-        if self.train and self.world > 1:
+        if self.train and self.world > 1 and self._xch is None:
             import torch.distributed as dist
-            dist.all_reduce(self.total, group=self.group)       # the one collective of the path: 16 bytes
+            dist.all_reduce(self.total, group=self.group)       # exchange="nccl": one 16-byte all-reduce after the graph
         ev = None
         if self.detect:
             self._host.copy_(self.meta, non_blocking=True)      # the single D2H copy of the path

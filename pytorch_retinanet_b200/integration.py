@@ -47,11 +47,15 @@ def patch_retinanet(model, pre_nms_topk=None, fuse_head_layout=False, fold_box_r
     old = model.anchor_generator
     new = AnchorGenerator(sizes=getattr(old, "sizes", None), aspect_ratios=getattr(old, "aspect_ratios", None),
                           strides=getattr(old, "strides", None), offset=getattr(old, "offset", None))
-    try:
-        dev = next(iter(old.cell_anchors)).device
-        new = new.to(dev)
-    except StopIteration:
-        pass
+    old_cells = list(getattr(old, "cell_anchors", []))
+    if old_cells:
+        # carry the existing buffers over (a custom generator / a loaded checkpoint may hold values that the
+        # constructor arguments do not reproduce); same names, same order -> identical state_dict entries
+        if len(old_cells) != len(list(new.cell_anchors)):
+            raise ValueError(f"anchor generator holds {len(old_cells)} cell-anchor tables for {new.num_features} strides")
+        from .anchors import BufferList
+        new.cell_anchors = BufferList([c.detach().clone().float() for c in old_cells])
+        new = new.to(old_cells[0].device)
     model.anchor_generator = new
     model.retinanet_head.losses = RetinaNetLosses(model.num_classes)
     model.process_detections = types.MethodType(process_detections, model)

@@ -35,8 +35,10 @@ def _shared_anchors(anchors: Sequence[Tensor]) -> Tuple[Tensor, int]:
 
 def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
                        packed: PackedTargets, alpha: float, gamma: float, beta: float, match_thr: float,
-                       back_thr: float, batch_div: float, want_grad: bool):
-    """One C call (rn_train_loss): matcher, then loss + gradients + final reduction.  Returns (out_total [4], out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
+                       back_thr: float, batch_div: float, want_grad: bool, exchange=None):
+    """One C call (rn_train_loss): matcher, then loss + gradients + final reduction (+ the peer-memory exchange of the
+    16-byte loss vector when ``exchange`` is a :class:`distributed.PeerExchange`).  Returns (out_total [4],
+    out_image [N,3], grad_logits|None, grad_bbox|None, codes)."""
     lib = _native.load()
     dev = cls_preds.device
     N, A, C = cls_preds.shape
@@ -62,15 +64,30 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
                                _native.ptr(anchors, torch.float32, "anchors"), anchor_stride,
                                _native.ptr(packed.boxes, torch.float32, "target boxes"),
                                _native.ptr(packed.labels, torch.int64, "target labels"), _native.ptr(packed.offsets),
-                               N, A, C, float(match_thr), float(back_thr), float(alpha), float(gamma), float(beta),
-                               _REG_WEIGHTS_C, float(batch_div), _native.ptr(codes), _native.ptr(fg),
+                               N, packed.total, A, C, float(match_thr), float(back_thr), float(alpha), float(gamma),
+                               float(beta), _REG_WEIGHTS_C, float(batch_div), _native.ptr(codes), _native.ptr(fg),
                                _native.ptr(out_image), _native.ptr(out_total), _native.ptr(gl), _native.ptr(gb),
-                               _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+                               _native.ptr(ws), ws_bytes, _native.stream_ptr(dev),
+                               None if exchange is None else exchange.ref)
     _native.check(rc, "rn_train_loss")
     return out_total, out_image, gl, gb, codes
 
 
+def _scale_in_place(buf: Tensor, g: Tensor) -> None:
+    """buf *= g (device scalar) with one launch whose blocks exit at once when g == 1 (the usual case)."""
+    gs = g.detach().to(device=buf.device, dtype=torch.float32).contiguous()
+    with _native.on_device(buf.device):
+        rc = _native.load().rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
+                                                      _native.stream_ptr(buf.device))
+    _native.check(rc, "rn_scale_by_device_scalar")
+
+
 class _FusedRetinaNetLoss(torch.autograd.Function):
+    """The gradient buffers written by the forward kernel are handed to autograd by ``backward`` (scaled in place, no
+    copy of the 1 GB tensors).  A buffer that an earlier ``backward`` already gave away (``retain_graph=True`` followed
+    by a second backward, or the two losses back-propagated one after the other) is recomputed from the saved inputs
+    with one more pass of the forward kernel, so every autograd usage the reference supports gives the same numbers."""
+
     @staticmethod
     def forward(ctx, cls_preds, bbox_preds, anchors, anchor_stride, packed, hp):
         want = cls_preds.requires_grad or bbox_preds.requires_grad
@@ -82,37 +99,63 @@ class _FusedRetinaNetLoss(torch.autograd.Function):
         else:
             total, image, gl, gb, _ = fused_loss_forward(cls_preds, bbox_preds, anchors, anchor_stride, packed,
                                                          hp["alpha"], hp["gamma"], hp["beta"], hp["match_thr"],
-                                                         hp["back_thr"], hp["batch_div"], want)
-        group = hp.get("all_reduce_group", False)
-        if group is not False:
-            # image-sharded batch: the ONE collective of the path — 16 bytes over NCCL/NVLink.  The local
-            # gradients are already scaled by 1/N_global, so backward needs no communication.
-            import torch.distributed as dist
-            dist.all_reduce(total, group=group)
+                                                         hp["back_thr"], hp["batch_div"], want, hp.get("exchange"))
+        total = _exchange_total(total, hp, in_kernel=cls_preds.shape[0] > 0)
+        ctx.set_materialize_grads(False)          # a loss that is not back-propagated arrives as None, not as zeros
         ctx.grads = (gl, gb)
         ctx.in_dtypes = (cls_preds.dtype, bbox_preds.dtype)
+        if want:
+            ctx.save_for_backward(cls_preds, bbox_preds)
+            ctx.recompute = (anchors, anchor_stride, packed, hp)
         ctx.mark_non_differentiable(image, total)
         return total[0], total[1], image, total
 
     @staticmethod
     def backward(ctx, g_cls, g_reg, _g_image, _g_total):
-        gl, gb = ctx.grads
-        ctx.grads = (None, None)
-        if gl is None:
+        need = (g_cls is not None and ctx.needs_input_grad[0], g_reg is not None and ctx.needs_input_grad[1])
+        if not any(need):
             return None, None, None, None, None, None
-        lib = _native.load()
+        bufs = list(ctx.grads)
+        if any(n and b is None for n, b in zip(need, bufs)):
+            cls_preds, bbox_preds = ctx.saved_tensors
+            anchors, anchor_stride, packed, hp = ctx.recompute
+            if cls_preds.shape[0] == 0:
+                fresh = (torch.zeros_like(cls_preds, dtype=torch.float32), torch.zeros_like(bbox_preds, dtype=torch.float32))
+            else:
+                fresh = fused_loss_forward(cls_preds, bbox_preds, anchors, anchor_stride, packed, hp["alpha"], hp["gamma"],
+                                           hp["beta"], hp["match_thr"], hp["back_thr"], hp["batch_div"], True)[2:4]
+            bufs = [b if b is not None else f for b, f in zip(bufs, fresh)]
         outs = []
-        for buf, g, dt in ((gl, g_cls, ctx.in_dtypes[0]), (gb, g_reg, ctx.in_dtypes[1])):
-            if g is None:
+        for i, g in enumerate((g_cls, g_reg)):
+            if not need[i]:
                 outs.append(None)
                 continue
-            gs = g.detach().to(device=buf.device, dtype=torch.float32).contiguous()
-            with _native.on_device(buf.device):
-                rc = lib.rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
-                                                   _native.stream_ptr(buf.device))
-            _native.check(rc, "rn_scale_by_device_scalar")
-            outs.append(buf if dt == torch.float32 else buf.to(dt))
+            buf, bufs[i] = bufs[i], None              # handed over: autograd may take the tensor without a copy
+            _scale_in_place(buf, g)
+            outs.append(buf if ctx.in_dtypes[i] == torch.float32 else buf.to(ctx.in_dtypes[i]))
+        ctx.grads = tuple(bufs)
         return outs[0], outs[1], None, None, None, None
+
+
+def _exchange_total(total: Tensor, hp: dict, in_kernel: bool = True) -> Tensor:
+    """Image-sharded batch: the ONE exchange of the path — the sum over the ranks of the 16-byte vector
+    [cls, reg, sum F, N_local].  With ``hp["exchange"]`` (a :class:`distributed.PeerExchange`) the loss's final
+    reduction kernel already did it over peer memory (``in_kernel``; an empty shard, which launches no kernel, joins
+    through :meth:`PeerExchange.exchange`); with ``hp["all_reduce_group"]`` it is one ``all_reduce`` (NCCL, or gloo in
+    the CPU tests).  The local gradients are already scaled by 1/N_global, so backward needs no communication."""
+    x = hp.get("exchange")
+    if x is not None:
+        if not in_kernel:
+            x.exchange(total)
+    else:
+        group = hp.get("all_reduce_group", False)
+        if group is not False:
+            import torch.distributed as dist
+            dist.all_reduce(total, group=group)
+    scale = hp.get("total_scale", 1.0)
+    if scale != 1.0:
+        total[:2] *= scale
+    return total
 
 
 def _level_desc(cls_levels: Sequence[Tensor], box_levels: Sequence[Tensor], C: int):
@@ -145,7 +188,7 @@ def _f32_contig(t: Tensor) -> Tensor:
 
 
 def fused_loss_forward_levels(cls_levels, box_levels, anchors: Tensor, anchor_stride: int, packed: PackedTargets, C: int,
-                              alpha, gamma, beta, match_thr, back_thr, batch_div, want_grad: bool):
+                              alpha, gamma, beta, match_thr, back_thr, batch_div, want_grad: bool, exchange=None):
     """rn_match + rn_loss_levels on the RAW per-level conv outputs: no permute/cat pass."""
     lib = _native.load()
     xs, bs = [_f32_contig(t) for t in cls_levels], [_f32_contig(t) for t in box_levels]
@@ -169,13 +212,15 @@ def fused_loss_forward_levels(cls_levels, box_levels, anchors: Tensor, anchor_st
                                 _native.ptr(fg), N, A, C, float(alpha), float(gamma), float(beta), _REG_WEIGHTS_C,
                                 float(batch_div), _native.ptr(out_image), _native.ptr(out_total),
                                 _ptr_array(gxs) if want_grad else None, _ptr_array(gbs) if want_grad else None,
-                                _native.ptr(ws), ws_bytes, _native.stream_ptr(dev))
+                                _native.ptr(ws), ws_bytes, _native.stream_ptr(dev),
+                                None if exchange is None else exchange.ref)
     _native.check(rc, "rn_loss_levels")
     return out_total, out_image, gxs, gbs
 
 
 class _FusedRetinaNetLossLevels(torch.autograd.Function):
-    """inputs: anchors, anchor_stride, packed, hp, C, L, then L class-level tensors and L box-level tensors."""
+    """inputs: anchors, anchor_stride, packed, hp, C, L, then L class-level tensors and L box-level tensors.
+    Gradient buffers are handed over / recomputed exactly as in :class:`_FusedRetinaNetLoss`."""
 
     @staticmethod
     def forward(ctx, anchors, anchor_stride, packed, hp, C, L, *levels):
@@ -183,37 +228,43 @@ class _FusedRetinaNetLossLevels(torch.autograd.Function):
         want = any(t.requires_grad for t in levels)
         total, image, gxs, gbs = fused_loss_forward_levels(cls_levels, box_levels, anchors, anchor_stride, packed, C,
                                                            hp["alpha"], hp["gamma"], hp["beta"], hp["match_thr"],
-                                                           hp["back_thr"], hp["batch_div"], want)
-        group = hp.get("all_reduce_group", False)
-        if group is not False:
-            import torch.distributed as dist
-            dist.all_reduce(total, group=group)
+                                                           hp["back_thr"], hp["batch_div"], want, hp.get("exchange"))
+        total = _exchange_total(total, hp)
+        ctx.set_materialize_grads(False)
         ctx.grads = (gxs, gbs)
         ctx.L = L
         ctx.in_dtypes = [t.dtype for t in levels]
+        if want:
+            ctx.save_for_backward(*levels)
+            ctx.recompute = (anchors, anchor_stride, packed, hp, C)
         ctx.mark_non_differentiable(image, total)
         return total[0], total[1], image, total
 
     @staticmethod
     def backward(ctx, g_cls, g_reg, _g_image, _g_total):
-        gxs, gbs = ctx.grads
-        ctx.grads = (None, None)
         L = ctx.L
-        if gxs is None:
+        need = (g_cls is not None and any(ctx.needs_input_grad[6:6 + L]),
+                g_reg is not None and any(ctx.needs_input_grad[6 + L:6 + 2 * L]))
+        if not any(need):
             return (None,) * (6 + 2 * L)
-        lib = _native.load()
+        bufs = list(ctx.grads)
+        if any(n and b is None for n, b in zip(need, bufs)):
+            levels = ctx.saved_tensors
+            anchors, anchor_stride, packed, hp, C = ctx.recompute
+            fresh = fused_loss_forward_levels(levels[:L], levels[L:], anchors, anchor_stride, packed, C, hp["alpha"],
+                                              hp["gamma"], hp["beta"], hp["match_thr"], hp["back_thr"], hp["batch_div"],
+                                              True)[2:4]
+            bufs = [b if b is not None else f for b, f in zip(bufs, fresh)]
         outs = []
-        for bufs, g in ((gxs, g_cls), (gbs, g_reg)):
-            gs = None if g is None else g.detach().to(device=bufs[0].device, dtype=torch.float32).contiguous()
-            for buf in bufs:
-                if gs is None:
-                    outs.append(None)
-                    continue
-                with _native.on_device(buf.device):
-                    rc = lib.rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
-                                                       _native.stream_ptr(buf.device))
-                _native.check(rc, "rn_scale_by_device_scalar")
-                outs.append(buf)
+        for i, g in enumerate((g_cls, g_reg)):
+            if not need[i]:
+                outs.extend([None] * L)
+                continue
+            mine, bufs[i] = bufs[i], None
+            for buf in mine:
+                _scale_in_place(buf, g)
+            outs.extend(mine)
+        ctx.grads = tuple(bufs)
         outs = [o if (o is None or dt == torch.float32) else o.to(dt) for o, dt in zip(outs, ctx.in_dtypes)]
         return (None,) * 6 + tuple(outs)
 

@@ -156,7 +156,7 @@ def test_train_loss_call_equals_match_then_loss(P, case):
         rc = lib.rn_loss(x.data_ptr(), bb.data_ptr(), anc.data_ptr(), 0, packed.boxes.data_ptr(), packed.offsets.data_ptr(),
                          codes.data_ptr(), fg.data_ptr(), N, A, C, 0.25, gamma, 0.1, _REG_WEIGHTS_C, float(n_img), image.data_ptr(),
                          total.data_ptr(), None if gl is None else gl.data_ptr(), None if gb is None else gb.data_ptr(),
-                         ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream)
+                         ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream, None)
         _native.check(rc, "rn_loss")
         return total, image, gl, gb, codes
 

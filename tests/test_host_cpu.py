@@ -23,10 +23,19 @@ def test_abi_exports_every_declared_symbol():
     raw = ctypes.CDLL(_native.lib_path())
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.rn_abi_version() == 1
+    assert lib.rn_abi_version() == _native.header_abi_version() == 2
     # argument errors are reported through return codes + rn_last_error (no GPU touched)
-    assert lib.rn_match(None, 10, 0, None, None, None, 1, 0.5, 0.4, None, None, None, None) == -1
+    assert lib.rn_match(None, 10, 0, None, None, None, 1, 0, 0.5, 0.4, None, None, None, None) == -1
     assert b"null" in lib.rn_last_error()
+    # the packed match codes keep the GT index in 20 bits: too many boxes is an error, not silent corruption
+    one = ctypes.c_void_p(16)                               # never dereferenced: the size check comes first
+    assert lib.rn_match(one, 10, 0, one, one, one, 1, 1 << 20, 0.5, 0.4, None, one, one, None) == -2
+    assert b"2^20" in lib.rn_last_error()
+    assert lib.rn_match(one, 10, 0, one, None, one, 1, 1 << 20, 0.3, 0.4, one, None, None, None) == -1   # box_utils.py:66
+    bad = _native.RnExchange()
+    bad.rank, bad.world = 3, 2
+    assert lib.rn_exchange_total(one, ctypes.byref(bad), None) == -1
+    assert lib.rn_comm_bytes() == 2048
     assert lib.rn_postprocess_workspace_bytes(16, 201600, 80, 1 << 20, 100) > (1 << 20) * 8
     assert lib.rn_loss_workspace_bytes(16, 201600, 80) == (16 * 788 * 2 + 16 * 2 + 2) * 8
 
