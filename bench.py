@@ -10,15 +10,18 @@ One "step" = one pass of the whole hot path over one batch of synthetic COCO-sha
   matcher + focal + smooth-L1 loss with gradients (rn_train_loss) and post-processing (sigmoid/threshold/decode/
   clip/NMS/top-100, rn_postprocess) of the same batch.  `value` runs it as HotPathGraph.step (one CUDA graph, double
   buffered); `api.*` holds the same step through the drop-in calls (RetinaNetLosses.forward + backward +
-  process_detections) and the unpipelined graph.
-N > 1: every rank owns its own 16 images (weak scaling; 8 GPUs = configs[2], batch 128) and the
-ranks exchange one 16-byte all-reduce per step.
+  process_detections) and the unpipelined graph; `e2e` is the same graph step fed from pinned HOST buffers.
+N > 1: every rank owns its own 16 images (weak scaling; 8 GPUs = configs[2], batch 128); the ranks' 16-byte loss
+vectors are summed inside the loss's final reduction kernel over peer-mapped memory (NVLink).
+`extra.configs` adds the other BASELINE configs at their stated sizes (config 3: global batch 128 split over the
+ranks; config 4: batch 256 inference with and without the top-k extension; config 5: batch 64, 500 GT/img).
 
-Prints ONE JSON line (see README / DESIGN.md for the keys).  `--impl reference` times the
-reference's own CPU implementation of the same step (the torch oracle port, all host threads) on a
-bounded sample of the same workload.
+Prints ONE JSON line (see README / DESIGN.md for the keys).  `--impl reference` times the UNMODIFIED reference's
+own CPU implementation of the same step (baseline/_ref; the oracle port only if no reference tree is reachable) on
+all host threads, every step a bounded sample of the same workload.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -109,72 +112,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(batch, n_images, backward=True):
-    """The reference's path on CPU for `n_images` images of `batch` (oracle port of losses.py:113-145
-    and models.py:160-243; NMS through torchvision.ops.nms like the reference)."""
-    from oracle import torch_oracle as O
-    try:
-        import torchvision
-        nms_fn = torchvision.ops.nms
-    except Exception:
-        nms_fn = None
-    cfg = batch["config"]
-    anc = batch["anchors"]
-    x = batch["cls_preds"][:n_images].clone().requires_grad_(backward)
-    b = batch["bbox_preds"][:n_images].clone().requires_grad_(backward)
-    anchors = [O.image_anchors(O.fpn_grid_sizes(*cfg.padded_hw)) for _ in range(n_images)]   # anchors.py:223-226
-    out = O.batch_loss(batch["targets"][:n_images], x, b, anchors, cfg.num_classes)
-    if backward:
-        (out["classification_loss"] + out["regression_loss"]).backward()
-    dets = O.postprocess(x.detach(), b.detach(), anchors, batch["im_szs"][:n_images], nms_fn=nms_fn)
-    assert anc.shape == anchors[0].shape
-    return out, dets
-
-
-def time_cpu_reference(batch, n_images, repeats=1):
-    torch.set_num_threads(os.cpu_count() or 1)
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        cpu_reference_step(batch, n_images)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_images / best, best
-
-
-# ------------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    torch.set_num_threads(os.cpu_count() or 1)              # every host thread the box has
-    cfg = S.CONFIGS[WORKLOAD_CFG]
-    sample = cfg.batch                                      # the whole 16-image batch of the workload: ~3 s per step
-    batch = S.make_batch(cfg, 0, sample)
-    for _ in range(args.warmup_ref):
-        cpu_reference_step(batch, 2)
-    times = []
-    for _ in range(args.steps_ref):
-        t0 = time.perf_counter()
-        cpu_reference_step(batch, sample)
-        times.append(time.perf_counter() - t0)
-    ms = 1000.0 * sum(times) / len(times)
-    value = sample / (ms / 1000.0)
-    cores = torch.get_num_threads()
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world),
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} images of configs[1] per step (reference cost is linear in images: "
-                                   f"python loop per image), torch CPU eager, {cores} threads, os.cpu_count={os.cpu_count()}"},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    _emit(line)
-
-
 def workload_config(world):
+    """The `config` object — identical in both arms (the driver compares them)."""
     cfg = S.CONFIGS[WORKLOAD_CFG]
     return {"workload": "BASELINE.json configs[1]: COCO-shaped 800x1333 (padded 800x1344), 80 classes, 9 anchors/loc "
                         "P3-P7 (A=201600), batch 16 per GPU, <=100 GT/img; step = loss fwd+bwd + post-process",
@@ -184,17 +123,154 @@ def workload_config(world):
             "logits": "clustered N(-7,1.3^2) + N(5,1.5^2) on matched anchors (SURVEY.md 8d)"}
 
 
+# ---- the reference's path, on whatever device the tensors live ------------------------------------------------------
+def load_reference_or_port():
+    """(kind, step function).  kind "reference" = the unmodified reference package driven through its own API
+    (baseline/reference.py); "port" = the op-for-op oracle port, used only when no reference tree is reachable."""
+    try:
+        from baseline.reference import load_reference, reference_root, reference_step
+        ref = load_reference()
+        load_reference_or_port.where = os.path.relpath(reference_root(), ROOT) if reference_root().startswith(ROOT) else reference_root()
+
+        def step(batch, n_images, backward=True, device=None):
+            cfg = batch["config"]
+            x, b, tg = batch["cls_preds"][:n_images], batch["bbox_preds"][:n_images], batch["targets"][:n_images]
+            if device is not None:
+                x, b = x.to(device), b.to(device)
+                tg = [{k: v.to(device) for k, v in t.items()} for t in tg]
+            return reference_step(ref, x, b, tg, cfg.padded_hw, batch["im_szs"][:n_images], cfg.num_classes, backward)
+        return "reference", step
+    except Exception as e:                                   # no reference tree on this machine
+        sys.stderr.write(f"bench: reference tree unavailable ({e}); using the oracle port\n")
+        from oracle import torch_oracle as O
+        try:
+            import torchvision
+            nms_fn = torchvision.ops.nms
+        except Exception:
+            nms_fn = None
+
+        def step(batch, n_images, backward=True, device=None):
+            cfg = batch["config"]
+            dev = torch.device("cpu") if device is None else device
+            x = batch["cls_preds"][:n_images].to(dev).clone().requires_grad_(backward)
+            b = batch["bbox_preds"][:n_images].to(dev).clone().requires_grad_(backward)
+            tg = [{k: v.to(dev) for k, v in t.items()} for t in batch["targets"][:n_images]]
+            anchors = [O.image_anchors(O.fpn_grid_sizes(*cfg.padded_hw), device=dev) for _ in range(n_images)]   # anchors.py:223-226
+            out = O.batch_loss(tg, x, b, anchors, cfg.num_classes)
+            if backward:
+                (out["classification_loss"] + out["regression_loss"]).backward()
+            dets = O.postprocess(x.detach(), b.detach(), anchors, batch["im_szs"][:n_images], nms_fn=nms_fn)
+            return out, dets
+        return "port", step
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: rank 0 alone times the reference's CPU path on all host threads, K steps after W warm-ups,
+    each step a bounded sample of the workload's batch sized so that the whole run ends within a few minutes."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)              # every host thread the box has
+    cfg = S.CONFIGS[WORKLOAD_CFG]
+    kind, step = load_reference_or_port()
+    batch = S.make_batch(cfg, 0, cfg.batch)
+    step(batch, 1)                                          # untimed: first-touch / thread-pool start-up
+    t0 = time.perf_counter()
+    step(batch, 2)
+    t_img = (time.perf_counter() - t0) / 2
+    budget_s = 150.0
+    sample = int(max(1, min(cfg.batch, budget_s / ((args.steps + args.warmup) * t_img))))
+    for _ in range(args.warmup):
+        step(batch, sample)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step(batch, sample)
+        times.append(time.perf_counter() - t0)
+    ms = 1000.0 * sum(times) / len(times)
+    value = sample / (ms / 1000.0)
+    cores = torch.get_num_threads()
+    what = (f"the unmodified reference ({load_reference_or_port.where}: AnchorGenerator.forward, RetinaNetLosses.forward + "
+            "backward, Retinanet.process_detections)" if kind == "reference" else "torch CPU eager port of the reference (oracle/torch_oracle.py)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} of the batch's {cfg.batch} images per step (reference cost is linear in images: "
+                                   f"python loop per image, losses.py:126, models.py:181), {what}, torch CPU eager, "
+                                   f"{cores} threads, os.cpu_count={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    _emit(line)
+
+
+# ---- rank placement (e2e ingest): cores and host memory next to the rank's GPU --------------------------------------
+def _parse_cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def place_rank(local_rank, local_world):
+    """Pins this process to cores of the NUMA node its GPU hangs off (a disjoint slice per rank) and prefers that
+    node for host allocations made from now on (the pinned staging buffers).  Best effort; returns what was done."""
+    info = {"numa_node": None, "cpus": None, "mempolicy": None}
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        info["pci"] = bus
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+    except Exception as e:
+        info["error"] = f"numa node of the GPU unknown: {e}"
+        node = -1
+    info["numa_node"] = node
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = allowed
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                near = [c for c in _parse_cpulist(f.read()) if c in set(allowed)]
+            if near:
+                cpus = near
+        k = max(1, len(cpus) // max(1, local_world))
+        mine = cpus[(local_rank * k) % len(cpus):][:k] or cpus
+        os.sched_setaffinity(0, mine)
+        info["cpus"] = f"{mine[0]}-{mine[-1]} ({len(mine)} of {len(allowed)} allowed)"
+    except Exception as e:
+        info["error"] = f"affinity: {e}"
+    if node >= 0:
+        try:                                                # set_mempolicy(MPOL_PREFERRED, {node})
+            mask = ctypes.c_ulong(1 << node)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy errno %d" % ctypes.get_errno()
+        except Exception as e:
+            info["mempolicy"] = f"unavailable: {e}"
+    return info
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import pytorch_retinanet_b200 as P
     from pytorch_retinanet_b200 import _native
+    from pytorch_retinanet_b200.box_utils import PackedTargets
     from pytorch_retinanet_b200.detections import postprocess_batch
-    from pytorch_retinanet_b200.distributed import ShardedRetinaNetLosses
+    from pytorch_retinanet_b200.distributed import ShardedRetinaNetLosses, close_exchanges, get_exchange
+    from pytorch_retinanet_b200.graphs import HotPathGraph
+    from pytorch_retinanet_b200.losses import fused_loss_forward
     from types import SimpleNamespace
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    placement = place_rank(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     lib = _native.load()
+    peak, peak_src = measured_peak_gbs()
     cfg = S.CONFIGS[WORKLOAD_CFG]
     n_img = cfg.batch
     first = rank * n_img                                   # per-image seeds are global image indices
@@ -206,10 +282,15 @@ def run_ours(args, rank, world, local_rank):
     gen = P.AnchorGenerator().to(dev)
     fmaps = [torch.empty((n_img, 1, h, w), device=dev) for h, w in S.grid_sizes(cfg.padded_hw)]
     images = SimpleNamespace(image_sizes=batch["im_szs"])
-    losses = ShardedRetinaNetLosses(C, global_batch=n_img * world)
-    if os.environ.get("RN_BENCH_NO_ALLREDUCE"):             # DIAGNOSTIC ONLY (not a valid bench line): isolates the
-        losses = P.RetinaNetLosses(C)                       # cost of the per-step collective at N > 1
-    stub =SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
+    exchange_mode = os.environ.get("RN_BENCH_EXCHANGE", "auto")       # auto = in-kernel peer exchange, NCCL if unavailable
+    xch = get_exchange(None, exchange_mode) if world > 1 else None
+    exchange_used = "none (1 GPU)" if world == 1 else ("peer memory, inside the loss's final reduction kernel" if xch is not None
+                                                       else "NCCL all_reduce after the graph")
+    losses = ShardedRetinaNetLosses(C, global_batch=n_img * world, exchange=xch if xch is not None else "nccl")
+    if os.environ.get("RN_BENCH_NO_EXCHANGE"):              # DIAGNOSTIC ONLY (not a valid bench line): isolates the
+        losses = P.RetinaNetLosses(C)                       # cost of the per-step exchange at N > 1
+        exchange_used = "DISABLED (diagnostic run, losses are per-rank)"
+    stub = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100)
 
     def step(cls, box):
         # Both halves of the path on the same batch, through the drop-in API.  The inference half goes first:
@@ -242,22 +323,30 @@ def run_ours(args, rank, world, local_rank):
             ms = float(t.item())
         return ms / steps
 
+    # ---- multi-GPU parity, where the driver can see it: the sharded step (graph + in-kernel exchange, and the drop-in
+    # ShardedRetinaNetLosses) on 2 small images per rank against the CPU oracle on the whole 2*world-image batch ----
+    parity = parity_check(P, HotPathGraph, ShardedRetinaNetLosses, xch, rank, world, dev, dist)
+    if not parity["ok"]:
+        if rank == 0:
+            sys.stderr.write("bench: multi-GPU parity check FAILED: %s\n" % json.dumps(parity))
+        raise SystemExit(3)
+
     # ---- device-resident throughput: the step as ONE CUDA graph (same C-ABI calls, two concurrent branches).
     # Two graphs on two input buffers alternate (double buffering): step i+1 is launched, then the losses, gradients
     # and detections of step i are read — every step's results are consumed, one step late, so the host work of a
     # step (GT packing, graph launch, count copy, slicing) overlaps with the GPU work of the other buffer. ----
-    from pytorch_retinanet_b200.graphs import HotPathGraph
     gsum_max = sum(int(t["boxes"].shape[0]) for t in targets)
     gb = (n_img * world) if world > 1 else None
     anc0 = gen(images, fmaps)[0]
-    graph = HotPathGraph(C, d_cls, d_box, anc0, batch["im_szs"], max_targets=max(4096, gsum_max), global_batch=gb)
+    gkw = dict(max_targets=max(4096, gsum_max), global_batch=gb, exchange=xch if xch is not None else "nccl")
+    graph = HotPathGraph(C, d_cls, d_box, anc0, batch["im_szs"], **gkw)
     d_cls2, d_box2 = d_cls.clone(), d_box.clone()
-    graph2 = HotPathGraph(C, d_cls2, d_box2, anc0, batch["im_szs"], max_targets=max(4096, gsum_max), global_batch=gb)
+    graph2 = HotPathGraph(C, d_cls2, d_box2, anc0, batch["im_szs"], **gkw)
     gpend = []
 
     def step_graph_pipelined():
         g = graph if (len(gpend) == 0 or gpend[-1][0] is graph2) else graph2
-        gpend.append((g, g.step(targets)))                  # pack GT + graph launch (+ 16-byte all-reduce at N > 1)
+        gpend.append((g, g.step(targets)))                  # pack GT + graph launch (exchange inside the graph)
         if len(gpend) > 1:
             r = gpend.pop(0)[1]
             return r.losses, r.detections(), r.grads        # detections() waits for that step's counts
@@ -267,16 +356,20 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    launches0 = lib.rn_launch_count()
     ms_step = timed(step_graph_pipelined, args.steps)
+    eager_launches = lib.rn_launch_count() - launches0      # launches our library issued directly (rn_pack_targets)
+    gpu_launches = int(eager_launches + args.steps * graph.kernel_nodes)
     while gpend:
         gpend.pop(0)[1].detections()
     if args.only_step:
         if rank == 0:
             sampler.stop()
             _emit({"metric": METRIC, "value": n_img * world / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world,
-                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "only_step": True})
+                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "only_step": True,
+                   "gpu_launches": gpu_launches})
+        close_exchanges()
         return
-    del graph2, d_cls2, d_box2
 
     # ---- one graph, results read in the same step (one host sync per step) ----
     def step_graph():
@@ -286,6 +379,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(3):
         step_graph()
     ms_graph_sync = timed(step_graph, args.steps)
+    torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for _ in range(20):
         graph.step(targets)
@@ -296,20 +390,6 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(d_cls, d_box)
     ms_dropin = timed(lambda: step(d_cls, d_box), args.steps)
-
-    # ---- drop-in calls, inference half enqueued first and collected at the END OF THE SAME STEP (no host sync between
-    # the halves; nothing is carried over to the next step) ----
-    def step_overlapped():
-        anchors = gen(images, fmaps)
-        handle = P.process_detections_async(stub, {"cls_preds": d_cls, "bbox_preds": d_box}, anchors, batch["im_szs"])
-        x, b = d_cls.detach().requires_grad_(True), d_box.detach().requires_grad_(True)
-        out = losses(targets, {"cls_preds": x, "bbox_preds": b}, anchors)
-        (out["classification_loss"] + out["regression_loss"]).backward()
-        return out, handle.detections(), x.grad
-
-    for _ in range(3):
-        step_overlapped()
-    ms_overlapped = timed(step_overlapped, args.steps)
 
     # ---- same work, software-pipelined: detections of step i are collected while step i+1 is enqueued ----
     pending = []
@@ -330,59 +410,73 @@ def run_ours(args, rank, world, local_rank):
         pending.pop(0).detections()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end: pinned host inputs -> H2D every step, results read back ----
-    stage_cls, stage_box = torch.empty_like(d_cls), torch.empty_like(d_box)
-
-    # The batch is ingested in chunks of images on a copy stream while the previous chunk is processed on the
-    # compute stream (images are independent; every chunk's loss is divided by the GLOBAL batch, so the sum of
-    # the chunk losses is the loss of the batch — the same mechanism as the multi-GPU sharding).
-    n_chunks = 4 if n_img % 4 == 0 else 1
-    per = n_img // n_chunks
+    # ---- end to end: pinned HOST inputs -> H2D every step -> graph step -> results copied back to the host.
+    # The two graphs' input buffers alternate: the copy stream fills buffer (i+1)%2 while the graph of step i runs,
+    # so the PCIe link never waits for the GPU and the GPU work hides behind the next step's ingest. ----
+    graphs = (graph, graph2)
     copy_stream = torch.cuda.Stream(device=dev)
-    chunk_losses = ShardedRetinaNetLosses(C, global_batch=n_img * world)
+    host_targets = batch["targets"]                          # CPU tensors, as the reference's collate_fn hands them over
+    M = 100
+    h_out = [dict(boxes=torch.empty((n_img, M, 4), pin_memory=True), scores=torch.empty((n_img, M), pin_memory=True),
+                  labels=torch.empty((n_img, M), dtype=torch.int64, pin_memory=True),
+                  total=torch.empty((4,), pin_memory=True)) for _ in range(2)]
+    free_ev = [None, None]                                    # buffer k's previous graph step has finished
+    e2e_pending = []
+    counter = [0]
 
     def e2e_step():
+        k = counter[0] % 2
+        counter[0] += 1
+        g = graphs[k]
         main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)                       # staging buffers of the previous step are free again
-        ready = []
+        if free_ev[k] is not None:
+            copy_stream.wait_event(free_ev[k])
         with torch.cuda.stream(copy_stream):
-            for k in range(n_chunks):
-                sl = slice(k * per, (k + 1) * per)
-                stage_cls[sl].copy_(h_cls[sl], non_blocking=True)
-                stage_box[sl].copy_(h_box[sl], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                ready.append(ev)
-        anchors = gen(images, fmaps)
-        tot_c, tot_r, pend = None, None, []
-        for k in range(n_chunks):
-            sl = slice(k * per, (k + 1) * per)
-            main.wait_event(ready[k])
-            x, b = stage_cls[sl].requires_grad_(True), stage_box[sl].requires_grad_(True)
-            out = chunk_losses(targets[sl], {"cls_preds": x, "bbox_preds": b}, anchors[:per])
-            (out["classification_loss"] + out["regression_loss"]).backward()
-            tot_c = out["classification_loss"].detach() if tot_c is None else tot_c + out["classification_loss"].detach()
-            tot_r = out["regression_loss"].detach() if tot_r is None else tot_r + out["regression_loss"].detach()
-            pend.append(P.process_detections_async(stub, {"cls_preds": stage_cls[sl], "bbox_preds": stage_box[sl]},
-                                                   anchors[:per], batch["im_szs"][sl]))
-        # (world > 1: every chunk loss already went through the ranks' all-reduce inside the loss function)
-        host = torch.stack([tot_c, tot_r]).cpu()
-        host_d = []
-        for p_ in pend:                                       # padded [n,100,*] slabs + counts: 3 D2H copies per chunk
-            ob, os_, ol, counts = p_.result()
-            host_d.append((ob.cpu(), os_.cpu(), ol.cpu(), counts))
-        return host, host_d
+            g.cls_preds.copy_(h_cls, non_blocking=True)
+            g.bbox_preds.copy_(h_box, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main.wait_event(ready)
+        r = g.step(host_targets)                            # GT: one pinned staging block, one async copy (no packing launch)
+        ho = h_out[k]
+        ho["total"].copy_(g.total, non_blocking=True)
+        ho["boxes"].copy_(g.out_boxes, non_blocking=True)
+        ho["scores"].copy_(g.out_scores, non_blocking=True)
+        ho["labels"].copy_(g.out_labels, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        free_ev[k] = done
+        e2e_pending.append((r, done))
+        if len(e2e_pending) > 1:                             # consume step i-1 on the host while step i runs
+            pr, pdone = e2e_pending.pop(0)
+            counts = pr.result()[3]
+            pdone.synchronize()
+            return counts
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(e2e_step, e2e_steps)
-    h2d = h_cls.numel() * 4 + h_box.numel() * 4
-    d2h = 8 + sum(int(d["boxes"].shape[0]) * 28 for d in step(d_cls, d_box)[1]) + (n_img + 2) * 4
+    while e2e_pending:
+        pr, pdone = e2e_pending.pop(0)
+        pr.result()
+        pdone.synchronize()
+    gt_bytes = graph._off_bytes + gsum_max * 24
+    h2d = h_cls.numel() * 4 + h_box.numel() * 4 + gt_bytes
+    d2h = 16 + n_img * M * 28 + (n_img + 4) * 4
+
+    # raw H2D rate of the same pinned buffers (all ranks at once): the PCIe / host-memory roof e2e is measured against
+    def h2d_probe():
+        d_cls2.copy_(h_cls, non_blocking=True)
+        d_box2.copy_(h_box, non_blocking=True)
+
+    for _ in range(2):
+        h2d_probe()
+    ms_probe = timed(h2d_probe, 5)
+    probe_gbs = (h_cls.numel() + h_box.numel()) * 4 / (ms_probe * 1e-3) / 1e9
+    del graph2, d_cls2, d_box2, graphs
 
     # ---- dominant kernel (fused loss fwd+grad) timed alone, live, for the roofline ----
-    from pytorch_retinanet_b200.box_utils import PackedTargets
-    from pytorch_retinanet_b200.losses import fused_loss_forward
     packed = PackedTargets([t["boxes"] for t in targets], [t["labels"] for t in targets], dev)
     anc = gen(images, fmaps)[0]
 
@@ -393,6 +487,7 @@ def run_ours(args, rank, world, local_rank):
     for name, fn in (("loss_fwd_bwd", lambda: loss_only(True)), ("loss_fwd", lambda: loss_only(False)),
                      ("loss_kernel_alone", graph._enqueue_loss),     # loss_kernel<4,grad> + finalize on precomputed codes
                      ("loss_fwd_kernel_alone", lambda: graph._enqueue_loss(False)),
+                     ("match_alone", graph._enqueue_match),
                      ("postprocess", lambda: postprocess_batch(d_cls, d_box, anc, 0, batch["im_szs"], 0.05, 0.5, 100))):
         for _ in range(3):
             fn()
@@ -402,111 +497,309 @@ def run_ours(args, rank, world, local_rank):
     # reference head's view/permute/contiguous/cat pass that it makes unnecessary (layers.py:189-195, 253-259)
     n1 = None
     if not args.no_levels:
-        from pytorch_retinanet_b200.detections import postprocess_levels_async
-        from pytorch_retinanet_b200.losses import fused_loss_forward_levels
-        cls_lv = [t.to(dev) for t in S.nac_to_levels(h_cls, cfg.padded_hw)]
-        box_lv = [t.to(dev) for t in S.nac_to_levels(h_box, cfg.padded_hw)]
+        n1 = levels_leg(S, HotPathGraph, cfg, h_cls, h_box, dev, anc, packed, batch, targets, C, n_img, gsum_max, timed, args)
 
-        def relayout():
-            outs = []
-            for x in cls_lv:
-                Nn, _, H, W = x.shape
-                outs.append(x.view(Nn, -1, C, H, W).permute(0, 3, 4, 1, 2).contiguous().view(Nn, -1, C))
-            return torch.cat(outs, dim=1)
-
-        lv = {}
-        for name, fn in (("loss_fwd_bwd", lambda: fused_loss_forward_levels(cls_lv, box_lv, anc, 0, packed, C, 0.25, 2.0, 0.1,
-                                                                           0.5, 0.4, float(n_img), True)),
-                         ("postprocess", lambda: postprocess_levels_async(cls_lv, box_lv, C, anc, 0, batch["im_szs"], 0.05, 0.5,
-                                                                          100).result()),
-                         ("reference_head_relayout_cls_fwd", relayout)):
-            for _ in range(3):
-                fn()
-            lv[name] = timed(fn, max(5, args.steps))
-        glv = HotPathGraph(C, cls_lv, box_lv, anc, batch["im_szs"], max_targets=max(4096, gsum_max))
-
-        def step_graph_levels():
-            r = glv.step(targets)
-            return r.losses, r.detections(), r.grads
-
-        for _ in range(3):
-            step_graph_levels()
-        lv["graph_step_sync"] = timed(step_graph_levels, max(5, args.steps))
-        del glv
-        n1 = {"ms": lv, "note": "loss / post-processing on raw [N, 9*C, H_l, W_l] conv outputs (no permute+cat); graph_step_sync = "
-                                "HotPathGraph on the level lists, results read in the same step; "
-                                "reference_head_relayout_cls_fwd = torch time of the re-layout pass this removes (forward only; "
-                                "its backward costs the same again)"}
-        del cls_lv, box_lv
-    peak, peak_src = measured_peak_gbs()
     gsum = sum(int(t["boxes"].shape[0]) for t in batch["targets"])
     bytes_fb = n_img * (2 * 4 * A * C + 2 * 16 * A) + 16 * A + 24 * gsum + 12 * n_img     # B_fb
     bytes_f = n_img * (4 * A * C + 16 * A) + 16 * A + 24 * gsum + 12 * n_img               # B_f
     bytes_p = n_img * (4 * A * C + 16 * A + 100 * 28) + 16 * A                             # B_p
+
+    def bw(nbytes, ms, note=None):
+        d = {"GBps": nbytes / (ms * 1e-3) / 1e9, "ms": ms, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+        if note:
+            d["note"] = note
+        return d
+
     ach_fb = bytes_fb / (kern["loss_fwd_bwd"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "rn_train_loss = match_kernel + loss_kernel<4,grad> + finalize (training loss, "
                                           "fwd+grad in one pass over the logits)",
                 "achieved": ach_fb, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach_fb / peak,
-                "traffic": 2.076e9 + 4.9e6, "traffic_note": "ncu --set full, loss_kernel 1.047 GB read + 1.029 GB write, "
-                "match_kernel 3.3 MB, finalize < 1 MB per launch (profiles/r01_ncu_graph_step_summary.txt)", "bytes_per_launch": bytes_fb, "ms_per_launch": kern["loss_fwd_bwd"],
-                "others": {"loss_fwd": {"GBps": bytes_f / (kern["loss_fwd"] * 1e-3) / 1e9, "ms": kern["loss_fwd"],
-                                        "frac": bytes_f / (kern["loss_fwd"] * 1e-3) / 1e9 / peak},
-                           "postprocess": {"GBps": bytes_p / (kern["postprocess"] * 1e-3) / 1e9, "ms": kern["postprocess"],
-                                           "frac": bytes_p / (kern["postprocess"] * 1e-3) / 1e9 / peak,
-                                           "note": "whole synchronous call: streaming score filter (168 us = 0.94 of peak under "
-                                                   "ncu) + latency-bound lazy NMS (64 us, one CTA per image) + the count copy/sync"},
-                           "loss_fwd_kernel_alone": {"GBps": bytes_f / (kern["loss_fwd_kernel_alone"] * 1e-3) / 1e9,
-                                                     "ms": kern["loss_fwd_kernel_alone"],
-                                                     "frac": bytes_f / (kern["loss_fwd_kernel_alone"] * 1e-3) / 1e9 / peak,
-                                                     "note": "the forward-only streaming kernel (+ finalize) by itself; loss_fwd "
-                                                             "adds the ALU-bound matcher (~43 us) in front of it"},
-                           "loss_kernel_alone": {"GBps": bytes_fb / (kern["loss_kernel_alone"] * 1e-3) / 1e9,
-                                                 "ms": kern["loss_kernel_alone"],
-                                                 "frac": bytes_fb / (kern["loss_kernel_alone"] * 1e-3) / 1e9 / peak,
-                                                 "note": "loss_kernel<4,grad> + finalize, codes precomputed by rn_match"},
-                           "graph_step": {"GBps": (bytes_fb + bytes_p) / (ms_step * 1e-3) / 1e9, "ms": ms_step,
-                                          "frac": (bytes_fb + bytes_p) / (ms_step * 1e-3) / 1e9 / peak,
-                                          "note": "B_fb + B_p over the whole timed step (both branches of the graph, target "
-                                                  "packing and result read-back included); the logits are counted once per branch"}}}
+                "traffic": 2.076e9 + 4.9e6,
+                "traffic_source": "NOT measured in this run: one `ncu --set full` capture of the same launch (loss_kernel 1.047 GB "
+                                  "read + 1.029 GB write, match_kernel 3.3 MB, finalize < 1 MB), profiles/r01_ncu_graph_step_summary.txt",
+                "bytes_per_launch": bytes_fb, "ms_per_launch": kern["loss_fwd_bwd"],
+                "others": {"loss_fwd": bw(bytes_f, kern["loss_fwd"], "matcher + forward-only loss kernel + finalize (the reference's "
+                                                                      "validation_step path)"),
+                           "postprocess": bw(bytes_p, kern["postprocess"], "whole synchronous call: streaming score filter + lazy NMS "
+                                                                           "+ the count copy/sync"),
+                           "loss_fwd_kernel_alone": bw(bytes_f, kern["loss_fwd_kernel_alone"], "forward-only streaming kernel "
+                                                                                                "(+ finalize) on precomputed codes"),
+                           "loss_kernel_alone": bw(bytes_fb, kern["loss_kernel_alone"], "loss_kernel<4,grad> + finalize, codes "
+                                                                                         "precomputed by rn_match"),
+                           "match_alone": {"ms": kern["match_alone"], "iou_pairs_per_s": float(A) * gsum / (kern["match_alone"] * 1e-3),
+                                           "note": "ALU-bound (SURVEY 8d): nominal anchor x GT pairs per second, not a bandwidth"},
+                           "graph_step": bw(bytes_fb + bytes_p, ms_step, "B_fb + B_p over the whole timed step (both branches of the "
+                                                                         "graph, target packing and result read-back included); the "
+                                                                         "logits are counted once per branch")}}
 
-    # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----
+    # ---- the other BASELINE configs at their stated sizes ----
+    extra = {"configs": other_configs(S, P, HotPathGraph, lib, dev, rank, world, timed, peak, xch, args)}
+
+    # ---- reference eager code on CUDA tensors (the secondary comparator of SURVEY 8d), rank 0 ----
+    cuda_eager = None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = n_img                                      # the whole batch, 3 passes: ~10 s of CPU work
-        v, dt = time_cpu_reference(batch, sample, repeats=3)
-        cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"the same {sample}-image batch, best of 3 passes ({dt:.2f} s per pass), torch CPU eager port of the "
-                         f"reference (oracle/torch_oracle.py), os.cpu_count={os.cpu_count()}"}
+    if rank == 0 and not args.no_cpu_baseline:
+        kind, ref_step = load_reference_or_port()
+        sub = 4
+        ref_step(batch, 1, True, dev)                        # warm-up (cuDNN-free, but allocator + kernels' first use)
+        torch.cuda.synchronize(dev)
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ref_step(batch, sub, True, dev)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        cuda_eager = {"value": sub / best, "unit": "images/s", "ms_per_step": best * 1e3, "images": sub, "kind": kind,
+                      "note": "the reference's own eager torch code (AnchorGenerator.forward, RetinaNetLosses.forward + backward, "
+                              "process_detections) with CUDA tensors on this GPU, first %d images of the batch, best of 2 "
+                              "(python loop per image and per class: cost is linear in images)" % sub}
+        if world == 1:
+            # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----
+            torch.set_num_threads(os.cpu_count() or 1)
+            ref_step(batch, 1)
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                ref_step(batch, n_img)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            cpu = {"value": n_img / best, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind,
+                   "sample": f"the same {n_img}-image batch, best of 2 passes ({best:.2f} s per pass), "
+                             + (f"the unmodified reference ({load_reference_or_port.where})" if kind == "reference" else "oracle port of the reference")
+                             + f", torch CPU eager, os.cpu_count={os.cpu_count()}"}
+    if world > 1:
+        tp = torch.tensor([probe_gbs], device=dev)
+        dist.all_reduce(tp)
+        probe_total = float(tp.item())
+    else:
+        probe_total = probe_gbs
     if rank == 0:
         total = n_img * world
+        e2e_gbs = h2d * world / (ms_e2e * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": total / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), pipeline="2 input buffers x 2 CUDA graphs alternate; results of step i are "
-                                                            "read after step i+1 is launched (api.graph_sync = no pipelining)"),
+            "config": workload_config(world),
             "clocks": clocks,
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps},
-            "api": {"value_through": "HotPathGraph.step: one CUDA graph of rn_train_loss (match+loss fwd+grad) || rn_postprocess; two "
-                                     "graphs / input buffers alternate, every step's losses, gradients and detections are read "
-                                     "one step late",
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "through": "HotPathGraph.step on two alternating input buffers: pinned host logits / boxes / GT -> H2D on a copy "
+                               "stream -> graph -> losses + detection slabs copied back to pinned host memory, every step",
+                    "ingest_GBps_all_gpus": e2e_gbs, "h2d_roof_GBps_all_gpus": probe_total,
+                    "frac_of_h2d_roof": e2e_gbs / probe_total if probe_total else None,
+                    "h2d_roof_note": "raw cudaMemcpyAsync rate of the same pinned buffers with all ranks copying at once, measured in "
+                                     "this run: e2e is bound by host->device ingest (PCIe / host memory), not by a kernel",
+                    "placement": placement},
+            "api": {"value_through": "HotPathGraph.step: one CUDA graph of rn_train_loss (match+loss fwd+grad, exchange inside) || "
+                                     "rn_postprocess; two graphs / input buffers alternate, every step's losses, gradients and "
+                                     "detections are read one step late; anchors generated once (cached), outside the timed region",
+                    "pipeline": "2 input buffers x 2 CUDA graphs alternate; results of step i are read after step i+1 is launched "
+                                "(graph_sync = no pipelining)",
                     "graph_sync": {"value": total / (ms_graph_sync * 1e-3), "unit": "images/s", "ms_per_step": ms_graph_sync,
                                    "note": "one graph, results read in the same step (one host sync per step)"},
                     "graph_host_enqueue_us": host_us_graph,
                     "dropin_sync": {"value": total / (ms_dropin * 1e-3), "unit": "images/s", "ms_per_step": ms_dropin,
                                     "note": "RetinaNetLosses.forward + backward + process_detections (reference signatures, "
                                             "autograd), one host sync per step"},
-                    "dropin_overlapped": {"value": total / (ms_overlapped * 1e-3), "unit": "images/s", "ms_per_step": ms_overlapped,
-                                          "note": "drop-in calls, process_detections_async enqueued before the training half and "
-                                                  "collected at the end of the same step"},
                     "dropin_pipelined": {"value": total / (ms_pipe * 1e-3), "unit": "images/s", "ms_per_step": ms_pipe,
                                          "note": "drop-in calls with process_detections_async: results of step i read while "
                                                  "step i+1 is enqueued"}},
-            "gpu_launches": args.steps * 7,    # per graph step: pack_targets, match, loss, finalize, score filter, lazy NMS, status
-            "roofline": roofline, "cpu_baseline": cpu, "n1_levels": n1,
+            "gpu_launches": gpu_launches,
+            "gpu_launches_note": f"counted: {graph.kernel_nodes} kernel nodes recorded in the captured graph x {args.steps} replays + "
+                                 f"{eager_launches} launches issued directly by the library in the timed region (rn_launch_count)",
+            "exchange": exchange_used, "parity_check": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "cuda_eager_baseline": cuda_eager, "n1_levels": n1, "extra": extra,
         }
         _emit(line)
+    close_exchanges()
+
+
+def parity_check(P, HotPathGraph, losses_cls, xch, rank, world, dev, dist):
+    """Sharded loss of a 2*world-image batch (config-1 shape) through the graph step and the drop-in sharded loss, each
+    rank holding 2 images, against the CPU oracle on the WHOLE batch (rank 0 computes it and broadcasts the numbers):
+    global losses within 1e-5, this rank's gradient slice within 2e-5 (retinanet/losses.py:138-140)."""
+    from oracle import torch_oracle as O
+    cfg = S.CONFIGS[1]
+    per = 2
+    n_tot = per * world
+    b = S.make_batch(cfg, 700, n_tot, clustered=True)
+    lo = rank * per
+    anc = b["anchors"].to(dev)
+    x = b["cls_preds"][lo:lo + per].to(dev)
+    bb = b["bbox_preds"][lo:lo + per].to(dev)
+    tg = [{k: v.to(dev) for k, v in t.items()} for t in b["targets"][lo:lo + per]]
+    g = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"][:per], global_batch=n_tot if world > 1 else None,
+                     exchange=xch if xch is not None else "nccl")
+    r = g.step(tg)
+    got = torch.stack([r.losses["classification_loss"], r.losses["regression_loss"]]).cpu()
+    L = losses_cls(cfg.num_classes, global_batch=n_tot, exchange=xch if xch is not None else "nccl") if world > 1 else P.RetinaNetLosses(cfg.num_classes)
+    xg, bg = x.clone().requires_grad_(True), bb.clone().requires_grad_(True)
+    out = L(tg, {"cls_preds": xg, "bbox_preds": bg}, [anc] * per)
+    (out["classification_loss"] + out["regression_loss"]).backward()
+    got2 = torch.stack([out["classification_loss"].detach(), out["regression_loss"].detach()]).cpu()
+    same = bool(torch.equal(got, got2) and torch.equal(r.grads[0], xg.grad) and torch.equal(r.grads[1], bg.grad))
+    # the oracle on the whole batch is cheap at this shape (49k anchors, 20 classes): every rank computes it
+    xo = b["cls_preds"].clone().requires_grad_(True)
+    bo = b["bbox_preds"].clone().requires_grad_(True)
+    want = O.batch_loss(b["targets"], xo, bo, [b["anchors"]] * n_tot, cfg.num_classes)
+    (want["classification_loss"] + want["regression_loss"]).backward()
+    w = torch.stack([want["classification_loss"].detach(), want["regression_loss"].detach()])
+    loss_err = float(((got - w).abs() / w.abs()).max())
+    gx = xo.grad[lo:lo + per]
+    grad_err = float(((xg.grad.cpu() - gx).abs() / gx.abs().clamp_min(1e-9)).max())
+    gbx = bo.grad[lo:lo + per]
+    gbox_err = float(((bg.grad.cpu() - gbx).abs() / gbx.abs().clamp_min(1e-7)).max())
+    ok = same and loss_err <= 1e-5 and grad_err <= 2e-5 and gbox_err <= 2e-5
+    stats = torch.tensor([loss_err, grad_err, gbox_err, 0.0 if ok else 1.0], device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    if xch is not None and xch.error():
+        stats[3] = 1.0
+    s = stats.tolist()
+    return {"ok": s[3] == 0.0, "loss_rel_err": s[0], "grad_logits_rel_err": s[1], "grad_bbox_rel_err": s[2],
+            "graph_equals_dropin": same, "images": n_tot,
+            "what": "global loss of 2 images/rank (config-1 shape) through HotPathGraph and ShardedRetinaNetLosses vs the CPU "
+                    "oracle on the whole batch; max over ranks; tolerances 1e-5 (losses) / 2e-5 (gradients)"}
+
+
+def levels_leg(S, HotPathGraph, cfg, h_cls, h_box, dev, anc, packed, batch, targets, C, n_img, gsum_max, timed, args):
+    from pytorch_retinanet_b200.detections import postprocess_levels_async
+    from pytorch_retinanet_b200.losses import fused_loss_forward_levels
+    cls_lv = [t.to(dev) for t in S.nac_to_levels(h_cls, cfg.padded_hw)]
+    box_lv = [t.to(dev) for t in S.nac_to_levels(h_box, cfg.padded_hw)]
+
+    def relayout():
+        outs = []
+        for x in cls_lv:
+            Nn, _, H, W = x.shape
+            outs.append(x.view(Nn, -1, C, H, W).permute(0, 3, 4, 1, 2).contiguous().view(Nn, -1, C))
+        return torch.cat(outs, dim=1)
+
+    lv = {}
+    for name, fn in (("loss_fwd_bwd", lambda: fused_loss_forward_levels(cls_lv, box_lv, anc, 0, packed, C, 0.25, 2.0, 0.1,
+                                                                       0.5, 0.4, float(n_img), True)),
+                     ("postprocess", lambda: postprocess_levels_async(cls_lv, box_lv, C, anc, 0, batch["im_szs"], 0.05, 0.5,
+                                                                      100).result()),
+                     ("reference_head_relayout_cls_fwd", relayout)):
+        for _ in range(3):
+            fn()
+        lv[name] = timed(fn, max(5, args.steps))
+    glv = HotPathGraph(C, cls_lv, box_lv, anc, batch["im_szs"], max_targets=max(4096, gsum_max))
+
+    def step_graph_levels():
+        r = glv.step(targets)
+        return r.losses, r.detections(), r.grads
+
+    for _ in range(3):
+        step_graph_levels()
+    lv["graph_step_sync"] = timed(step_graph_levels, max(5, args.steps))
+    return {"ms": lv, "note": "loss / post-processing on raw [N, 9*C, H_l, W_l] conv outputs (no permute+cat); graph_step_sync = "
+                              "HotPathGraph on the level lists, results read in the same step; "
+                              "reference_head_relayout_cls_fwd = torch time of the re-layout pass this removes (forward only; "
+                              "its backward costs the same again)"}
+
+
+def other_configs(S, P, HotPathGraph, lib, dev, rank, world, timed, peak, xch, args):
+    """BASELINE.json configs[2..4] at their stated sizes, on device-generated inputs (synth_data.make_batch_device).
+    config 3: global batch 128 split over the ranks (strong scaling; the whole batch on one GPU at N = 1);
+    config 4 (N = 1 only): batch 256 inference, top-k extension off and 1000/level;
+    config 5 (N = 1 only): batch 64, 500 GT boxes per image: loss fwd+grad, matcher alone (IoU pairs/s), post-processing."""
+    from pytorch_retinanet_b200.box_utils import PackedTargets, match_batch
+    from pytorch_retinanet_b200.detections import postprocess_batch
+    from pytorch_retinanet_b200.losses import fused_loss_forward
+    out = {}
+    reps = max(5, min(args.steps, 10))
+    if args.no_extra:
+        return None
+
+    # ---- config 3 ----
+    c3 = S.CONFIGS[3]
+    per = c3.batch // world
+    b = S.make_batch_device(c3, rank * per, per, dev)
+    A, C = b["anchors"].shape[0], c3.num_classes
+    gsum = sum(int(t["boxes"].shape[0]) for t in b["targets"])
+    g = HotPathGraph(C, b["cls_preds"], b["bbox_preds"], b["anchors"], b["im_szs"], max_targets=max(4096, gsum),
+                     global_batch=c3.batch if world > 1 else None, exchange=xch if xch is not None else "nccl")
+
+    def step3():
+        r = g.step(b["targets"])
+        return r.losses, r.detections(), r.grads
+
+    for _ in range(3):
+        step3()
+    ms = timed(step3, reps)
+    nbytes = per * (2 * 4 * A * C + 2 * 16 * A) + per * (4 * A * C + 16 * A + 100 * 28) + 32 * A + 24 * gsum
+    out["config3"] = {"what": "BASELINE.json configs[2]: batch 128 image-sharded, step = loss fwd+grad + post-process "
+                              "(HotPathGraph.step, results read in the same step)", "global_batch": c3.batch,
+                      "images_per_gpu": per, "n_gpus": world, "ms_per_step": ms, "images_per_s": c3.batch / (ms * 1e-3),
+                      "hbm_frac_per_gpu": nbytes / (ms * 1e-3) / 1e9 / peak, "scaling": "strong", "steps": reps}
+    del g, b
+    torch.cuda.empty_cache()
+    if world > 1:
+        return out
+
+    # ---- config 4: inference, batch 256 ----
+    c4 = S.CONFIGS[4]
+    b = S.make_batch_device(c4, 0, c4.batch, dev)
+    A, C, N = b["anchors"].shape[0], c4.num_classes, c4.batch
+    offs = [0]
+    for h, w in S.grid_sizes(c4.padded_hw):
+        offs.append(offs[-1] + 9 * h * w)
+    bytes_p = N * (4 * A * C + 16 * A + 100 * 28) + 16 * A
+    res4 = {"what": "BASELINE.json configs[3]: inference post-processing, batch 256, score 0.05, NMS 0.5, 100 dets/img "
+                    "(synchronous postprocess_batch call incl. the count copy)", "batch": N, "steps": reps}
+    for name, topk in (("topk_none", None), ("topk_1000_per_level", 1000)):
+        def pp():
+            return postprocess_batch(b["cls_preds"], b["bbox_preds"], b["anchors"], 0, b["im_szs"], 0.05, 0.5, 100,
+                                     pre_nms_topk=topk, level_offsets=offs if topk else None)
+        for _ in range(2):
+            r = pp()
+        ms = timed(pp, reps)
+        res4[name] = {"ms": ms, "images_per_s": N / (ms * 1e-3), "hbm_frac": bytes_p / (ms * 1e-3) / 1e9 / peak,
+                      "detections": int(sum(r[3]))}
+    out["config4"] = res4
+    del b
+    torch.cuda.empty_cache()
+
+    # ---- config 5: dense crowd, batch 64, 500 GT/img ----
+    c5 = S.CONFIGS[5]
+    b = S.make_batch_device(c5, 0, c5.batch, dev)
+    A, C, N = b["anchors"].shape[0], c5.num_classes, c5.batch
+    packed = PackedTargets([t["boxes"] for t in b["targets"]], [t["labels"] for t in b["targets"]], dev)
+    gsum = packed.total
+
+    def loss5(want):
+        return fused_loss_forward(b["cls_preds"], b["bbox_preds"], b["anchors"], 0, packed, 0.25, 2.0, 0.1, 0.5, 0.4, float(N), want)
+
+    def match5():
+        return match_batch(b["anchors"], 0, packed, A, 0.5, 0.4, False, True)
+
+    def pp5():
+        return postprocess_batch(b["cls_preds"], b["bbox_preds"], b["anchors"], 0, b["im_szs"], 0.05, 0.5, 100)
+
+    t5 = {}
+    for name, fn in (("loss_fwd_bwd", lambda: loss5(True)), ("loss_fwd", lambda: loss5(False)), ("match", match5), ("postprocess", pp5)):
+        for _ in range(2):
+            fn()
+        t5[name] = timed(fn, reps)
+    bytes_fb = N * (2 * 4 * A * C + 2 * 16 * A) + 16 * A + 24 * gsum + 12 * N
+    bytes_f = N * (4 * A * C + 16 * A) + 16 * A + 24 * gsum + 12 * N
+    bytes_p = N * (4 * A * C + 16 * A + 100 * 28) + 16 * A
+    pairs = float(A) * gsum
+    out["config5"] = {"what": "BASELINE.json configs[4]: dense crowd 1024x1024, 500 GT boxes/img, 80 classes, batch 64",
+                      "batch": N, "gt_boxes": gsum, "steps": reps,
+                      "loss_fwd_bwd": {"ms": t5["loss_fwd_bwd"], "images_per_s": N / (t5["loss_fwd_bwd"] * 1e-3),
+                                       "hbm_frac": bytes_fb / (t5["loss_fwd_bwd"] * 1e-3) / 1e9 / peak},
+                      "loss_fwd": {"ms": t5["loss_fwd"], "hbm_frac": bytes_f / (t5["loss_fwd"] * 1e-3) / 1e9 / peak},
+                      "match": {"ms": t5["match"], "iou_pairs": pairs, "iou_pairs_per_s": pairs / (t5["match"] * 1e-3),
+                                "note": "ALU-bound: nominal anchor x GT pairs (A x sum G) per second, not a bandwidth"},
+                      "postprocess": {"ms": t5["postprocess"], "images_per_s": N / (t5["postprocess"] * 1e-3),
+                                      "hbm_frac": bytes_p / (t5["postprocess"] * 1e-3) / 1e9 / peak}}
+    del b
+    torch.cuda.empty_cache()
+    return out
 
 
 def _emit(line: dict) -> None:
@@ -527,18 +820,18 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and CUDA-eager reference legs")
     ap.add_argument("--no-levels", action="store_true", help="skip the row-N1 (per-level NCHW) timing leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra.configs (BASELINE configs 3-5 at their stated sizes)")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the warm-up and the timed graph steps "
                                                                 "(what `value` measures) and print a reduced line")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    args.steps = max(args.steps, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        args.steps_ref = max(1, min(args.steps, 3))
-        args.warmup_ref = max(1, min(args.warmup, 1))
         run_reference(args, rank, world)
         return
     if world > 1:

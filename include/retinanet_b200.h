@@ -74,6 +74,9 @@ int rn_exchange_total(float *total /*[4] in/out*/, const rn_exchange_t *exchange
 
 int rn_abi_version(void);
 const char *rn_last_error(void);
+/* Number of kernel launches this library has issued in the process so far (launches recorded into a CUDA graph
+ * during stream capture count once, when recorded).  Instrumentation for bench.py's `gpu_launches`.            */
+uint64_t rn_launch_count(void);
 
 /* ---- anchors ---------------------------------------------------------------------------------
  * Replaces AnchorGenerator.grid_anchors / _compute_grid_offsets (retinanet/anchors.py:151-197) for

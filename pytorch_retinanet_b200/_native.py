@@ -40,6 +40,7 @@ SIGNATURES = {
     "rn_exchange_total": (_c.c_int, [_vp, _xp, _vp]),
     "rn_abi_version": (_c.c_int, []),
     "rn_last_error": (_c.c_char_p, []),
+    "rn_launch_count": (_c.c_uint64, []),
     "rn_anchor_grid": (_c.c_int, [_vp, _vp, _c.c_int, _f64, _vp, _i64, _vp]),
     "rn_pack_targets": (_c.c_int, [_vp, _vp, _vp, _c.c_int, _vp, _vp, _vp, _vp, _vp]),
     "rn_match": (_c.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _c.c_int, _i64, _f32, _f32, _vp, _vp, _vp, _vp]),

@@ -9,6 +9,7 @@
 #define RN_SM_COUNT_B200 148
 
 void rn_set_error(const char *fmt, ...);
+void rn_note_launch(void);   // counts the kernel launches this library issues (rn_launch_count)
 
 #define RN_CHECK_ARG(cond, code, ...)   \
     do {                                \
@@ -25,6 +26,7 @@ void rn_set_error(const char *fmt, ...);
             rn_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));  \
             return (int)e__;                                                       \
         }                                                                          \
+        rn_note_launch();                                                          \
     } while (0)
 
 namespace rn {

@@ -221,6 +221,7 @@ class HotPathGraph:
             self._pp_ws_bytes = (lib.rn_postprocess_levels_workspace_bytes if self.levels else
                                  lib.rn_postprocess_workspace_bytes)(N, A, C, self.cap, M)
             self._pp_ws = torch.empty((self._pp_ws_bytes,), dtype=torch.uint8, device=dev)
+        self._stage = None
         self._side = torch.cuda.Stream(device=dev, priority=-1) if (train and detect and concurrent) else None
         self.graph = torch.cuda.CUDAGraph()
         self._capture()
@@ -313,8 +314,10 @@ class HotPathGraph:
                 self._enqueue_all()
             torch.cuda.current_stream(self.dev).wait_stream(warm)
             torch.cuda.synchronize(self.dev)
+            recorded = self.lib.rn_launch_count()
             with torch.cuda.graph(self.graph):
                 self._enqueue_all()
+            self.kernel_nodes = int(self.lib.rn_launch_count() - recorded)    # kernel launches recorded into the graph
 
     # ---- per step ----
     def load_targets(self, targets: Sequence[Dict[str, Tensor]]) -> None:
@@ -348,7 +351,18 @@ class HotPathGraph:
         """Host-resident targets (the reference's ``collate_fn`` output): one pinned image of the static target buffer,
         one asynchronous H2D copy (no per-tensor copies, no packing launch)."""
         N, total, cap = self.N, sum(counts), max(self.max_targets, 1)
-        stage = torch.empty((self._off_bytes + cap * 24,), dtype=torch.uint8, pin_memory=True)
+        # two pinned staging blocks alternate (allocated once): the block written now is not the one whose copy of the
+        # previous step may still be in flight; its own last copy (two steps ago) is waited for, which never blocks
+        # in steady state
+        if self._stage is None:
+            self._stage = [torch.empty((self._off_bytes + cap * 24,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+            self._stage_ev = [None, None]
+            self._stage_k = 0
+        k = self._stage_k
+        self._stage_k = 1 - k
+        if self._stage_ev[k] is not None:
+            self._stage_ev[k].synchronize()
+        stage = self._stage[k]
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + c)
@@ -364,6 +378,9 @@ class HotPathGraph:
         # only the used prefix of each section matters; three slices of one pinned block, stream-ordered before the graph
         self._tgt_buf[:self._off_bytes + total * 16].copy_(stage[:self._off_bytes + total * 16], non_blocking=True)
         self._tgt_buf[lab0:lab0 + total * 8].copy_(stage[lab0:lab0 + total * 8], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self._stage_ev[k] = ev
 
     def step(self, targets: Optional[Sequence[Dict[str, Tensor]]] = None) -> GraphStepResult:
         """One pass of the path over the current contents of ``cls_preds`` / ``bbox_preds``.  ``targets=None`` keeps the

@@ -157,3 +157,65 @@ def make_batch(cfg: PathConfig, first_image: int = 0, count: Optional[int] = Non
         targets.append({"boxes": gt, "labels": lab})
     return {"cls_preds": cls, "bbox_preds": box, "anchors": anchors, "targets": targets,
             "im_szs": [cfg.im_hw] * count, "config": cfg}
+
+
+# ---- the same distributions generated ON the device (bench legs whose batches are too large to draw on the host
+# within the bench's time budget: 256 images of config 4, 128 of config 3, 64 of config 5).  Different random streams
+# than make_batch (CUDA generator), same per-image seeding rule and shapes; parity tests always use make_batch. ----
+def make_batch_device(cfg: PathConfig, first_image: int, count: int, device, clustered: Optional[bool] = None,
+                      want_bbox: bool = True):
+    """Inputs for images [first_image, first_image+count) drawn with a CUDA generator seeded per image
+    (1000*config_id + image_index).  Returns the same dict as :func:`make_batch` with CUDA tensors."""
+    clustered = cfg.clustered if clustered is None else clustered
+    device = torch.device(device)
+    anchors = default_anchors(cfg.padded_hw).to(device)
+    A, C = anchors.shape[0], cfg.num_classes
+    cls = torch.empty((count, A, C), dtype=torch.float32, device=device)
+    box = torch.empty((count, A, 4), dtype=torch.float32, device=device) if want_bbox else None
+    H, W = cfg.im_hw
+    targets = []
+    g = torch.Generator(device=device)
+    for i in range(count):
+        g.manual_seed(1000 * cfg.config_id + first_image + i)
+        lo, hi = cfg.gt_range
+        G = lo if lo == hi else lo + (first_image + i) * 7919 % (hi - lo + 1)
+        k = G * 2 + 8                                            # oversample, keep the first G valid boxes
+        cx = torch.rand(k, generator=g, device=device) * W
+        cy = torch.rand(k, generator=g, device=device) * H
+        scale = 2.0 ** (4.0 + 5.0 * torch.rand(k, generator=g, device=device))
+        r = 2.0 ** (-1.58 + 3.16 * torch.rand(k, generator=g, device=device))
+        w, h = scale / r.sqrt(), scale * r.sqrt()
+        b = torch.stack([(cx - w / 2).clamp(0, W), (cy - h / 2).clamp(0, H), (cx + w / 2).clamp(0, W), (cy + h / 2).clamp(0, H)], 1)
+        ok = ((b[:, 2] - b[:, 0]) >= 2) & ((b[:, 3] - b[:, 1]) >= 2)
+        gt = b[ok][:G].contiguous()
+        G = gt.shape[0]
+        labels = torch.randint(1, C + 1, (G,), generator=g, device=device, dtype=torch.int64)
+        cls[i].normal_(-7.0, 1.3, generator=g)
+        if want_bbox:
+            box[i].normal_(0.0, 0.1, generator=g)
+        if clustered and G > 0:
+            vals = torch.empty(A, device=device)
+            idxs = torch.empty(A, dtype=torch.int64, device=device)
+            ag = (gt[:, 2] - gt[:, 0]) * (gt[:, 3] - gt[:, 1])
+            for s0 in range(0, A, 65536):
+                a = anchors[s0:s0 + 65536]
+                aa = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+                wh = (torch.min(gt[:, None, 2:], a[None, :, 2:]) - torch.max(gt[:, None, :2], a[None, :, :2])).clamp(min=0)
+                inter = wh[..., 0] * wh[..., 1]
+                v, ix = (inter / (ag[:, None] + aa[None] - inter)).max(0)
+                vals[s0:s0 + 65536], idxs[s0:s0 + 65536] = v, ix
+            fg = torch.nonzero(vals > 0.5).squeeze(1)
+            if fg.numel():
+                gi = idxs[fg]
+                cls[i][fg, labels[gi] - 1] += torch.randn(fg.numel(), generator=g, device=device) * 1.5 + 5.0
+                if want_bbox:
+                    a, bb = anchors[fg], gt[gi]
+                    aw, ah = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+                    ax, ay = (a[:, 0] + a[:, 2]) / 2, (a[:, 1] + a[:, 3]) / 2
+                    bw, bh = bb[:, 2] - bb[:, 0], bb[:, 3] - bb[:, 1]
+                    bx, by = (bb[:, 0] + bb[:, 2]) / 2, (bb[:, 1] + bb[:, 3]) / 2
+                    tgt = torch.stack([(bx - ax) / aw, (by - ay) / ah, torch.log(bw / aw + 1e-8), torch.log(bh / ah + 1e-8)], 1)
+                    box[i][fg] = tgt + torch.randn((fg.numel(), 4), generator=g, device=device) * 0.05
+        targets.append({"boxes": gt, "labels": labels})
+    return {"cls_preds": cls, "bbox_preds": box, "anchors": anchors, "targets": targets,
+            "im_szs": [cfg.im_hw] * count, "config": cfg}

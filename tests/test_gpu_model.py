@@ -1,0 +1,81 @@
+"""The REAL reference model on the GPU (-m gpu): ``Retinanet(resnet18)`` from the unmodified reference package
+(baseline/_ref on the GPU box, /root/reference in the build container), patched with ``patch_retinanet``, against an
+unpatched deep copy of itself on the same CUDA inputs — ``forward`` (losses), ``backward`` (parameter gradients) and
+``predict`` (detections after ``transform.postprocess``).  Call sites under test: retinanet/models.py:262-272 and
+:279-288 (``GeneralizedRCNNTransform`` ImageList, layers.py:100-108 delegation).  Skipped only when no reference tree is
+reachable."""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from baseline.reference import load_reference, reference_available  # noqa: E402
+
+
+def _model_and_inputs():
+    ref = load_reference()
+    torch.manual_seed(0)
+    m = ref.Retinanet(num_classes=7, backbone_kind="resnet18", pretrained=False, min_size=256, max_size=384)
+    head = m.retinanet_head
+    with torch.no_grad():                                   # spread the random-init logits so that a few thousand pass 0.05
+        head.classification_head.class_subnet_output.weight.normal_(0, 0.1)
+        head.classification_head.class_subnet_output.bias.fill_(-3.5)
+        head.regression_head.box_subnet_output.weight.normal_(0, 0.02)
+    imgs = [torch.rand(3, 240, 320), torch.rand(3, 300, 260)]
+    tg = [{"boxes": torch.tensor([[20., 30., 120., 160.], [100., 50., 300., 200.]]), "labels": torch.tensor([1, 3])},
+          {"boxes": torch.tensor([[10., 10., 200., 250.]]), "labels": torch.tensor([7])}]
+    return m.cuda(), [i.cuda() for i in imgs], [{k: v.cuda() for k, v in t.items()} for t in tg]
+
+
+@pytest.mark.skipif(not reference_available(), reason="no reference tree (baseline/_ref, /root/reference)")
+@pytest.mark.parametrize("mode", ["plain", "fused_layout_and_resize"])
+def test_patched_real_model_matches_unpatched_on_gpu(mode):
+    import pytorch_retinanet_b200 as P
+    base, imgs, tg = _model_and_inputs()
+    ours = copy.deepcopy(base)
+    kw = dict(fuse_head_layout=True, fold_box_resize=True) if mode != "plain" else {}
+    P.patch_retinanet(ours, **kw)
+    assert list(ours.state_dict().keys()) == list(base.state_dict().keys())
+    assert type(ours.anchor_generator).__module__.startswith("pytorch_retinanet_b200")
+
+    # ---- forward + backward (models.py:274-288) ----
+    want = base([i.clone() for i in imgs], [dict(t) for t in tg])
+    got = ours([i.clone() for i in imgs], [dict(t) for t in tg])
+    for k in ("classification_loss", "regression_loss"):
+        w, g = float(want[k]), float(got[k])
+        assert abs(g - w) <= 1e-5 * abs(w), (k, g, w)
+    (want["classification_loss"] + want["regression_loss"]).backward()
+    (got["classification_loss"] + got["regression_loss"]).backward()
+    checked = 0
+    for (n, pw), (_, pg) in zip(base.named_parameters(), ours.named_parameters()):
+        if pw.grad is None:
+            assert pg.grad is None or float(pg.grad.abs().sum()) == 0.0, n
+            continue
+        assert pg.grad is not None, n
+        den = float(pw.grad.norm())
+        if den > 0:
+            assert float((pg.grad - pw.grad).norm()) <= 2e-4 * den, (n, float((pg.grad - pw.grad).norm()), den)
+            checked += 1
+    assert checked > 20
+
+    # ---- predict (models.py:245-272): detections in ORIGINAL image coordinates ----
+    with torch.no_grad():
+        dw = base.predict([i.clone() for i in imgs])
+        dg = ours.predict([i.clone() for i in imgs])
+    assert len(dw) == len(dg) == 2
+    for a, b in zip(dg, dw):
+        assert a["boxes"].shape == b["boxes"].shape and a["boxes"].shape[0] > 10
+        assert a["labels"].dtype == torch.int64 and a["scores"].dtype == torch.float32
+        # same device, same expf: scores are bit-identical; the reference's final sort is unstable, so compare per score
+        assert torch.equal(a["scores"], b["scores"])
+        tie = torch.zeros_like(a["scores"], dtype=torch.bool)
+        tie[1:] |= a["scores"][1:] == a["scores"][:-1]
+        tie[:-1] |= a["scores"][:-1] == a["scores"][1:]
+        assert torch.equal(a["labels"][~tie], b["labels"][~tie])
+        assert torch.allclose(a["boxes"][~tie], b["boxes"][~tie], rtol=1e-5, atol=1e-4)
