@@ -75,6 +75,8 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
 
 def _scale_in_place(buf: Tensor, g: Tensor) -> None:
     """buf *= g (device scalar) with one launch whose blocks exit at once when g == 1 (the usual case)."""
+    if buf.numel() == 0:
+        return
     gs = g.detach().to(device=buf.device, dtype=torch.float32).contiguous()
     with _native.on_device(buf.device):
         rc = _native.load().rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
