@@ -57,7 +57,6 @@ struct LossParams {
     long long anchor_stride;
     int C;
     int chunks;
-    unsigned magic;              // ceil(2^32 / (C/VEC))
     float alpha, gamma, beta, batch_div;
     float4 wts;
 };
@@ -81,6 +80,16 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
 
 // One CTA's share of the loss: LOSS_SPAN anchors of image n.  Writes the CTA's partial sums.
 // VEC = 4: C % 4 == 0 and 16-byte aligned rows (128-bit path); VEC = 1: any C (scalar path).
+//
+// The streaming loop knows nothing about targets: EVERY element is accumulated as a negative (and gets the negative's
+// gradient) — no per-vector code load, no index arithmetic, no select.  The per-anchor epilogue then repairs the rows
+// that are not plain negatives, all of them rare: the ONE positive column of a foreground anchor is re-read (L2 hit),
+// its negative term taken back and its gradient element overwritten; the rows of ignore anchors (IoU in the
+// [bg, fg] band) are re-read by their warp, 32 vectors at a time, their contribution subtracted and their gradient
+// rows zeroed.  An image without GT boxes (every anchor is ignore, box_utils.py:70-71) is skipped outright, so its
+// loss is exactly 0.  NB: a NaN / +inf logit inside an IGNORED anchor therefore poisons the sum (inf - inf), where
+// the reference, which drops those rows before any arithmetic, stays finite; everywhere else non-finite logits
+// propagate exactly as in the reference.
 template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
 __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, const int chunk) {
     const long long a0 = (long long)chunk * LOSS_SPAN;
@@ -88,106 +97,137 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     const long long row0 = (long long)n * P.A + a0;
     const int CV = P.C / VEC;                       // vectors per anchor row
     const int nvec = span * CV;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *src = P.logits + row0 * P.C;
+    float *dst = WANT_GRAD ? P.grad_logits + row0 * P.C : nullptr;
+
+    if (__ldg(P.gt_off + n + 1) == __ldg(P.gt_off + n)) {      // no GT: nothing contributes, gradients are zero
+        if (WANT_GRAD) {
+            for (int f = t; f < nvec; f += LOSS_BLOCK) {
+                if (VEC == 4) rn::st_stream_f4((float4 *)dst + f, make_float4(0.f, 0.f, 0.f, 0.f));
+                else dst[f] = 0.0f;
+            }
+            if (t < span) P.grad_bbox[row0 + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (t == 0) {
+            double *o = P.partials + ((long long)n * P.chunks + chunk) * 2;
+            o[0] = 0.0;
+            o[1] = 0.0;
+        }
+        return;
+    }
     const int F = __ldg(P.fg_count + n);
     const float inv = 1.0f / (fmaxf((float)F, 1.0f) * P.batch_div);   // gradient scale
     const float neg_gscale = P.alpha * inv;
-    const float *src = P.logits + row0 * P.C;
-    float *dst = WANT_GRAD ? P.grad_logits + row0 * P.C : nullptr;
-    const int *codes = P.codes + row0;
+    const float x_mid = kMidX - 1.0f;
 
-    float acc_neg = 0.0f;   // sum p^g * softplus(x) over non-ignored elements treated as negatives
-    float acc_pos = 0.0f;   // correction + positive terms (already alpha-weighted)
+    float acc_neg = 0.0f;   // sum p^g * softplus(x), every element treated as a negative
+    float acc_pos = 0.0f;   // positive terms minus what the positives' columns added to acc_neg (alpha-weighted)
 
     for (int base = 0; base < nvec; base += LOSS_BLOCK * LOSS_U) {
         float v[LOSS_U][VEC];
-        int code[LOSS_U], c0[LOSS_U];
-        bool valid[LOSS_U];
 #pragma unroll
         for (int u = 0; u < LOSS_U; ++u) {
-            const int f = base + u * LOSS_BLOCK + threadIdx.x;
-            valid[u] = f < nvec;
-            code[u] = -2;
-            c0[u] = 0;
+            const int f = base + u * LOSS_BLOCK + t;
             if (VEC == 4) {
-                float4 t = make_float4(-30.f, -30.f, -30.f, -30.f);
-                if (valid[u]) t = rn::ld_stream_f4((const float4 *)src + f);
-                v[u][0] = t.x; v[u][VEC > 1 ? 1 : 0] = t.y; v[u][VEC > 2 ? 2 : 0] = t.z; v[u][VEC > 3 ? 3 : 0] = t.w;
+                float4 q = make_float4(-100.f, -100.f, -100.f, -100.f);    // padding: every term is exactly 0
+                if (f < nvec) q = rn::ld_stream_f4((const float4 *)src + f);
+                v[u][0] = q.x; v[u][VEC > 1 ? 1 : 0] = q.y; v[u][VEC > 2 ? 2 : 0] = q.z; v[u][VEC > 3 ? 3 : 0] = q.w;
             } else {
-                v[u][0] = valid[u] ? __ldg(src + f) : -30.f;
-            }
-            if (valid[u]) {
-                const int al = P.magic ? (int)__umulhi((unsigned)f, P.magic) : f;   // f / CV
-                c0[u] = (f - al * CV) * VEC;
-                code[u] = __ldg(codes + al);
+                v[u][0] = f < nvec ? __ldg(src + f) : -100.f;
             }
         }
 #pragma unroll
         for (int u = 0; u < LOSS_U; ++u) {
             float g[VEC];
-            // ignore anchors (and the padding lanes): the logits are replaced by -100, for which p, softplus,
-            // the loss term and the gradient are all exactly 0 — no separate masking below
-            if (code[u] == -2) {
+            bool mid = !PRECISE;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) v[u][k] = -100.0f;
-            }
-            float vmax = v[u][0];
+            for (int k = 0; k < VEC; ++k) mid = mid && (v[u][k] <= x_mid);       // false for NaN
+            float local = 0.0f;
+            if (!PRECISE && __all_sync(0xffffffffu, mid)) {
 #pragma unroll
-            for (int k = 1; k < VEC; ++k) vmax = fmaxf(vmax, v[u][k]);
-            const bool small = !PRECISE && __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
-            float pk[VEC], spk[VEC];
-            if (small) {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) sigmoid_softplus_small(v[u][k], pk[k], spk[k]);
+                for (int k = 0; k < VEC; ++k) {
+                    float wp;
+                    focal_neg_mid<WANT_GRAD, GAMMA2>(v[u][k], P.gamma, local, wp);
+                    g[k] = wp * neg_gscale;
+                }
             } else {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) sigmoid_softplus<PRECISE>(v[u][k] + 1.0f, pk[k], spk[k]);
-            }
-            float local = 0.0f;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                const float w = pow_gamma<GAMMA2>(pk[k], P.gamma);
-                local = fmaf(w, spk[k], local);
-                g[k] = w * pk[k] * neg_gscale;
+                for (int k = 0; k < VEC; ++k) {
+                    float pk, spk;
+                    sigmoid_softplus<PRECISE>(v[u][k] + 1.0f, pk, spk);
+                    const float w = pow_gamma<GAMMA2>(pk, P.gamma);
+                    local = fmaf(w, spk, local);
+                    g[k] = w * pk * neg_gscale;
+                }
             }
             acc_neg += local;
-            const int k = (code[u] >> 20) - c0[u];     // code < 0 -> (code >> 20) == -1 -> k < 0
-            if ((unsigned)k < (unsigned)VEC) {          // this vector holds the anchor's positive column (rare)
-                float x = v[u][0];
-#pragma unroll
-                for (int q = 1; q < VEC; ++q) x = (k == q) ? v[u][q] : x;
-                x += 1.0f;
-                float p, sp;
-                sigmoid_softplus<PRECISE>(x, p, sp);
-                const float wn = pow_gamma<GAMMA2>(p, P.gamma);
-                const float wp = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
-                acc_pos += wp * (sp - x) - P.alpha * wn * sp;   // softplus(-x) = softplus(x) - x
-                const float gp = wp * (p - 1.0f) * inv;
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) g[q] = (k == q) ? gp : g[q];
-            }
-            if (WANT_GRAD && valid[u]) {
-                const int f = base + u * LOSS_BLOCK + threadIdx.x;
-                if (VEC == 4) {
-                    rn::st_stream_f4((float4 *)dst + f, make_float4(g[0], g[VEC > 1 ? 1 : 0], g[VEC > 2 ? 2 : 0],
-                                                                    g[VEC > 3 ? 3 : 0]));
-                } else {
-                    dst[f] = g[0];
+            if (WANT_GRAD) {
+                const int f = base + u * LOSS_BLOCK + t;
+                if (f < nvec) {
+                    if (VEC == 4) {
+                        rn::st_stream_f4((float4 *)dst + f, make_float4(g[0], g[VEC > 1 ? 1 : 0], g[VEC > 2 ? 2 : 0],
+                                                                        g[VEC > 3 ? 3 : 0]));
+                    } else {
+                        dst[f] = g[0];
+                    }
                 }
             }
         }
     }
 
-    // ---- regression: one thread per anchor of the span (losses.py:66-71, 19-27) ----
+    // ---- per-anchor epilogue (thread t <-> anchor t of the span); the gradient rows written above are finished ----
+    if (WANT_GRAD) __syncthreads();
+    const int code = t < span ? __ldg(P.codes + row0 + t) : -1;
+    // (1) ignore anchors: the warp takes their rows back, CV vectors over the 32 lanes
+    unsigned ign = __ballot_sync(0xffffffffu, code == -2);
+    while (ign) {
+        const int arow = warp * 32 + __ffs(ign) - 1;
+        ign &= ign - 1;
+        const float *row = src + (long long)arow * P.C;
+        float sub = 0.0f;
+        for (int j = lane; j < CV; j += 32) {
+            float q[VEC];
+            if (VEC == 4) {
+                const float4 w4 = __ldg((const float4 *)row + j);
+                q[0] = w4.x; q[VEC > 1 ? 1 : 0] = w4.y; q[VEC > 2 ? 2 : 0] = w4.z; q[VEC > 3 ? 3 : 0] = w4.w;
+            } else {
+                q[0] = __ldg(row + j);
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float pk, spk;
+                sigmoid_softplus<PRECISE>(q[k] + 1.0f, pk, spk);
+                sub = fmaf(pow_gamma<GAMMA2>(pk, P.gamma), spk, sub);
+            }
+            if (WANT_GRAD) {
+                float *grow = dst + (long long)arow * P.C;
+                if (VEC == 4) ((float4 *)grow)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else grow[j] = 0.0f;
+            }
+        }
+        acc_neg -= sub;
+    }
+    // (2) foreground anchors: the positive column (losses.py:96-105) and the regression term (losses.py:66-71, 19-27)
     float reg = 0.0f;
-    if (threadIdx.x < span) {
-        const int code = __ldg(codes + threadIdx.x);
+    if (t < span) {
         float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (code >= 0) {
+            const int cls = code >> 20;
+            if (cls < P.C) {                       // cls = kNoClass (label outside 1..C): all-negative class targets
+                const float x = __ldg(src + (long long)t * P.C + cls) + 1.0f;
+                float p, sp;
+                sigmoid_softplus<PRECISE>(x, p, sp);
+                const float wn = pow_gamma<GAMMA2>(p, P.gamma);
+                const float wpos = pow_gamma<GAMMA2>(1.0f - p, P.gamma) * (1.0f - P.alpha);
+                acc_pos += wpos * (sp - x) - P.alpha * wn * sp;   // softplus(-x) = softplus(x) - x
+                if (WANT_GRAD) dst[(long long)t * P.C + cls] = wpos * (p - 1.0f) * inv;
+            }
             const float4 gtb = P.gt[P.gt_off[n] + (code & 0xFFFFF)];
-            const float4 an = P.anchors[(long long)n * P.anchor_stride + a0 + threadIdx.x];
-            const float4 pr = P.bbox[row0 + threadIdx.x];
-            const float4 t = rn::encode_box(gtb, an, P.wts);
-            const float d[4] = {pr.x - t.x, pr.y - t.y, pr.z - t.z, pr.w - t.w};
+            const float4 an = P.anchors[(long long)n * P.anchor_stride + a0 + t];
+            const float4 pr = P.bbox[row0 + t];
+            const float4 tt = rn::encode_box(gtb, an, P.wts);
+            const float d[4] = {pr.x - tt.x, pr.y - tt.y, pr.z - tt.z, pr.w - tt.w};
             float gr[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -205,7 +245,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
             }
             gb = make_float4(gr[0], gr[1], gr[2], gr[3]);
         }
-        if (WANT_GRAD) P.grad_bbox[row0 + threadIdx.x] = gb;
+        if (WANT_GRAD) P.grad_bbox[row0 + t] = gb;
     }
 
     double s_neg = acc_neg, s_pos = acc_pos, s_reg = reg;
@@ -471,8 +511,6 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
     P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
     const bool vec4 = (C % 4 == 0) && (((uintptr_t)logits & 15) == 0) && (!grad_logits || ((uintptr_t)grad_logits & 15) == 0);
-    const int CV = vec4 ? C / 4 : C;
-    P.magic = CV == 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned)CV - 1) / (unsigned)CV);
     dim3 grid((unsigned)P.chunks, (unsigned)N);
     const bool precise = g_math_mode == 1;
     if (vec4) {
@@ -630,22 +668,26 @@ __device__ __forceinline__ void loss_levels_body(const LvlLossParams &P, const L
                 float x[4], g[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) x[k] = ign[pu][k] ? -100.0f : v[cu][pu][k];
-                const float vmax = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
-                const bool small = __all_sync(0xffffffffu, vmax <= kSmallX - 1.0f);
-                float local = 0.0f;
-                float pk[4], spk[4];
-                if (small) {
+                bool mid = true;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) sigmoid_softplus_small(x[k], pk[k], spk[k]);
+                for (int k = 0; k < 4; ++k) mid = mid && (x[k] <= kMidX - 1.0f);       // false for NaN
+                float local = 0.0f;
+                if (__all_sync(0xffffffffu, mid)) {            // every element as a negative; positives are patched after the walk
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float wp;
+                        focal_neg_mid<WANT_GRAD, GAMMA2>(x[k], P.gamma, local, wp);
+                        g[k] = wp * neg_gscale;
+                    }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) sigmoid_softplus<false>(x[k] + 1.0f, pk[k], spk[k]);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {      // every element as a negative; the (rare) positives are patched after the walk
-                    const float w = pow_gamma<GAMMA2>(pk[k], P.gamma);
-                    local = fmaf(w, spk[k], local);
-                    g[k] = w * pk[k] * neg_gscale;
+                    for (int k = 0; k < 4; ++k) {
+                        float pk, spk;
+                        sigmoid_softplus<false>(x[k] + 1.0f, pk, spk);
+                        const float w = pow_gamma<GAMMA2>(pk, P.gamma);
+                        local = fmaf(w, spk, local);
+                        g[k] = w * pk * neg_gscale;
+                    }
                 }
                 acc_neg += local;
                 if (WANT_GRAD) {

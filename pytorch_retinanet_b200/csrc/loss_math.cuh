@@ -7,7 +7,6 @@ namespace rnloss {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kSmallE = 0.0625f;               // series path valid for e <= 1/16
-constexpr float kSmallX = -2.7725887f;           // x <= ln(1/16)
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -51,11 +50,47 @@ __device__ __forceinline__ void sigmoid_softplus(float x, float &p, float &sp) {
         sp = fmaxf(x, 0.0f) + l;
     }
 }
-// warp-uniform small-x path (x <= -2.77): e = exp(x) <= 1/16
-__device__ __forceinline__ void sigmoid_softplus_small(float v, float &p, float &sp) {
-    float e = ex2_approx(fmaf(v, kLog2e, kLog2e));   // exp(v + 1)
-    p = e * rcp_approx(1.0f + e);
-    sp = log1p_small(e);
+
+template <bool GAMMA2>
+__device__ __forceinline__ float pow_gamma(float b, float gamma);
+
+// ---- the warp-uniform "mid" path: every logit of the warp's vectors has x = v + 1 <= ln(1/4), i.e. e = exp(x) <= 1/4
+// (with logits ~ N(-7, 1.3) that is > 97 % of all warp-vectors; the old e <= 1/16 test passed 43 %).
+// Negative-class focal term  p^gamma * softplus(x)  with p = e/(1+e), softplus(x) = log1p(e):
+//   forward only, gamma = 2:  e^3 * H(e),  H(e) = log1p(e) / (e (1+e)^2)   — no reciprocal, 1 MUFU + 10 FP32 ops/element
+//   otherwise:                w * e * L(e), L(e) = log1p(e) / e, w = p^gamma, and the gradient factor w * p
+// H (degree 6) and L (degree 5) are Chebyshev-node interpolants on [0, 1/4]: relative error 6.5e-8 / 9.3e-9 in exact
+// arithmetic, ~2e-7 worst case in fp32 Horner (rounding, which averages out over the sum).
+constexpr float kMidX = -1.3862944f;             // ln(1/4); the kernels test the raw logit v <= kMidX - 1
+__device__ __forceinline__ float poly_H(float e) {
+    float h = fmaf(e, 5.274976224e+00f, -8.772363433e+00f);
+    h = fmaf(e, h, 8.332900750e+00f);
+    h = fmaf(e, h, -6.386249143e+00f);
+    h = fmaf(e, h, 4.332104384e+00f);
+    h = fmaf(e, h, -2.499981092e+00f);
+    return fmaf(e, h, 9.999999519e-01f);
+}
+__device__ __forceinline__ float poly_L(float e) {
+    float l = fmaf(e, -9.216756000e-02f, 1.815955511e-01f);
+    l = fmaf(e, l, -2.477561514e-01f);
+    l = fmaf(e, l, 3.332059974e-01f);
+    l = fmaf(e, l, -4.999973132e-01f);
+    return fmaf(e, l, 9.999999907e-01f);
+}
+// acc += term of raw logit v (x = v + 1); wp = w * p (the gradient is wp * alpha / (max(1,F) * batch)), only if WANT_GRAD
+template <bool WANT_GRAD, bool GAMMA2>
+__device__ __forceinline__ void focal_neg_mid(float v, float gamma, float &acc, float &wp) {
+    const float e = ex2_approx(fmaf(v, kLog2e, kLog2e));       // exp(v + 1)
+    if (!WANT_GRAD && GAMMA2) {
+        const float e2 = e * e;
+        acc = fmaf(e2 * e, poly_H(e), acc);
+        wp = 0.0f;
+    } else {
+        const float p = e * rcp_approx(1.0f + e);
+        const float w = pow_gamma<GAMMA2>(p, gamma);
+        acc = fmaf(w, e * poly_L(e), acc);
+        wp = w * p;
+    }
 }
 
 template <bool GAMMA2>

@@ -12,8 +12,9 @@ b = S.make_batch(cfg, 0, n)
 anc = b["anchors"].to(dev); x = b["cls_preds"].to(dev); bb = b["bbox_preds"].to(dev)
 tg = [{k: v.to(dev) for k, v in t.items()} for t in b["targets"]]
 packed = PackedTargets([t["boxes"] for t in tg], [t["labels"] for t in tg], dev)
-def t(fn, reps=50):
-    for _ in range(5): fn()
+REPS = int(os.environ.get("RN_REPS", "50"))
+def t(fn, reps=REPS):
+    for _ in range(min(5, reps)): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
