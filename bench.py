@@ -652,7 +652,9 @@ def parity_check(P, HotPathGraph, losses_cls, xch, rank, world, dev, dist):
         return float(((a - ref).abs() / (atol / rtol + ref.abs())).max())
 
     grad_err = close_err(xg.grad.cpu(), xo.grad[lo:lo + per], 2e-5, 1e-12)
-    gbox_err = close_err(bg.grad.cpu(), bo.grad[lo:lo + per], 2e-5, 1e-9)
+    # d(smooth-L1)/d(pred) = (pred - target) / beta / (F * N): the target's fp32 log differs by 1 ulp between the CPU
+    # and the GPU libm, which the subtraction turns into an ABSOLUTE error of ~1e-8 on gradients of ~1e-4
+    gbox_err = close_err(bg.grad.cpu(), bo.grad[lo:lo + per], 2e-5, 2e-8)
     ok = same and loss_err <= 1e-5 and grad_err <= 2e-5 and gbox_err <= 2e-5
     stats = torch.tensor([loss_err, grad_err, gbox_err, 0.0 if ok else 1.0], device=dev)
     if world > 1:
@@ -664,7 +666,7 @@ def parity_check(P, HotPathGraph, losses_cls, xch, rank, world, dev, dist):
             "graph_equals_dropin": same, "images": n_tot,
             "what": "global loss of 2 images/rank (config-1 shape) through HotPathGraph and ShardedRetinaNetLosses vs the CPU "
                     "oracle on the whole batch; max over ranks; losses: relative error <= 1e-5; gradients: |a-ref| / (atol/rtol + |ref|) "
-                    "<= rtol = 2e-5 with atol 1e-12 (logits) / 1e-9 (boxes), i.e. torch.allclose"}
+                    "<= rtol = 2e-5 with atol 1e-12 (logits) / 2e-8 (boxes), i.e. torch.allclose"}
 
 
 def levels_leg(S, HotPathGraph, cfg, h_cls, h_box, dev, anc, packed, batch, targets, C, n_img, gsum_max, timed, args):

@@ -52,7 +52,8 @@ struct LossParams {
     const int *fg_count;
     float *grad_logits;
     float4 *grad_bbox;
-    double *partials;            // [N][chunks][3]
+    double *partials;            // [N][chunks][2]
+    unsigned *ticket;            // the final reduction's ticket: re-armed here, so no memset node is needed
     long long A;
     long long anchor_stride;
     int C;
@@ -120,6 +121,10 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     const float inv = 1.0f / (fmaxf((float)F, 1.0f) * P.batch_div);   // gradient scale
     const float neg_gscale = P.alpha * inv;
     const float x_mid = kMidX - 1.0f;
+    // this thread's anchor of the epilogue: fetched now, so that its dependent loads (GT box, logit of the positive
+    // column) are one memory round trip after the streaming loop instead of two
+    const int code = t < span ? __ldg(P.codes + row0 + t) : -1;
+    const int gt0 = __ldg(P.gt_off + n);
 
     float acc_neg = 0.0f;   // sum p^g * softplus(x), every element treated as a negative
     float acc_pos = 0.0f;   // positive terms minus what the positives' columns added to acc_neg (alpha-weighted)
@@ -178,7 +183,6 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
 
     // ---- per-anchor epilogue (thread t <-> anchor t of the span); the gradient rows written above are finished ----
     if (WANT_GRAD) __syncthreads();
-    const int code = t < span ? __ldg(P.codes + row0 + t) : -1;
     // (1) ignore anchors: the warp takes their rows back, CV vectors over the 32 lanes
     unsigned ign = __ballot_sync(0xffffffffu, code == -2);
     while (ign) {
@@ -223,7 +227,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
                 acc_pos += wpos * (sp - x) - P.alpha * wn * sp;   // softplus(-x) = softplus(x) - x
                 if (WANT_GRAD) dst[(long long)t * P.C + cls] = wpos * (p - 1.0f) * inv;
             }
-            const float4 gtb = P.gt[P.gt_off[n] + (code & 0xFFFFF)];
+            const float4 gtb = P.gt[gt0 + (code & 0xFFFFF)];
             const float4 an = P.anchors[(long long)n * P.anchor_stride + a0 + t];
             const float4 pr = P.bbox[row0 + t];
             const float4 tt = rn::encode_box(gtb, an, P.wts);
@@ -259,6 +263,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
 
 template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
 __global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : LOSS_MINB) loss_kernel(const LossParams P) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.ticket = 0u;   // loss_finalize_kernel runs after this grid
     loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE>(P, blockIdx.y, blockIdx.x);
 }
 
@@ -348,10 +353,12 @@ __device__ __forceinline__ void finalize_image(const double *partials, const int
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const double2 *p = (const double2 *)partials + (long long)n * chunks;
     double c = 0.0, r = 0.0;
-    for (int k = t; k < chunks; k += FIN_BLOCK) {
-        const double2 v = __ldcg(p + k);
-        c += v.x;
-        r += v.y;
+    for (int k = t; k < chunks; k += 4 * FIN_BLOCK) {          // 4 independent loads in flight; fixed summation order
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = k + u * FIN_BLOCK < chunks ? __ldcg(p + k + u * FIN_BLOCK) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { c += v[u].x; r += v[u].y; }
     }
     c = rn::warp_sum(c);
     r = rn::warp_sum(r);
@@ -378,17 +385,33 @@ __device__ __forceinline__ void finalize_image(const double *partials, const int
     }
     __syncthreads();
     if (!s_last) return;                                        // block-uniform
+    // the last block sums the images in index order: FIN_BLOCK of them are fetched at a time (one round trip), thread 0
+    // adds them up serially from shared memory
+    __shared__ double s_ic[FIN_BLOCK], s_ir[FIN_BLOCK];
+    __shared__ int s_if[FIN_BLOCK];
+    double cs = 0.0, rs = 0.0;
+    long long fsum = 0;
+    __threadfence();
+    for (int i0 = 0; i0 < N; i0 += FIN_BLOCK) {
+        const int i = i0 + t;
+        if (i < N) {
+            const volatile double *vt = tail;
+            s_ic[t] = vt[2 * i];
+            s_ir[t] = vt[2 * i + 1];
+            s_if[t] = __ldcg(fg_count + i);
+        }
+        __syncthreads();
+        if (t == 0) {
+            const int m = min(FIN_BLOCK, N - i0);
+            for (int q = 0; q < m; ++q) { cs += s_ic[q]; rs += s_ir[q]; fsum += s_if[q]; }
+        }
+        __syncthreads();
+    }
     if (t == 0) {
-        __threadfence();
-        double cs = 0.0, rs = 0.0;
-        long long fsum = 0;
-        const volatile double *vt = tail;
-        for (int i = 0; i < N; ++i) { cs += vt[2 * i]; rs += vt[2 * i + 1]; fsum += __ldcg(fg_count + i); }
         s_v[0] = (float)(cs / (double)batch_div);               // losses.py:138-140
         s_v[1] = (float)(rs / (double)batch_div);
         s_v[2] = (float)fsum;                                   // sum_n F_n   } carried for the image-sharded
         s_v[3] = (float)N;                                      // local images } exchange
-        *ticket = 0u;
         if (X.world <= 1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) out_total[k] = s_v[k];
@@ -507,6 +530,7 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     P.logits = logits; P.bbox = (const float4 *)bbox; P.anchors = (const float4 *)anchors;
     P.gt = (const float4 *)gt_boxes; P.gt_off = gt_off; P.codes = codes; P.fg_count = fg_count;
     P.grad_logits = grad_logits; P.grad_bbox = (float4 *)grad_bbox; P.partials = (double *)workspace;
+    P.ticket = (unsigned *)((double *)workspace + (size_t)N * loss_chunks(A) * 2 + 2 * (size_t)N);
     P.A = A; P.anchor_stride = anchor_image_stride; P.C = C; P.chunks = loss_chunks(A);
     P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
     P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
@@ -521,8 +545,6 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     RN_CHECK_LAUNCH("rn_loss");
     {
         double *tail = (double *)workspace + (size_t)N * P.chunks * 2;
-        cudaError_t e = cudaMemsetAsync(tail + 2 * (size_t)N, 0, sizeof(unsigned), s);
-        if (e != cudaSuccess) { rn_set_error("rn_loss: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
         loss_finalize_kernel<<<N, FIN_BLOCK, 0, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
                                                      out_total, tail, X);
     }

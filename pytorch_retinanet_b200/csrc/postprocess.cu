@@ -32,6 +32,8 @@
 //  K5 image_topk     one CTA per image: 4-pass 8-bit radix select of the max_det-th score over
 //                    all kept boxes, deterministic tie handling (class asc, anchor asc), bitonic
 //                    sort of the <= max_det winners, output write (labels + 1).
+#include <cstring>
+
 #include "rn_common.cuh"
 
 namespace {
@@ -55,6 +57,7 @@ constexpr int LZ_CHUNK = 256;
 struct PPWorkspace {
     u32 *pool_count;     // [1] candidates found (may exceed capacity)
     u32 *img_count;      // [N] candidates found per image (LAZY; may exceed cap_n)
+    int *need_v1;        // [N] LAZY: image left to lazy_nms_kernel by lazy2_nms_kernel
     int *seg_count;      // [S]
     int *seg_off;        // [S+1]
     int *cursor;         // [S]
@@ -77,6 +80,7 @@ PPWorkspace carve(void *base, int N, int C, int64_t cap) {
     size_t o = 0;
     w.pool_count = (u32 *)(p + o); o += 256;
     w.img_count = (u32 *)(p + o); o = align_up(o + (size_t)N * 4, 256);
+    w.need_v1 = (int *)(p + o); o = align_up(o + (size_t)N * 4, 256);
     w.seg_count = (int *)(p + o); o = align_up(o + S * 4, 256);
     w.zero_bytes = o;
     w.seg_off = (int *)(p + o); o = align_up(o + (S + 1) * 4, 256);
@@ -548,6 +552,8 @@ struct LazyParams {
     int topk;                // pre_nms_topk per (image, pyramid level); 0 = off (reference behaviour)
     int nlev;
     long long lvl_off[RN_MAX_LEVELS + 1];   // anchor offsets of the pyramid levels
+    int *need_v1;            // [N] or null: written by lazy2_nms_kernel (1 = image left to lazy_nms_kernel), read by lazy_nms_kernel
+    int bin_shift;           // lazy2: score-bin width (see lazy2_nms_kernel)
 };
 
 struct LazySmem {
@@ -576,6 +582,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     u64 *s_cand = reinterpret_cast<u64 *>(lz_raw + ((sizeof(LazySmem) + 15) & ~(size_t)15));
 
     const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (P.need_v1 && P.need_v1[n] == 0) return;     // lazy2_nms_kernel finished this image
 #ifdef RN_LAZY_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
     int n_rounds = 0, n_chunks = 0;
@@ -877,6 +884,304 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
 #undef LZ_TICK
 }
 
+// ------------------------------------------------------------------------------------------- LAZY v2
+// The common case of the lazy algorithm without a selection sort and without a serial suppression scan.
+// One CTA per image, three ideas:
+//  * the top of the global order comes from a COUNTING SORT on score bins: one histogram pass over the image's
+//    candidate keys (2048 bins between the score threshold and 1.0), a block scan picks the largest prefix of bins
+//    that fits LZ2_CAP candidates, one scatter pass groups that prefix by bin, and every key ranks itself inside its
+//    (small) bin — the prefix is then in exact global order (score desc, class asc, anchor asc);
+//  * greedy NMS is independent per class (a candidate's fate depends only on higher-ranked candidates of ITS class),
+//    so the prefix is regrouped by class with a stable counting sort (per-32-chunk class counts + a column scan) and
+//    the 32 warps of the CTA run the classes in parallel: 32 candidates at a time against the class's kept list, the
+//    32x32 in-chunk conflicts resolved in registers by the REDUX fixed-point iteration of lazy_nms_kernel;
+//  * the kept flags, indexed by global rank, are compacted by a block scan: the first max_det kept candidates ARE
+//    the reference's output (models.py:193-240 with the documented tie rule).
+// pre_nms_topk (extension): a candidate is eligible iff fewer than k candidates of its pyramid level rank above it — a
+// second per-chunk count table, over the levels, gives that rank.
+// Exactness is never traded: whatever this kernel cannot finish — more than LZ2_MAXC classes, a score
+// bin with more than LZ2_BIN_MAX entries (mass ties), or fewer than max_det survivors while candidates remain beyond
+// the prefix — is flagged in need_v1[n] and redone from scratch by lazy_nms_kernel (launched right behind, its CTAs
+// exit at once for finished images), which in turn can hand over to the general algorithm.
+constexpr int LZ2_BLOCK = 1024;
+constexpr int LZ2_CAP = 4096;                 // candidates of the prefix
+constexpr int LZ2_BINS = 2048;
+constexpr int LZ2_MAXC = 128;                 // classes
+constexpr int LZ2_CHUNKS = LZ2_CAP / 32;
+constexpr int LZ2_BIN_MAX = 256;              // heaviest bin ranked in place (quadratic in the bin size)
+
+struct Lazy2Smem {
+    u64 key[LZ2_CAP];                         // the prefix in global order (rank -> key)
+    float4 box[LZ2_CAP];                      // class-grouped order (also the scatter target of the counting sort, as u64)
+    float area[LZ2_CAP];
+    unsigned short rank_of[LZ2_CAP];          // grouped position -> rank
+    unsigned short pos_of[LZ2_CAP];           // rank -> grouped position
+    unsigned short kidx[LZ2_CAP];             // per class segment: grouped positions of the kept boxes, in order
+    unsigned char ok[LZ2_CAP];                // grouped: passes remove_small_boxes
+    unsigned char kept[LZ2_CAP];              // by rank
+    u32 hist[LZ2_BINS];                       // bin counts, then scatter cursors (= inclusive prefix when done)
+    unsigned short ctab[LZ2_CHUNKS][LZ2_MAXC];   // class counts per 32-rank chunk, then exclusive prefix over the chunks
+    int cls_base[LZ2_MAXC + 1];
+    unsigned short ltab[LZ2_CHUNKS][RN_MAX_LEVELS];   // pre_nms_topk: level counts per chunk, then exclusive prefix
+    int lvl_total[RN_MAX_LEVELS];
+    int warp_tot[32];
+    int cut_bin, prefix, next_cls, heavy, total_kept;
+};
+
+// exclusive block scan of one int per thread (LZ2_BLOCK threads); returns the exclusive prefix, `total` = block sum
+__device__ __forceinline__ int lz2_block_scan(int v, int *warp_tot, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();                          // warp_tot may still be read from a previous call
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+    }
+    total = __shfl_sync(0xffffffffu, w, 31);
+    const int before = warp ? __shfl_sync(0xffffffffu, w, warp - 1) : 0;
+    return before + x - v;
+}
+
+__global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_constant__ LazyParams P) {
+    extern __shared__ __align__(16) unsigned char lz2_raw[];
+    Lazy2Smem &S = *reinterpret_cast<Lazy2Smem *>(lz2_raw);
+    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u32 found = P.img_count[n];
+    if (t == 0) {
+        const unsigned long long scaled = (unsigned long long)found * (unsigned long long)P.N;
+        atomicMax(P.status + 0, (int)min(scaled, 0x7fffffffULL));
+    }
+    const int K = (int)min(found, P.cap_n);
+    if (K == 0) {
+        if (t == 0) { P.out_count[n] = 0; P.need_v1[n] = 0; }
+        return;
+    }
+    const u64 *cand = P.cand_key + (size_t)n * P.cap_n;
+    const u32 hi0 = 0xC07FFFFFu;              // ~bits(1.0f): the smallest possible upper key half
+    const int shift = P.bin_shift;
+    auto bin_of = [&](u64 k) -> int {
+        const u32 hi = (u32)(k >> 32);
+        return hi <= hi0 ? 0 : (int)min((hi - hi0) >> shift, (u32)(LZ2_BINS - 1));
+    };
+
+    // ---- (1) histogram of the score bins ----
+    for (int i = t; i < LZ2_BINS; i += LZ2_BLOCK) S.hist[i] = 0;
+    for (int i = t; i < LZ2_CAP; i += LZ2_BLOCK) S.kept[i] = 0;
+    if (t == 0) { S.cut_bin = -1; S.prefix = 0; S.next_cls = 0; S.heavy = 0; }
+    __syncthreads();
+    for (int i = t; i < K; i += LZ2_BLOCK) atomicAdd(&S.hist[bin_of(__ldg(cand + i))], 1u);
+    __syncthreads();
+    // ---- (2) largest prefix of bins holding <= LZ2_CAP candidates; hist becomes the scatter cursor ----
+    {
+        const int c0 = (int)S.hist[2 * t], c1 = (int)S.hist[2 * t + 1];
+        int total;
+        const int ex = lz2_block_scan(c0 + c1, S.warp_tot, total);
+        const int in0 = ex + c0, in1 = in0 + c1;           // inclusive prefix after bin 2t / 2t+1 (monotone)
+        if (in1 <= LZ2_CAP) atomicMax(&S.cut_bin, 2 * t + 1);
+        else if (in0 <= LZ2_CAP) atomicMax(&S.cut_bin, 2 * t);
+        if ((c0 > LZ2_BIN_MAX && in0 <= LZ2_CAP) || (c1 > LZ2_BIN_MAX && in1 <= LZ2_CAP)) S.heavy = 1;
+        __syncthreads();
+        if (S.cut_bin == 2 * t) S.prefix = in0;
+        if (S.cut_bin == 2 * t + 1) S.prefix = in1;
+        S.hist[2 * t] = (u32)ex;
+        S.hist[2 * t + 1] = (u32)in0;
+    }
+    __syncthreads();
+    const int cut = S.cut_bin, Pn = S.prefix;
+    if (cut < 0 || S.heavy || Pn == 0) {      // first bin alone overflows / mass ties: not for this kernel
+        if (t == 0) P.need_v1[n] = 1;
+        return;
+    }
+    // ---- (3) scatter the prefix by bin, then every key ranks itself inside its bin ----
+    u64 *tmp = reinterpret_cast<u64 *>(S.box);
+    for (int i = t; i < K; i += LZ2_BLOCK) {
+        const u64 k = __ldg(cand + i);
+        const int b = bin_of(k);
+        if (b <= cut) tmp[atomicAdd(&S.hist[b], 1u)] = k;
+    }
+    __syncthreads();
+    for (int i = t; i < Pn; i += LZ2_BLOCK) {
+        const u64 k = tmp[i];
+        const int b = bin_of(k);
+        const int lo = b ? (int)S.hist[b - 1] : 0, hi = (int)S.hist[b];     // cursors now sit at the bins' ends
+        int r = lo;
+        for (int q = lo; q < hi; ++q) r += tmp[q] < k;
+        S.key[r] = k;
+    }
+    __syncthreads();
+    // ---- (4) class of every ranked candidate; stable regrouping by class; decode into the grouped arrays ----
+    const int C = P.C;
+    const u32 A32 = (u32)P.A;
+    const int nchunks = (Pn + 31) >> 5;
+    for (int i = t; i < nchunks * LZ2_MAXC; i += LZ2_BLOCK) S.ctab[i / LZ2_MAXC][i % LZ2_MAXC] = 0;
+    for (int i = t; i < nchunks * RN_MAX_LEVELS; i += LZ2_BLOCK) S.ltab[i / RN_MAX_LEVELS][i % RN_MAX_LEVELS] = 0;
+    __syncthreads();
+    const bool topk = P.topk > 0;
+    int my_lvl[LZ2_CHUNKS / 32], my_lric[LZ2_CHUNKS / 32];
+    int my_cls[LZ2_CHUNKS / 32], my_ric[LZ2_CHUNKS / 32];
+#pragma unroll
+    for (int q = 0; q < LZ2_CHUNKS / 32; ++q) {
+        const int chunk = warp + 32 * q, r = chunk * 32 + lane;
+        my_cls[q] = -1;
+        my_ric[q] = 0;
+        if (chunk < nchunks) {                                  // warp-uniform
+            const int cls = r < Pn ? (int)((u32)S.key[r] / A32) : -1;
+            const u32 peers = __match_any_sync(0xffffffffu, cls);
+            my_cls[q] = cls;
+            my_ric[q] = __popc(peers & ((1u << lane) - 1u));
+            if (cls >= 0 && lane == __ffs(peers) - 1) S.ctab[chunk][cls] = (unsigned short)__popc(peers);
+            my_lvl[q] = -1;
+            my_lric[q] = 0;
+            if (topk) {                                         // rank of the candidate inside its pyramid level
+                int lvl = -1;
+                if (cls >= 0) {
+                    const long long anchor = (long long)((u32)S.key[r] - (u32)cls * A32);
+                    lvl = 0;
+                    for (int l = 1; l < P.nlev; ++l) lvl += anchor >= P.lvl_off[l];
+                }
+                const u32 lp = __match_any_sync(0xffffffffu, lvl);
+                my_lvl[q] = lvl;
+                my_lric[q] = __popc(lp & ((1u << lane) - 1u));
+                if (lvl >= 0 && lane == __ffs(lp) - 1) S.ltab[chunk][lvl] = (unsigned short)__popc(lp);
+            }
+        }
+    }
+    __syncthreads();
+    int ccount = 0;
+    if (t < C) {
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int v = S.ctab[ch][t];
+            S.ctab[ch][t] = (unsigned short)ccount;
+            ccount += v;
+        }
+    }
+    if (topk && t >= LZ2_BLOCK - RN_MAX_LEVELS) {               // the last warp's lanes scan the level columns
+        const int l = t - (LZ2_BLOCK - RN_MAX_LEVELS);
+        int run = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int v = S.ltab[ch][l];
+            S.ltab[ch][l] = (unsigned short)run;
+            run += v;
+        }
+        S.lvl_total[l] = run;
+    }
+    {
+        int total;
+        const int ex = lz2_block_scan(t < C ? ccount : 0, S.warp_tot, total);
+        if (t < C) S.cls_base[t] = ex;
+        if (t == 0) S.cls_base[C] = total;
+    }
+    __syncthreads();
+    const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
+    const long long anc_row = (long long)n * P.anchor_stride;
+#pragma unroll
+    for (int q = 0; q < LZ2_CHUNKS / 32; ++q) {
+        const int chunk = warp + 32 * q, r = chunk * 32 + lane, cls = my_cls[q];
+        if (cls >= 0) {
+            const int g = S.cls_base[cls] + S.ctab[chunk][cls] + my_ric[q];
+            const long long anchor = (long long)((u32)S.key[r] - (u32)cls * A32);
+            const float4 b = decode_clip(P.box, n, P.A, anchor, P.anchors, anc_row + anchor, P.wts, imw, imh);
+            S.box[g] = b;
+            S.area[g] = nms_area(b);
+            bool ok = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);    // remove_small_boxes, models.py:203
+            if (topk) ok = ok && (S.ltab[chunk][my_lvl[q]] + my_lric[q] < P.topk);         // only the level's top-k scores
+            S.ok[g] = ok;
+            S.rank_of[g] = (unsigned short)r;
+            S.pos_of[r] = (unsigned short)g;
+        }
+    }
+    __syncthreads();
+    // ---- (5) greedy NMS, one warp per class at a time ----
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&S.next_cls, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= C) break;
+        const int base = S.cls_base[c], nc = S.cls_base[c + 1] - base;
+        int kc = 0;                                               // kept so far in this class
+        for (int s0 = 0; s0 < nc && kc < P.max_det; s0 += 32) {
+            const int j = s0 + lane;
+            const bool valid = j < nc;
+            const float4 b = valid ? S.box[base + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ar = valid ? S.area[base + j] : 0.f;
+            bool alive = valid && S.ok[base + j];
+            for (int k = 0; k < kc; ++k) {                        // boxes kept in earlier chunks of the class
+                const int kp = S.kidx[base + k];
+                if (alive && nms_suppresses(S.box[kp], S.area[kp], b, ar, P.thr)) alive = false;
+            }
+            const u32 am = __ballot_sync(0xffffffffu, alive);
+            u32 diag = 0;                                         // later boxes of this chunk that box `lane` suppresses
+            if (am & (am - 1)) {                                  // at least two alive
+                u32 rest = am;
+                while (rest) {
+                    const int jj = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    if (alive && jj > lane && nms_suppresses(b, ar, S.box[base + s0 + jj], S.area[base + s0 + jj], P.thr))
+                        diag |= 1u << jj;
+                }
+            }
+            bool kp = alive;
+#pragma unroll 1
+            for (int sweep = 0; sweep < 32; ++sweep) {            // fixed point of kept = alive & no kept earlier conflict
+                const u32 rem = __reduce_or_sync(0xffffffffu, kp ? diag : 0u);
+                const bool nk = alive && !((rem >> lane) & 1u);
+                const bool changed = nk != kp;
+                kp = nk;
+                if (!__any_sync(0xffffffffu, changed)) break;
+            }
+            const u32 km = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                S.kidx[base + kc + __popc(km & ((1u << lane) - 1u))] = (unsigned short)(base + j);
+                S.kept[S.rank_of[base + j]] = 1;
+            }
+            kc += __popc(km);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- (6) the first max_det kept candidates in global order ----
+    {
+        const int r0 = 4 * t;                                     // LZ2_CAP = 4 * LZ2_BLOCK
+        int f[4], cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { f[q] = (r0 + q < Pn) ? S.kept[r0 + q] : 0; cnt += f[q]; }
+        int total;
+        int pos = lz2_block_scan(cnt, S.warp_tot, total);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (f[q]) {
+                if (pos < P.max_det) {
+                    const u64 k = S.key[r0 + q];
+                    const long long o = (long long)n * P.max_det + pos;
+                    ((float4 *)P.out_boxes)[o] = finish_box(S.box[S.pos_of[r0 + q]], P.out_ratio, n, P.out_format);
+                    P.out_scores[o] = __uint_as_float(~(u32)(k >> 32));
+                    P.out_labels[o] = (long long)((u32)k / A32) + 1;          // models.py:230 labels + 1
+                }
+                ++pos;
+            }
+        }
+        if (t == 0) {
+            bool unfinished = total < P.max_det && Pn < K;        // survivors may hide beyond the prefix ...
+            if (unfinished && topk) {                             // ... unless every level already saw its k candidates
+                bool full = true;
+                for (int l = 0; l < P.nlev; ++l) full = full && S.lvl_total[l] >= P.topk;
+                unfinished = !full;
+            }
+            P.out_count[n] = min(total, P.max_det);
+            P.need_v1[n] = unfinished ? 1 : 0;
+        }
+    }
+}
+
 __global__ void set_status_capacity_kernel(int *status, int capacity) { status[1] = capacity; }
 
 // ------------------------------------------------------------------------------------------- K5
@@ -1106,7 +1411,7 @@ extern "C" size_t rn_postprocess_workspace_bytes(int N, int64_t A, int C, int64_
 
 // Everything after the streaming filter (shared by the [N,A,C] and the per-level entry points).
 static int pp_tail(const PPWorkspace &w, const FilterParams &F, const BoxSource &box, const float *anchors,
-                   int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A, int C, double nms_thr,
+                   int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A, int C, float score_thr, double nms_thr,
                    int max_det, int pre_nms_topk, const int64_t *level_off_host, int num_levels, bool lazy,
                    int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
                    int32_t *out_count, int32_t *out_status, const float *out_ratio_hw, int out_format, cudaStream_t s) {
@@ -1124,6 +1429,25 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const BoxSource 
         Z.out_ratio = out_ratio_hw; Z.out_format = out_format;
         for (int l = 0; l <= RN_MAX_LEVELS; ++l)
             Z.lvl_off[l] = (pre_nms_topk && l <= num_levels) ? (long long)level_off_host[l] : (long long)A;
+        Z.need_v1 = nullptr;
+        Z.bin_shift = 0;
+        if (C <= LZ2_MAXC && w.need_v1) {
+            // score bins of lazy2_nms_kernel: LZ2_BINS equal-width bins (in float bit patterns) between thr and 1.0
+            const float thr_pos = score_thr > 0.0f ? score_thr : 0.0f;
+            uint32_t lo_bits, one_bits;
+            const float one = 1.0f;
+            memcpy(&lo_bits, &thr_pos, 4);
+            memcpy(&one_bits, &one, 4);
+            const uint32_t range = one_bits > lo_bits ? one_bits - lo_bits : 1u;
+            int shift = 0;
+            while (((range) >> shift) >= (uint32_t)LZ2_BINS) ++shift;
+            Z.bin_shift = shift;
+            Z.need_v1 = w.need_v1;
+            static_assert(sizeof(Lazy2Smem) <= 227 * 1024, "lazy2 shared memory");
+            cudaFuncSetAttribute(lazy2_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Lazy2Smem));
+            lazy2_nms_kernel<<<N, LZ2_BLOCK, sizeof(Lazy2Smem), s>>>(Z);
+            RN_CHECK_LAUNCH("rn_postprocess/lazy2_nms");
+        }
         const size_t smem = ((sizeof(LazySmem) + 15) & ~(size_t)15) + (size_t)LZ_CACHE * sizeof(u64);
         cudaFuncSetAttribute(lazy_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         lazy_nms_kernel<<<N, LZ_BLOCK, smem, s>>>(Z);
@@ -1224,7 +1548,7 @@ extern "C" int rn_postprocess(const float *logits, const float *bbox, const floa
     BoxSource box;
     memset(&box, 0, sizeof(box));
     box.nac = (const float4 *)bbox;
-    return pp_tail(w, F, box, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
+    return pp_tail(w, F, box, anchors, anchor_image_stride, im_hw, N, A, C, score_thr, nms_thr, max_det, pre_nms_topk,
                    level_off_host, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count,
                    out_status, out_ratio_hw, out_format, s);
 }
@@ -1440,7 +1764,7 @@ extern "C" int rn_postprocess_levels(const float *const *cls_levels_host, const 
         else score_filter_levels_kernel<false><<<grid, PP_BLOCK, 0, s>>>(F, L);
         RN_CHECK_LAUNCH("rn_postprocess_levels/score_filter");
     }
-    return pp_tail(w, F, box, anchors, anchor_image_stride, im_hw, N, A, C, nms_thr, max_det, pre_nms_topk,
+    return pp_tail(w, F, box, anchors, anchor_image_stride, im_hw, N, A, C, score_thr, nms_thr, max_det, pre_nms_topk,
                    level_off, num_levels, lazy, cand_capacity, out_boxes, out_scores, out_labels, out_count, out_status,
                    out_ratio_hw, out_format, s);
 }

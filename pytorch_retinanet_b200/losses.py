@@ -33,6 +33,9 @@ def _shared_anchors(anchors: Sequence[Tensor]) -> Tuple[Tensor, int]:
     return st, st.shape[1]
 
 
+_SCRATCH: Dict[tuple, Tensor] = {}
+
+
 def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, anchor_stride: int,
                        packed: PackedTargets, alpha: float, gamma: float, beta: float, match_thr: float,
                        back_thr: float, batch_div: float, want_grad: bool, exchange=None):
@@ -51,14 +54,24 @@ def fused_loss_forward(cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor, a
     x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
     b = b if (b.dtype == torch.float32 and b.is_contiguous()) else b.to(torch.float32).contiguous()
     assert match_thr > back_thr                    # box_utils.py:66
-    codes = torch.empty((N, A), dtype=torch.int32, device=dev)
-    fg = torch.empty((N,), dtype=torch.int32, device=dev)
-    out_total = torch.empty((4,), dtype=torch.float32, device=dev)
-    out_image = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    # scratch of the call (match codes, foreground counts, partial sums): ONE cached block per (device, stream, shape) —
+    # stream-ordered reuse, like the post-processing workspace; the returned `codes` view is valid until the next call
+    ws_bytes = lib.rn_train_loss_workspace_bytes(N, A, C)
+    code_bytes = (N * A * 4 + 255) // 256 * 256
+    fg_bytes = (N * 4 + 255) // 256 * 256
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, N, A, C)
+    scratch = _SCRATCH.get(key)
+    if scratch is None:
+        if len(_SCRATCH) > 8:
+            _SCRATCH.clear()
+        scratch = _SCRATCH[key] = torch.empty((code_bytes + fg_bytes + ws_bytes,), dtype=torch.uint8, device=dev)
+    codes = scratch[:N * A * 4].view(torch.int32).view(N, A)
+    fg = scratch[code_bytes:code_bytes + N * 4].view(torch.int32)
+    ws = scratch[code_bytes + fg_bytes:]
+    out = torch.empty((4 + 3 * N,), dtype=torch.float32, device=dev)      # results handed to the caller: fresh per call
+    out_total, out_image = out[:4], out[4:].view(N, 3)
     gl = torch.empty_like(x) if want_grad else None
     gb = torch.empty_like(b) if want_grad else None
-    ws_bytes = lib.rn_train_loss_workspace_bytes(N, A, C)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     with _native.on_device(dev):
         rc = lib.rn_train_loss(_native.ptr(x, torch.float32, "cls_preds"), _native.ptr(b, torch.float32, "bbox_preds"),
                                _native.ptr(anchors, torch.float32, "anchors"), anchor_stride,
@@ -77,7 +90,8 @@ def _scale_in_place(buf: Tensor, g: Tensor) -> None:
     """buf *= g (device scalar) with one launch whose blocks exit at once when g == 1 (the usual case)."""
     if buf.numel() == 0:
         return
-    gs = g.detach().to(device=buf.device, dtype=torch.float32).contiguous()
+    gs = g if (g.dtype == torch.float32 and g.device == buf.device and not g.requires_grad) else \
+        g.detach().to(device=buf.device, dtype=torch.float32).contiguous()
     with _native.on_device(buf.device):
         rc = _native.load().rn_scale_by_device_scalar(_native.ptr(buf), buf.numel(), _native.ptr(gs),
                                                       _native.stream_ptr(buf.device))
