@@ -56,7 +56,7 @@ def reference_step(ref, cls_preds, bbox_preds, targets, padded_hw, im_szs, num_c
 
     n = cls_preds.shape[0]
     dev = cls_preds.device
-    gen = ref.anchors.AnchorGenerator()
+    gen = ref.anchors.AnchorGenerator().to(dev)
     h, w = padded_hw
     fmaps = [torch.empty((n, 1, -(-h // s), -(-w // s)), device=dev) for s in strides]
     anchors = gen(SimpleNamespace(image_sizes=list(im_szs)), fmaps)

@@ -336,8 +336,9 @@ def run_ours(args, rank, world, local_rank):
     # and detections of step i are read — every step's results are consumed, one step late, so the host work of a
     # step (GT packing, graph launch, count copy, slicing) overlaps with the GPU work of the other buffer. ----
     gsum_max = sum(int(t["boxes"].shape[0]) for t in targets)
-    gb = (n_img * world) if world > 1 else None
+    gb = (n_img * world) if (world > 1 and not os.environ.get("RN_BENCH_NO_EXCHANGE")) else None
     anc0 = gen(images, fmaps)[0]
+    barrier()                                               # ranks leave data generation seconds apart
     gkw = dict(max_targets=max(4096, gsum_max), global_batch=gb, exchange=xch if xch is not None else "nccl")
     graph = HotPathGraph(C, d_cls, d_box, anc0, batch["im_szs"], **gkw)
     d_cls2, d_box2 = d_cls.clone(), d_box.clone()
@@ -390,6 +391,25 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(d_cls, d_box)
     ms_dropin = timed(lambda: step(d_cls, d_box), args.steps)
+
+    # ---- drop-in calls in graph mode (patch_retinanet(model, graph=True)): reference signatures + autograd, the kernels
+    # replayed from CUDA graphs cached on the inputs' addresses ----
+    losses_g = P.RetinaNetLosses(C, graph=True)
+    stub_g = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100, rn_graph=True)
+    ms_dropin_graph = None
+    if world == 1:                                          # (single-GPU mode: the sharded loss keeps the eager path)
+        def step_dropin_graph():
+            anchors = gen(images, fmaps)
+            dets = P.process_detections(stub_g, {"cls_preds": d_cls, "bbox_preds": d_box}, anchors, batch["im_szs"])
+            x, b = d_cls.detach().requires_grad_(True), d_box.detach().requires_grad_(True)
+            out = losses_g(targets, {"cls_preds": x, "bbox_preds": b}, anchors)
+            (out["classification_loss"] + out["regression_loss"]).backward()
+            return out, dets, x.grad
+
+        for _ in range(3):
+            step_dropin_graph()
+        ms_dropin_graph = timed(step_dropin_graph, args.steps)
+        del losses_g, stub_g
 
     # ---- same work, software-pipelined: detections of step i are collected while step i+1 is enqueued ----
     pending = []
@@ -603,6 +623,10 @@ def run_ours(args, rank, world, local_rank):
                     "dropin_sync": {"value": total / (ms_dropin * 1e-3), "unit": "images/s", "ms_per_step": ms_dropin,
                                     "note": "RetinaNetLosses.forward + backward + process_detections (reference signatures, "
                                             "autograd), one host sync per step"},
+                    "dropin_graph_sync": None if ms_dropin_graph is None else {
+                        "value": total / (ms_dropin_graph * 1e-3), "unit": "images/s", "ms_per_step": ms_dropin_graph,
+                        "note": "the same drop-in calls with graph=True (patch_retinanet(model, graph=True)): reference "
+                                "signatures + autograd, kernels replayed from CUDA graphs cached on the inputs' addresses"},
                     "dropin_pipelined": {"value": total / (ms_pipe * 1e-3), "unit": "images/s", "ms_per_step": ms_pipe,
                                          "note": "drop-in calls with process_detections_async: results of step i read while "
                                                  "step i+1 is enqueued"}},

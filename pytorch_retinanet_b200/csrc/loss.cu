@@ -36,7 +36,10 @@ constexpr int LOSS_SPAN = 256;   // anchors per CTA
 #define LOSS_U_DEF 4
 #endif
 #ifndef LOSS_MINB
-#define LOSS_MINB 5
+#define LOSS_MINB 5       // fwd+grad: 48 registers, 5 CTAs/SM (measured r2: 386 us; 6 CTAs 388 us, 4 CTAs 393 us at config 2)
+#endif
+#ifndef LOSS_MINB_FWD
+#define LOSS_MINB_FWD 6   // forward only: 40 registers, 6 CTAs/SM (201 us; 5 CTAs 209 us, 4 CTAs 222 us, 8 CTAs x 2 loads 203 us)
 #endif
 constexpr int LOSS_U = LOSS_U_DEF;   // 128-bit loads in flight per thread
 
@@ -262,7 +265,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
 }
 
 template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
-__global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : LOSS_MINB) loss_kernel(const LossParams P) {
+__global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : (WANT_GRAD ? LOSS_MINB : LOSS_MINB_FWD)) loss_kernel(const LossParams P) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.ticket = 0u;   // loss_finalize_kernel runs after this grid
     loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE>(P, blockIdx.y, blockIdx.x);
 }
@@ -278,7 +281,7 @@ constexpr int FIN_BLOCK = 256;
 // upper half equals the expected sequence number carries a complete value (the LL idea: no flag, no fence).
 // Two parities: a rank can run at most one step ahead of the slowest reader of its previous values.
 constexpr int XCH_SLOT_WORDS = 2 * RN_MAX_PEERS * 4;
-constexpr long long XCH_TIMEOUT_CYCLES = 4000000000LL;         // ~2 s at 1.9 GHz
+constexpr long long XCH_TIMEOUT_CYCLES = 120000000000LL;       // ~60 s at 1.9 GHz: ranks may be seconds apart at start-up
 struct ExchangeDev {
     unsigned long long *peers[RN_MAX_PEERS];
     int rank, world;

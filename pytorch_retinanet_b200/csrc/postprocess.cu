@@ -909,6 +909,10 @@ constexpr int LZ2_BINS = 2048;
 constexpr int LZ2_MAXC = 128;                 // classes
 constexpr int LZ2_CHUNKS = LZ2_CAP / 32;
 constexpr int LZ2_BIN_MAX = 256;              // heaviest bin ranked in place (quadratic in the bin size)
+#ifndef LZ2_WAVE_DEF
+#define LZ2_WAVE_DEF 512
+#endif
+constexpr int LZ2_WAVE = LZ2_WAVE_DEF;        // ranks per lazy wave of the per-class NMS
 
 struct Lazy2Smem {
     u64 key[LZ2_CAP];                         // the prefix in global order (rank -> key)
@@ -922,6 +926,7 @@ struct Lazy2Smem {
     u32 hist[LZ2_BINS];                       // bin counts, then scatter cursors (= inclusive prefix when done)
     unsigned short ctab[LZ2_CHUNKS][LZ2_MAXC];   // class counts per 32-rank chunk, then exclusive prefix over the chunks
     int cls_base[LZ2_MAXC + 1];
+    int cls_cur[LZ2_MAXC], cls_kept[LZ2_MAXC];          // per class: members processed / boxes kept so far
     unsigned short ltab[LZ2_CHUNKS][RN_MAX_LEVELS];   // pre_nms_topk: level counts per chunk, then exclusive prefix
     int lvl_total[RN_MAX_LEVELS];
     int warp_tot[32];
@@ -955,6 +960,13 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
     extern __shared__ __align__(16) unsigned char lz2_raw[];
     Lazy2Smem &S = *reinterpret_cast<Lazy2Smem *>(lz2_raw);
     const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#ifdef RN_LAZY_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    int n_waves = 0;
+#define LZ2_TICK(id) do { __syncthreads(); if (t == 0) { long long now_ = clock64(); tacc[id] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define LZ2_TICK(id) do { } while (0)
+#endif
     const u32 found = P.img_count[n];
     if (t == 0) {
         const unsigned long long scaled = (unsigned long long)found * (unsigned long long)P.N;
@@ -980,6 +992,7 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
     __syncthreads();
     for (int i = t; i < K; i += LZ2_BLOCK) atomicAdd(&S.hist[bin_of(__ldg(cand + i))], 1u);
     __syncthreads();
+    LZ2_TICK(0);
     // ---- (2) largest prefix of bins holding <= LZ2_CAP candidates; hist becomes the scatter cursor ----
     {
         const int c0 = (int)S.hist[2 * t], c1 = (int)S.hist[2 * t + 1];
@@ -1001,6 +1014,7 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
         if (t == 0) P.need_v1[n] = 1;
         return;
     }
+    LZ2_TICK(1);
     // ---- (3) scatter the prefix by bin, then every key ranks itself inside its bin ----
     u64 *tmp = reinterpret_cast<u64 *>(S.box);
     for (int i = t; i < K; i += LZ2_BLOCK) {
@@ -1009,6 +1023,7 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
         if (b <= cut) tmp[atomicAdd(&S.hist[b], 1u)] = k;
     }
     __syncthreads();
+    LZ2_TICK(2);
     for (int i = t; i < Pn; i += LZ2_BLOCK) {
         const u64 k = tmp[i];
         const int b = bin_of(k);
@@ -1018,6 +1033,7 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
         S.key[r] = k;
     }
     __syncthreads();
+    LZ2_TICK(3);
     // ---- (4) class of every ranked candidate; stable regrouping by class; decode into the grouped arrays ----
     const int C = P.C;
     const u32 A32 = (u32)P.A;
@@ -1081,6 +1097,7 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
         if (t == 0) S.cls_base[C] = total;
     }
     __syncthreads();
+    LZ2_TICK(4);
     const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
     const long long anc_row = (long long)n * P.anchor_stride;
 #pragma unroll
@@ -1100,54 +1117,81 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
         }
     }
     __syncthreads();
-    // ---- (5) greedy NMS, one warp per class at a time ----
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&S.next_cls, 1);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= C) break;
-        const int base = S.cls_base[c], nc = S.cls_base[c + 1] - base;
-        int kc = 0;                                               // kept so far in this class
-        for (int s0 = 0; s0 < nc && kc < P.max_det; s0 += 32) {
-            const int j = s0 + lane;
-            const bool valid = j < nc;
-            const float4 b = valid ? S.box[base + j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float ar = valid ? S.area[base + j] : 0.f;
-            bool alive = valid && S.ok[base + j];
-            for (int k = 0; k < kc; ++k) {                        // boxes kept in earlier chunks of the class
-                const int kp = S.kidx[base + k];
-                if (alive && nms_suppresses(S.box[kp], S.area[kp], b, ar, P.thr)) alive = false;
-            }
-            const u32 am = __ballot_sync(0xffffffffu, alive);
-            u32 diag = 0;                                         // later boxes of this chunk that box `lane` suppresses
-            if (am & (am - 1)) {                                  // at least two alive
-                u32 rest = am;
-                while (rest) {
-                    const int jj = __ffs(rest) - 1;
-                    rest &= rest - 1;
-                    if (alive && jj > lane && nms_suppresses(b, ar, S.box[base + s0 + jj], S.area[base + s0 + jj], P.thr))
-                        diag |= 1u << jj;
-                }
-            }
-            bool kp = alive;
-#pragma unroll 1
-            for (int sweep = 0; sweep < 32; ++sweep) {            // fixed point of kept = alive & no kept earlier conflict
-                const u32 rem = __reduce_or_sync(0xffffffffu, kp ? diag : 0u);
-                const bool nk = alive && !((rem >> lane) & 1u);
-                const bool changed = nk != kp;
-                kp = nk;
-                if (!__any_sync(0xffffffffu, changed)) break;
-            }
-            const u32 km = __ballot_sync(0xffffffffu, kp);
-            if (kp) {
-                S.kidx[base + kc + __popc(km & ((1u << lane) - 1u))] = (unsigned short)(base + j);
-                S.kept[S.rank_of[base + j]] = 1;
-            }
-            kc += __popc(km);
-            __syncwarp();
-        }
-    }
+    LZ2_TICK(5);
+    // ---- (5) greedy NMS, one warp per class at a time, LAZILY in waves of LZ2_WAVE ranks: every class advances
+    // through its (rank-sorted) members below the wave's end; as soon as max_det candidates are kept among the ranks
+    // seen so far, the answer is complete (a kept flag only depends on higher-ranked members of the same class) ----
+    for (int i = t; i < C; i += LZ2_BLOCK) { S.cls_cur[i] = 0; S.cls_kept[i] = 0; }
+    if (t == 0) S.total_kept = 0;
     __syncthreads();
+    for (int wave_end = LZ2_WAVE; ; wave_end += LZ2_WAVE) {
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&S.next_cls, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= C) break;
+            const int base = S.cls_base[c], nc = S.cls_base[c + 1] - base;
+            int s0 = S.cls_cur[c], kc = S.cls_kept[c];
+            int added = 0;
+            while (s0 < nc && kc < P.max_det) {
+                const int j = s0 + lane;
+                const bool valid = j < nc && (int)S.rank_of[base + j] < wave_end;      // ranks ascend inside a class
+                const u32 vm = __ballot_sync(0xffffffffu, valid);
+                if (vm == 0) break;
+                const float4 b = valid ? S.box[base + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float ar = valid ? S.area[base + j] : 0.f;
+                bool alive = valid && S.ok[base + j];
+                for (int k = 0; k < kc; ++k) {                    // boxes kept earlier in this class
+                    const int kp = S.kidx[base + k];
+                    if (alive && nms_suppresses(S.box[kp], S.area[kp], b, ar, P.thr)) alive = false;
+                }
+                const u32 am = __ballot_sync(0xffffffffu, alive);
+                u32 diag = 0;                                     // later boxes of this chunk that box `lane` suppresses
+                if (am & (am - 1)) {                              // at least two alive
+                    u32 rest = am & (am - 1);                     // the first alive box is suppressed by nobody
+                    while (rest) {
+                        const int jj = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        if (alive && jj > lane && nms_suppresses(b, ar, S.box[base + s0 + jj], S.area[base + s0 + jj], P.thr))
+                            diag |= 1u << jj;
+                    }
+                }
+                bool kp = alive;
+#pragma unroll 1
+                for (int sweep = 0; sweep < 32; ++sweep) {        // fixed point of kept = alive & no kept earlier conflict
+                    const u32 rem = __reduce_or_sync(0xffffffffu, kp ? diag : 0u);
+                    const bool nk = alive && !((rem >> lane) & 1u);
+                    const bool changed = nk != kp;
+                    kp = nk;
+                    if (!__any_sync(0xffffffffu, changed)) break;
+                }
+                const u32 km = __ballot_sync(0xffffffffu, kp);
+                if (kp) {
+                    S.kidx[base + kc + __popc(km & ((1u << lane) - 1u))] = (unsigned short)(base + j);
+                    S.kept[S.rank_of[base + j]] = 1;
+                }
+                kc += __popc(km);
+                added += __popc(km);
+                s0 += __popc(vm);                                 // valid lanes form a prefix of the chunk
+                __syncwarp();
+                if (__popc(vm) < 32) break;                       // the rest of the class lies beyond this wave
+            }
+            if (lane == 0) {
+                S.cls_cur[c] = s0;
+                S.cls_kept[c] = kc;
+                if (added) atomicAdd(&S.total_kept, added);
+            }
+        }
+        __syncthreads();
+#ifdef RN_LAZY_TIMING
+        ++n_waves;
+#endif
+        if (S.total_kept >= P.max_det || wave_end >= Pn) break;
+        __syncthreads();
+        if (t == 0) S.next_cls = 0;
+        __syncthreads();
+    }
+    LZ2_TICK(6);
     // ---- (6) the first max_det kept candidates in global order ----
     {
         const int r0 = 4 * t;                                     // LZ2_CAP = 4 * LZ2_BLOCK
@@ -1180,6 +1224,13 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
             P.need_v1[n] = unfinished ? 1 : 0;
         }
     }
+#ifdef RN_LAZY_TIMING
+    LZ2_TICK(7);
+    if (t == 0)
+        printf("lazy2 img %d K %d prefix %d waves %d | hist %lld cut %lld scatter %lld rank %lld classes %lld decode %lld nms %lld out %lld\n",
+               n, K, Pn, n_waves, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
+#endif
+#undef LZ2_TICK
 }
 
 __global__ void set_status_capacity_kernel(int *status, int capacity) { status[1] = capacity; }

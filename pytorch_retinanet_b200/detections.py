@@ -259,6 +259,49 @@ def _level_offsets(self):
     return offs
 
 
+class _GraphPending:
+    """Result handle of ``process_detections`` in graph mode (``self.rn_graph = True``): same interface as
+    :class:`PendingDetections`; the outputs are copied out of the graph's static buffers (44 kB for 16 images)."""
+
+    def __init__(self, step_result, cls_preds, bbox_preds):
+        self._r, self._x, self._b = step_result, cls_preds, bbox_preds
+        self._done = None
+
+    def result(self):
+        if self._done is None:
+            ob, os_, ol, counts = self._r.result(self._x, self._b)
+            self._done = (ob.clone(), os_.clone(), ol.clone(), counts)
+            self._x = self._b = None
+        return self._done
+
+    def detections(self) -> List[Dict[str, Tensor]]:
+        return slice_detections(*self.result())
+
+
+def _graph_detections(self, x: Tensor, b: Tensor, an: Tensor, im_szs, original_image_sizes, box_format):
+    """Graph replay of the inference half (opt-in, ``patch_retinanet(model, graph=True)``), keyed like
+    ``RetinaNetLosses(graph=True)`` on the input addresses and shapes; None when the call does not qualify."""
+    if not (x.is_cuda and x.dtype == torch.float32 and b.dtype == torch.float32 and x.is_contiguous() and b.is_contiguous()
+            and not getattr(self, "pre_nms_topk", None)):
+        return None
+    cache = self.__dict__.setdefault("_rn_det_graphs", {})
+    key = (x.data_ptr(), b.data_ptr(), tuple(x.shape), an.data_ptr(), tuple((int(h), int(w)) for h, w in im_szs),
+           None if original_image_sizes is None else tuple((int(h), int(w)) for h, w in original_image_sizes), box_format,
+           float(getattr(self, "score_thres", SCORE_THRES)), float(getattr(self, "nms_thres", NMS_THRES)),
+           int(getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE)), torch.cuda.current_stream(x.device).cuda_stream)
+    g = cache.get(key)
+    if g is None:
+        from .graphs import HotPathGraph
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache)))
+        g = HotPathGraph(x.shape[2], x.detach(), b.detach(), an, im_szs, train=False, detect=True, score_thres=key[7],
+                         nms_thres=key[8], detections_per_img=key[9], original_image_sizes=original_image_sizes,
+                         box_format=box_format)
+        g.release_inputs()
+        cache[key] = g
+    return _GraphPending(g.step(), x, b)
+
+
 def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Tensor],
                              im_szs: List[Tuple[int, int]],
                              original_image_sizes: Optional[Sequence[Tuple[int, int]]] = None,
@@ -278,6 +321,10 @@ def process_detections_async(self, outputs: Dict[str, Tensor], anchors: List[Ten
                                         box_format=box_format)
     class_logits = outputs.pop("cls_preds")
     bboxes = outputs.pop("bbox_preds")
+    if getattr(self, "rn_graph", False) and stride == 0:
+        pending = _graph_detections(self, class_logits.detach(), bboxes.detach(), an, im_szs, original_image_sizes, box_format)
+        if pending is not None:
+            return pending
     return postprocess_batch_async(class_logits, bboxes, an, stride, im_szs,
                                    getattr(self, "score_thres", SCORE_THRES), getattr(self, "nms_thres", NMS_THRES),
                                    getattr(self, "detections_per_img", MAX_DETECTIONS_PER_IMAGE),

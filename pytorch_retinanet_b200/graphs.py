@@ -62,10 +62,13 @@ class GraphStepResult:
         """d(classification_loss)/d cls_preds and d(regression_loss)/d bbox_preds, already divided by the batch size."""
         return self._o.grad_cls_preds, self._o.grad_bbox_preds
 
-    def result(self):
+    def result(self, cls_preds=None, bbox_preds=None):
         """(boxes [N,max_det,4], scores [N,max_det], labels [N,max_det] int64, counts list[int]) — waits for the
-        count copy only."""
+        count copy only.  ``cls_preds`` / ``bbox_preds``: the live input tensors, needed only after
+        :meth:`HotPathGraph.release_inputs` for the (rare) eager re-run."""
         o = self._o
+        cls_in = o.cls_preds if cls_preds is None else cls_preds
+        box_in = o.bbox_preds if bbox_preds is None else bbox_preds
         if not o.detect:
             raise RuntimeError("HotPathGraph was built with detect=False")
         if self._dets is None:
@@ -78,11 +81,13 @@ class GraphStepResult:
                 # same inputs through the drop-in call, which knows how to grow the pool and switch algorithm
                 kw = dict(cand_capacity=max(found, o.cap), original_image_sizes=o.original_image_sizes, box_format=o.box_format,
                           pre_nms_topk=o.topk or None)
+                if cls_in is None:
+                    raise RuntimeError("HotPathGraph: the eager re-run needs the input tensors (release_inputs() was called)")
                 if o.levels:
-                    self._dets = postprocess_levels_async(o.cls_preds, o.bbox_preds, o.C, o.anchors, o.anchor_stride, o.im_szs,
+                    self._dets = postprocess_levels_async(cls_in, box_in, o.C, o.anchors, o.anchor_stride, o.im_szs,
                                                           o.score_thres, o.nms_thres, o.max_det, **kw).result()
                 else:
-                    self._dets = postprocess_batch(o.cls_preds, o.bbox_preds, o.anchors, o.anchor_stride, o.im_szs,
+                    self._dets = postprocess_batch(cls_in, box_in, o.anchors, o.anchor_stride, o.im_szs,
                                                    o.score_thres, o.nms_thres, o.max_det,
                                                    level_offsets=o.level_offsets if o.topk else None, **kw)
             else:
@@ -222,9 +227,18 @@ class HotPathGraph:
                                  lib.rn_postprocess_workspace_bytes)(N, A, C, self.cap, M)
             self._pp_ws = torch.empty((self._pp_ws_bytes,), dtype=torch.uint8, device=dev)
         self._stage = None
+        self.steps_done, self.grads_taken = 0, False
         self._side = torch.cuda.Stream(device=dev, priority=-1) if (train and detect and concurrent) else None
         self.graph = torch.cuda.CUDAGraph()
         self._capture()
+
+    def release_inputs(self) -> None:
+        """Drops the references to the input tensors (the captured kernels keep their ADDRESSES).  For callers that
+        replay the graph only while the same addresses hold live tensors of the same shape — ``RetinaNetLosses(graph=
+        True)`` / ``process_detections`` in graph mode key their graph cache on exactly that — so that the caching
+        allocator can recycle the blocks between steps.  The eager re-run of a candidate-pool overflow then needs the
+        tensors passed to :meth:`GraphStepResult.result` again."""
+        self.cls_preds = self.bbox_preds = None
 
     # ---- raw C-ABI launches on the CURRENT stream (the same calls the drop-in path makes) ----
     def _enqueue_train(self):
@@ -387,6 +401,8 @@ class HotPathGraph:
         ground truth loaded by the last :meth:`load_targets`."""
         if self.train and targets is not None:
             self.load_targets(targets)
+        self.steps_done += 1
+        self.grads_taken = False
         self.graph.replay()
         if self.train and self.world > 1 and self._xch is None:
             import torch.distributed as dist

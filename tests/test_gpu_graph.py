@@ -224,3 +224,48 @@ def test_graph_pre_nms_topk_extension(P):
     bs = [t.to(dev) for t in S.nac_to_levels(b["bbox_preds"], cfg.padded_hw)]
     gl = HotPathGraph(cfg.num_classes, xs, bs, anc, b["im_szs"], train=False, pre_nms_topk=50)
     _assert_same_dets(gl.step().detections(), want)
+
+
+def test_dropin_calls_in_graph_mode(P):
+    """``RetinaNetLosses(graph=True)`` / ``process_detections`` with ``rn_graph`` replay cached CUDA graphs keyed on the
+    inputs' addresses: bit-identical to the eager drop-in calls, step after step, with inputs that move, change shape
+    and change content; the reference's call pattern (one backward per forward) is what the mode supports."""
+    cfg = S.CONFIGS[1]
+    dev = torch.device("cuda")
+    anc = S.default_anchors(cfg.padded_hw).to(dev)
+    Lg = P.RetinaNetLosses(cfg.num_classes, graph=True)
+    stub_g = SimpleNamespace(score_thres=0.05, nms_thres=0.5, detections_per_img=100, rn_graph=True)
+    bufs = {}
+    for step, (first, n_img) in enumerate([(7, 3), (40, 3), (80, 2), (7, 3), (41, 3)]):
+        b = S.make_batch(cfg, first, n_img, clustered=True)
+        tg = to_cuda_targets(b["targets"])
+        if step == 1:                                               # one image without ground truth
+            tg[1] = {"boxes": torch.zeros((0, 4), device=dev), "labels": torch.zeros((0,), dtype=torch.int64, device=dev)}
+        # the SAME device buffers per shape (what the caching allocator gives a model in steady state), new contents
+        x, bb = bufs.setdefault(n_img, (torch.empty_like(b["cls_preds"], device=dev), torch.empty_like(b["bbox_preds"], device=dev)))
+        x.copy_(b["cls_preds"])
+        bb.copy_(b["bbox_preds"])
+        want_out, want_gx, want_gb, want_img, want_dets = _dropin(P, cfg, x, bb, anc, tg, b["im_szs"])
+        xg, bg = x.detach().requires_grad_(True), bb.detach().requires_grad_(True)     # same storage, fresh autograd leaves
+        out = Lg(tg, {"cls_preds": xg, "bbox_preds": bg}, [anc] * n_img)
+        (out["classification_loss"] + out["regression_loss"]).backward()
+        assert torch.equal(out["classification_loss"].detach(), want_out["classification_loss"].detach()), step
+        assert torch.equal(out["regression_loss"].detach(), want_out["regression_loss"].detach()), step
+        assert torch.equal(xg.grad, want_gx) and torch.equal(bg.grad, want_gb), step
+        assert torch.equal(Lg.last_per_image, want_img), step
+        outputs = {"cls_preds": x, "bbox_preds": bb}
+        dets = P.process_detections(stub_g, outputs, [anc] * n_img, b["im_szs"])
+        assert outputs == {}
+        _assert_same_dets(dets, want_dets)
+    assert len(Lg._graphs) == 2 and len(stub_g._rn_det_graphs) == 2    # one graph per (addresses, shape)
+    # a second backward through the same forward is refused loudly in this mode
+    xg = x.detach().requires_grad_(True)
+    out = Lg(tg, {"cls_preds": xg, "bbox_preds": bb}, [anc] * n_img)
+    out["classification_loss"].backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        out["classification_loss"].backward()
+    # scaled grad_output
+    xg = x.detach().requires_grad_(True)
+    out = Lg(tg, {"cls_preds": xg, "bbox_preds": bb}, [anc] * n_img)
+    (2.0 * out["classification_loss"]).backward()
+    assert torch.equal(xg.grad, 2.0 * want_gx)
