@@ -403,8 +403,10 @@ def run_ours(args, rank, world, local_rank):
             dets = P.process_detections(stub_g, {"cls_preds": d_cls, "bbox_preds": d_box}, anchors, batch["im_szs"])
             x, b = d_cls.detach().requires_grad_(True), d_box.detach().requires_grad_(True)
             out = losses_g(targets, {"cls_preds": x, "bbox_preds": b}, anchors)
-            (out["classification_loss"] + out["regression_loss"]).backward()
-            return out, dets, x.grad
+            # autograd.grad hands the gradients on as a model's backward would (to the head's CatBackward); .backward()
+            # on these LEAF tensors would make AccumulateGrad clone the graph's static 1 GB buffer
+            gx, gb_ = torch.autograd.grad(out["classification_loss"] + out["regression_loss"], (x, b))
+            return out, dets, gx
 
         for _ in range(3):
             step_dropin_graph()

@@ -913,6 +913,11 @@ constexpr int LZ2_BIN_MAX = 256;              // heaviest bin ranked in place (q
 #define LZ2_WAVE_DEF 512
 #endif
 constexpr int LZ2_WAVE = LZ2_WAVE_DEF;        // ranks per lazy wave of the per-class NMS
+#ifndef LZ2_FIRST_DEF
+#define LZ2_FIRST_DEF 1024
+#endif
+constexpr int LZ2_FIRST = LZ2_FIRST_DEF;      // size aimed at by the first (short) prefix
+constexpr int LZ2_LD = 4;                     // candidate keys in flight per thread in the two passes over the list
 
 struct Lazy2Smem {
     u64 key[LZ2_CAP];                         // the prefix in global order (rank -> key)
@@ -926,11 +931,12 @@ struct Lazy2Smem {
     u32 hist[LZ2_BINS];                       // bin counts, then scatter cursors (= inclusive prefix when done)
     unsigned short ctab[LZ2_CHUNKS][LZ2_MAXC];   // class counts per 32-rank chunk, then exclusive prefix over the chunks
     int cls_base[LZ2_MAXC + 1];
-    int cls_cur[LZ2_MAXC], cls_kept[LZ2_MAXC];          // per class: members processed / boxes kept so far
+    int cls_cnt[LZ2_MAXC], cls_cur[LZ2_MAXC], cls_kept[LZ2_MAXC];    // per class: members / members processed / boxes kept
+    unsigned char cls_order[LZ2_MAXC];                  // classes by descending member count
     unsigned short ltab[LZ2_CHUNKS][RN_MAX_LEVELS];   // pre_nms_topk: level counts per chunk, then exclusive prefix
     int lvl_total[RN_MAX_LEVELS];
     int warp_tot[32];
-    int cut_bin, prefix, next_cls, heavy, total_kept;
+    int cut_bin, first_bin, prefix, next_cls, heavy, total_kept;
 };
 
 // exclusive block scan of one int per thread (LZ2_BLOCK threads); returns the exclusive prefix, `total` = block sum
@@ -984,214 +990,271 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
         const u32 hi = (u32)(k >> 32);
         return hi <= hi0 ? 0 : (int)min((hi - hi0) >> shift, (u32)(LZ2_BINS - 1));
     };
-
-    // ---- (1) histogram of the score bins ----
-    for (int i = t; i < LZ2_BINS; i += LZ2_BLOCK) S.hist[i] = 0;
-    for (int i = t; i < LZ2_CAP; i += LZ2_BLOCK) S.kept[i] = 0;
-    if (t == 0) { S.cut_bin = -1; S.prefix = 0; S.next_cls = 0; S.heavy = 0; }
-    __syncthreads();
-    for (int i = t; i < K; i += LZ2_BLOCK) atomicAdd(&S.hist[bin_of(__ldg(cand + i))], 1u);
-    __syncthreads();
-    LZ2_TICK(0);
-    // ---- (2) largest prefix of bins holding <= LZ2_CAP candidates; hist becomes the scatter cursor ----
-    {
-        const int c0 = (int)S.hist[2 * t], c1 = (int)S.hist[2 * t + 1];
-        int total;
-        const int ex = lz2_block_scan(c0 + c1, S.warp_tot, total);
-        const int in0 = ex + c0, in1 = in0 + c1;           // inclusive prefix after bin 2t / 2t+1 (monotone)
-        if (in1 <= LZ2_CAP) atomicMax(&S.cut_bin, 2 * t + 1);
-        else if (in0 <= LZ2_CAP) atomicMax(&S.cut_bin, 2 * t);
-        if ((c0 > LZ2_BIN_MAX && in0 <= LZ2_CAP) || (c1 > LZ2_BIN_MAX && in1 <= LZ2_CAP)) S.heavy = 1;
-        __syncthreads();
-        if (S.cut_bin == 2 * t) S.prefix = in0;
-        if (S.cut_bin == 2 * t + 1) S.prefix = in1;
-        S.hist[2 * t] = (u32)ex;
-        S.hist[2 * t + 1] = (u32)in0;
-    }
-    __syncthreads();
-    const int cut = S.cut_bin, Pn = S.prefix;
-    if (cut < 0 || S.heavy || Pn == 0) {      // first bin alone overflows / mass ties: not for this kernel
-        if (t == 0) P.need_v1[n] = 1;
-        return;
-    }
-    LZ2_TICK(1);
-    // ---- (3) scatter the prefix by bin, then every key ranks itself inside its bin ----
-    u64 *tmp = reinterpret_cast<u64 *>(S.box);
-    for (int i = t; i < K; i += LZ2_BLOCK) {
-        const u64 k = __ldg(cand + i);
-        const int b = bin_of(k);
-        if (b <= cut) tmp[atomicAdd(&S.hist[b], 1u)] = k;
-    }
-    __syncthreads();
-    LZ2_TICK(2);
-    for (int i = t; i < Pn; i += LZ2_BLOCK) {
-        const u64 k = tmp[i];
-        const int b = bin_of(k);
-        const int lo = b ? (int)S.hist[b - 1] : 0, hi = (int)S.hist[b];     // cursors now sit at the bins' ends
-        int r = lo;
-        for (int q = lo; q < hi; ++q) r += tmp[q] < k;
-        S.key[r] = k;
-    }
-    __syncthreads();
-    LZ2_TICK(3);
-    // ---- (4) class of every ranked candidate; stable regrouping by class; decode into the grouped arrays ----
     const int C = P.C;
     const u32 A32 = (u32)P.A;
-    const int nchunks = (Pn + 31) >> 5;
-    for (int i = t; i < nchunks * LZ2_MAXC; i += LZ2_BLOCK) S.ctab[i / LZ2_MAXC][i % LZ2_MAXC] = 0;
-    for (int i = t; i < nchunks * RN_MAX_LEVELS; i += LZ2_BLOCK) S.ltab[i / RN_MAX_LEVELS][i % RN_MAX_LEVELS] = 0;
-    __syncthreads();
     const bool topk = P.topk > 0;
-    int my_lvl[LZ2_CHUNKS / 32], my_lric[LZ2_CHUNKS / 32];
-    int my_cls[LZ2_CHUNKS / 32], my_ric[LZ2_CHUNKS / 32];
-#pragma unroll
-    for (int q = 0; q < LZ2_CHUNKS / 32; ++q) {
-        const int chunk = warp + 32 * q, r = chunk * 32 + lane;
-        my_cls[q] = -1;
-        my_ric[q] = 0;
-        if (chunk < nchunks) {                                  // warp-uniform
-            const int cls = r < Pn ? (int)((u32)S.key[r] / A32) : -1;
-            const u32 peers = __match_any_sync(0xffffffffu, cls);
-            my_cls[q] = cls;
-            my_ric[q] = __popc(peers & ((1u << lane) - 1u));
-            if (cls >= 0 && lane == __ffs(peers) - 1) S.ctab[chunk][cls] = (unsigned short)__popc(peers);
-            my_lvl[q] = -1;
-            my_lric[q] = 0;
-            if (topk) {                                         // rank of the candidate inside its pyramid level
-                int lvl = -1;
-                if (cls >= 0) {
-                    const long long anchor = (long long)((u32)S.key[r] - (u32)cls * A32);
-                    lvl = 0;
-                    for (int l = 1; l < P.nlev; ++l) lvl += anchor >= P.lvl_off[l];
-                }
-                const u32 lp = __match_any_sync(0xffffffffu, lvl);
-                my_lvl[q] = lvl;
-                my_lric[q] = __popc(lp & ((1u << lane) - 1u));
-                if (lvl >= 0 && lane == __ffs(lp) - 1) S.ltab[chunk][lvl] = (unsigned short)__popc(lp);
-            }
-        }
-    }
-    __syncthreads();
-    int ccount = 0;
-    if (t < C) {
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int v = S.ctab[ch][t];
-            S.ctab[ch][t] = (unsigned short)ccount;
-            ccount += v;
-        }
-    }
-    if (topk && t >= LZ2_BLOCK - RN_MAX_LEVELS) {               // the last warp's lanes scan the level columns
-        const int l = t - (LZ2_BLOCK - RN_MAX_LEVELS);
-        int run = 0;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int v = S.ltab[ch][l];
-            S.ltab[ch][l] = (unsigned short)run;
-            run += v;
-        }
-        S.lvl_total[l] = run;
-    }
-    {
-        int total;
-        const int ex = lz2_block_scan(t < C ? ccount : 0, S.warp_tot, total);
-        if (t < C) S.cls_base[t] = ex;
-        if (t == 0) S.cls_base[C] = total;
-    }
-    __syncthreads();
-    LZ2_TICK(4);
     const float imh = (float)P.im_hw[2 * n], imw = (float)P.im_hw[2 * n + 1];
     const long long anc_row = (long long)n * P.anchor_stride;
-#pragma unroll
-    for (int q = 0; q < LZ2_CHUNKS / 32; ++q) {
-        const int chunk = warp + 32 * q, r = chunk * 32 + lane, cls = my_cls[q];
-        if (cls >= 0) {
-            const int g = S.cls_base[cls] + S.ctab[chunk][cls] + my_ric[q];
-            const long long anchor = (long long)((u32)S.key[r] - (u32)cls * A32);
-            const float4 b = decode_clip(P.box, n, P.A, anchor, P.anchors, anc_row + anchor, P.wts, imw, imh);
-            S.box[g] = b;
-            S.area[g] = nms_area(b);
-            bool ok = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);    // remove_small_boxes, models.py:203
-            if (topk) ok = ok && (S.ltab[chunk][my_lvl[q]] + my_lric[q] < P.topk);         // only the level's top-k scores
-            S.ok[g] = ok;
-            S.rank_of[g] = (unsigned short)r;
-            S.pos_of[r] = (unsigned short)g;
-        }
-    }
-    __syncthreads();
-    LZ2_TICK(5);
-    // ---- (5) greedy NMS, one warp per class at a time, LAZILY in waves of LZ2_WAVE ranks: every class advances
-    // through its (rank-sorted) members below the wave's end; as soon as max_det candidates are kept among the ranks
-    // seen so far, the answer is complete (a kept flag only depends on higher-ranked members of the same class) ----
-    for (int i = t; i < C; i += LZ2_BLOCK) { S.cls_cur[i] = 0; S.cls_kept[i] = 0; }
-    if (t == 0) S.total_kept = 0;
-    __syncthreads();
-    for (int wave_end = LZ2_WAVE; ; wave_end += LZ2_WAVE) {
-        for (;;) {
-            int c = 0;
-            if (lane == 0) c = atomicAdd(&S.next_cls, 1);
-            c = __shfl_sync(0xffffffffu, c, 0);
-            if (c >= C) break;
-            const int base = S.cls_base[c], nc = S.cls_base[c + 1] - base;
-            int s0 = S.cls_cur[c], kc = S.cls_kept[c];
-            int added = 0;
-            while (s0 < nc && kc < P.max_det) {
-                const int j = s0 + lane;
-                const bool valid = j < nc && (int)S.rank_of[base + j] < wave_end;      // ranks ascend inside a class
-                const u32 vm = __ballot_sync(0xffffffffu, valid);
-                if (vm == 0) break;
-                const float4 b = valid ? S.box[base + j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float ar = valid ? S.area[base + j] : 0.f;
-                bool alive = valid && S.ok[base + j];
-                for (int k = 0; k < kc; ++k) {                    // boxes kept earlier in this class
-                    const int kp = S.kidx[base + k];
-                    if (alive && nms_suppresses(S.box[kp], S.area[kp], b, ar, P.thr)) alive = false;
-                }
-                const u32 am = __ballot_sync(0xffffffffu, alive);
-                u32 diag = 0;                                     // later boxes of this chunk that box `lane` suppresses
-                if (am & (am - 1)) {                              // at least two alive
-                    u32 rest = am & (am - 1);                     // the first alive box is suppressed by nobody
-                    while (rest) {
-                        const int jj = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        if (alive && jj > lane && nms_suppresses(b, ar, S.box[base + s0 + jj], S.area[base + s0 + jj], P.thr))
-                            diag |= 1u << jj;
-                    }
-                }
-                bool kp = alive;
+    u64 *tmp = reinterpret_cast<u64 *>(S.box);
+
+    // Two attempts at most: a SHORT prefix (the first bins holding >= LZ2_FIRST candidates — the common case needs a
+    // few hundred ranks for max_det survivors), then the largest prefix that fits LZ2_CAP.
+    int Pn = 0, total_kept = 0;
 #pragma unroll 1
-                for (int sweep = 0; sweep < 32; ++sweep) {        // fixed point of kept = alive & no kept earlier conflict
-                    const u32 rem = __reduce_or_sync(0xffffffffu, kp ? diag : 0u);
-                    const bool nk = alive && !((rem >> lane) & 1u);
-                    const bool changed = nk != kp;
-                    kp = nk;
-                    if (!__any_sync(0xffffffffu, changed)) break;
-                }
-                const u32 km = __ballot_sync(0xffffffffu, kp);
-                if (kp) {
-                    S.kidx[base + kc + __popc(km & ((1u << lane) - 1u))] = (unsigned short)(base + j);
-                    S.kept[S.rank_of[base + j]] = 1;
-                }
-                kc += __popc(km);
-                added += __popc(km);
-                s0 += __popc(vm);                                 // valid lanes form a prefix of the chunk
-                __syncwarp();
-                if (__popc(vm) < 32) break;                       // the rest of the class lies beyond this wave
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // ---- (1) histogram of the score bins (LZ2_LD keys in flight per thread) ----
+        for (int i = t; i < LZ2_BINS; i += LZ2_BLOCK) S.hist[i] = 0;
+        for (int i = t; i < LZ2_CAP; i += LZ2_BLOCK) S.kept[i] = 0;
+        if (t == 0) { S.cut_bin = -1; S.first_bin = LZ2_BINS; S.prefix = 0; S.next_cls = 0; S.heavy = 0; S.total_kept = 0; }
+        __syncthreads();
+        for (int i0 = 0; i0 < K; i0 += LZ2_BLOCK * LZ2_LD) {
+            u64 k[LZ2_LD];
+#pragma unroll
+            for (int u = 0; u < LZ2_LD; ++u) {
+                const int i = i0 + u * LZ2_BLOCK + t;
+                k[u] = i < K ? __ldg(cand + i) : ~0ULL;
             }
-            if (lane == 0) {
-                S.cls_cur[c] = s0;
-                S.cls_kept[c] = kc;
-                if (added) atomicAdd(&S.total_kept, added);
+#pragma unroll
+            for (int u = 0; u < LZ2_LD; ++u)
+                if (i0 + u * LZ2_BLOCK + t < K) atomicAdd(&S.hist[bin_of(k[u])], 1u);
+        }
+        __syncthreads();
+        LZ2_TICK(0);
+        // ---- (2) the cut: hist becomes the scatter cursor (exclusive prefix) ----
+        {
+            const int c0 = (int)S.hist[2 * t], c1 = (int)S.hist[2 * t + 1];
+            int total;
+            const int ex = lz2_block_scan(c0 + c1, S.warp_tot, total);
+            const int in0 = ex + c0, in1 = in0 + c1;           // inclusive prefix after bin 2t / 2t+1 (monotone)
+            if (in1 <= LZ2_CAP) atomicMax(&S.cut_bin, 2 * t + 1);          // largest bin whose prefix fits
+            else if (in0 <= LZ2_CAP) atomicMax(&S.cut_bin, 2 * t);
+            if (in0 >= LZ2_FIRST) atomicMin(&S.first_bin, 2 * t);          // smallest bin whose prefix reaches LZ2_FIRST
+            else if (in1 >= LZ2_FIRST) atomicMin(&S.first_bin, 2 * t + 1);
+            __syncthreads();
+            const int cutb = (attempt == 0 && S.first_bin <= S.cut_bin) ? S.first_bin : S.cut_bin;
+            if ((c0 > LZ2_BIN_MAX && 2 * t <= cutb) || (c1 > LZ2_BIN_MAX && 2 * t + 1 <= cutb)) S.heavy = 1;
+            if (cutb == 2 * t) S.prefix = in0;
+            if (cutb == 2 * t + 1) S.prefix = in1;
+            __syncthreads();
+            if (t == 0) S.cut_bin = cutb;
+            S.hist[2 * t] = (u32)ex;
+            S.hist[2 * t + 1] = (u32)in0;
+        }
+        __syncthreads();
+        const int cut = S.cut_bin;
+        Pn = S.prefix;
+        if (cut < 0 || S.heavy || Pn == 0) {      // first bin alone overflows / mass ties: not for this kernel
+            if (t == 0) P.need_v1[n] = 1;
+            return;
+        }
+        LZ2_TICK(1);
+        // ---- (3) scatter the prefix by bin, then every key ranks itself inside its bin ----
+        for (int i0 = 0; i0 < K; i0 += LZ2_BLOCK * LZ2_LD) {
+            u64 k[LZ2_LD];
+#pragma unroll
+            for (int u = 0; u < LZ2_LD; ++u) {
+                const int i = i0 + u * LZ2_BLOCK + t;
+                k[u] = i < K ? __ldg(cand + i) : ~0ULL;
+            }
+#pragma unroll
+            for (int u = 0; u < LZ2_LD; ++u) {
+                if (i0 + u * LZ2_BLOCK + t < K) {
+                    const int b = bin_of(k[u]);
+                    if (b <= cut) tmp[atomicAdd(&S.hist[b], 1u)] = k[u];
+                }
             }
         }
         __syncthreads();
+        LZ2_TICK(2);
+        for (int i = t; i < Pn; i += LZ2_BLOCK) {
+            const u64 k = tmp[i];
+            const int b = bin_of(k);
+            const int lo = b ? (int)S.hist[b - 1] : 0, hi = (int)S.hist[b];     // cursors now sit at the bins' ends
+            int r = lo;
+            for (int q = lo; q < hi; ++q) r += tmp[q] < k;
+            S.key[r] = k;
+        }
+        __syncthreads();
+        LZ2_TICK(3);
+        // ---- (4) class of every ranked candidate; stable regrouping by class; decode into the grouped arrays ----
+        const int nchunks = (Pn + 31) >> 5;
+        for (int i = t; i < nchunks * LZ2_MAXC; i += LZ2_BLOCK) S.ctab[i / LZ2_MAXC][i % LZ2_MAXC] = 0;
+        for (int i = t; i < nchunks * RN_MAX_LEVELS; i += LZ2_BLOCK) S.ltab[i / RN_MAX_LEVELS][i % RN_MAX_LEVELS] = 0;
+        __syncthreads();
+        int my_lvl[LZ2_CHUNKS / 32], my_lric[LZ2_CHUNKS / 32];
+        int my_cls[LZ2_CHUNKS / 32], my_ric[LZ2_CHUNKS / 32];
+#pragma unroll
+        for (int q = 0; q < LZ2_CHUNKS / 32; ++q) {
+            const int chunk = warp + 32 * q, r = chunk * 32 + lane;
+            my_cls[q] = -1;
+            my_ric[q] = 0;
+            my_lvl[q] = -1;
+            my_lric[q] = 0;
+            if (chunk < nchunks) {                                  // warp-uniform
+                const int cls = r < Pn ? (int)((u32)S.key[r] / A32) : -1;
+                const u32 peers = __match_any_sync(0xffffffffu, cls);
+                my_cls[q] = cls;
+                my_ric[q] = __popc(peers & ((1u << lane) - 1u));
+                if (cls >= 0 && lane == __ffs(peers) - 1) S.ctab[chunk][cls] = (unsigned short)__popc(peers);
+                if (topk) {                                         // rank of the candidate inside its pyramid level
+                    int lvl = -1;
+                    if (cls >= 0) {
+                        const long long anchor = (long long)((u32)S.key[r] - (u32)cls * A32);
+                        lvl = 0;
+                        for (int l = 1; l < P.nlev; ++l) lvl += anchor >= P.lvl_off[l];
+                    }
+                    const u32 lp = __match_any_sync(0xffffffffu, lvl);
+                    my_lvl[q] = lvl;
+                    my_lric[q] = __popc(lp & ((1u << lane) - 1u));
+                    if (lvl >= 0 && lane == __ffs(lp) - 1) S.ltab[chunk][lvl] = (unsigned short)__popc(lp);
+                }
+            }
+        }
+        __syncthreads();
+        int ccount = 0;
+        if (t < C) {                                                // column scan over the chunks, 8 loads in flight
+            for (int ch0 = 0; ch0 < nchunks; ch0 += 8) {
+                int v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ch0 + u < nchunks ? S.ctab[ch0 + u][t] : 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ch0 + u < nchunks) S.ctab[ch0 + u][t] = (unsigned short)ccount;
+                    ccount += v[u];
+                }
+            }
+        }
+        if (topk && t >= LZ2_BLOCK - RN_MAX_LEVELS) {               // the last warp's lanes scan the level columns
+            const int l = t - (LZ2_BLOCK - RN_MAX_LEVELS);
+            int run = 0;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int v = S.ltab[ch][l];
+                S.ltab[ch][l] = (unsigned short)run;
+                run += v;
+            }
+            S.lvl_total[l] = run;
+        }
+        {
+            int total;
+            const int ex = lz2_block_scan(t < C ? ccount : 0, S.warp_tot, total);
+            if (t < C) { S.cls_base[t] = ex; S.cls_cnt[t] = ccount; S.cls_cur[t] = 0; S.cls_kept[t] = 0; }
+            if (t == 0) S.cls_base[C] = total;
+        }
+        __syncthreads();
+        if (t < C) {                                                // heaviest classes first (longest-processing-time order)
+            const int mine = S.cls_cnt[t];
+            int rk = 0;
+            for (int c = 0; c < C; ++c) {
+                const int o = S.cls_cnt[c];
+                rk += (o > mine) || (o == mine && c < t);
+            }
+            S.cls_order[rk] = (unsigned char)t;
+        }
+        LZ2_TICK(4);
+#pragma unroll
+        for (int q = 0; q < LZ2_CHUNKS / 32; ++q) {
+            const int chunk = warp + 32 * q, r = chunk * 32 + lane, cls = my_cls[q];
+            if (cls >= 0) {
+                const int g = S.cls_base[cls] + S.ctab[chunk][cls] + my_ric[q];
+                const long long anchor = (long long)((u32)S.key[r] - (u32)cls * A32);
+                const float4 b = decode_clip(P.box, n, P.A, anchor, P.anchors, anc_row + anchor, P.wts, imw, imh);
+                S.box[g] = b;
+                S.area[g] = nms_area(b);
+                bool ok = (__fsub_rn(b.z, b.x) >= 0.01f) && (__fsub_rn(b.w, b.y) >= 0.01f);    // remove_small_boxes, models.py:203
+                if (topk) ok = ok && (S.ltab[chunk][my_lvl[q]] + my_lric[q] < P.topk);         // only the level's top-k scores
+                S.ok[g] = ok;
+                S.rank_of[g] = (unsigned short)r;
+                S.pos_of[r] = (unsigned short)g;
+            }
+        }
+        __syncthreads();
+        LZ2_TICK(5);
+        // ---- (5) greedy NMS, one warp per class at a time, LAZILY in waves of LZ2_WAVE ranks: every class advances
+        // through its (rank-sorted) members below the wave's end; as soon as max_det candidates are kept among the
+        // ranks seen so far, the answer is complete (a kept flag only depends on higher-ranked members of the class) ----
+        for (int wave_end = LZ2_WAVE; ; wave_end += LZ2_WAVE) {
+            for (;;) {
+                int ci = 0;
+                if (lane == 0) ci = atomicAdd(&S.next_cls, 1);
+                ci = __shfl_sync(0xffffffffu, ci, 0);
+                if (ci >= C) break;
+                const int c = S.cls_order[ci];
+                const int base = S.cls_base[c], nc = S.cls_cnt[c];
+                int s0 = S.cls_cur[c], kc = S.cls_kept[c];
+                int added = 0;
+                while (s0 < nc && kc < P.max_det) {
+                    const int j = s0 + lane;
+                    const bool valid = j < nc && (int)S.rank_of[base + j] < wave_end;      // ranks ascend inside a class
+                    const u32 vm = __ballot_sync(0xffffffffu, valid);
+                    if (vm == 0) break;
+                    const float4 b = valid ? S.box[base + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float ar = valid ? S.area[base + j] : 0.f;
+                    bool alive = valid && S.ok[base + j];
+                    for (int k = 0; k < kc; ++k) {                    // boxes kept earlier in this class
+                        const int kp = S.kidx[base + k];
+                        if (alive && nms_suppresses(S.box[kp], S.area[kp], b, ar, P.thr)) alive = false;
+                    }
+                    const u32 am = __ballot_sync(0xffffffffu, alive);
+                    u32 diag = 0;                                     // later boxes of this chunk that box `lane` suppresses
+                    if (am & (am - 1)) {                              // at least two alive
+                        u32 rest = am & (am - 1);                     // the first alive box is suppressed by nobody
+                        while (rest) {
+                            const int jj = __ffs(rest) - 1;
+                            rest &= rest - 1;
+                            if (alive && jj > lane && nms_suppresses(b, ar, S.box[base + s0 + jj], S.area[base + s0 + jj], P.thr))
+                                diag |= 1u << jj;
+                        }
+                    }
+                    bool kp = alive;
+#pragma unroll 1
+                    for (int sweep = 0; sweep < 32; ++sweep) {        // fixed point of kept = alive & no kept earlier conflict
+                        const u32 rem = __reduce_or_sync(0xffffffffu, kp ? diag : 0u);
+                        const bool nk = alive && !((rem >> lane) & 1u);
+                        const bool changed = nk != kp;
+                        kp = nk;
+                        if (!__any_sync(0xffffffffu, changed)) break;
+                    }
+                    const u32 km = __ballot_sync(0xffffffffu, kp);
+                    if (kp) {
+                        S.kidx[base + kc + __popc(km & ((1u << lane) - 1u))] = (unsigned short)(base + j);
+                        S.kept[S.rank_of[base + j]] = 1;
+                    }
+                    kc += __popc(km);
+                    added += __popc(km);
+                    s0 += __popc(vm);                                 // valid lanes form a prefix of the chunk
+                    __syncwarp();
+                    if (__popc(vm) < 32) break;                       // the rest of the class lies beyond this wave
+                }
+                if (lane == 0) {
+                    S.cls_cur[c] = s0;
+                    S.cls_kept[c] = kc;
+                    if (added) atomicAdd(&S.total_kept, added);
+                }
+            }
+            __syncthreads();
 #ifdef RN_LAZY_TIMING
-        ++n_waves;
+            ++n_waves;
 #endif
-        if (S.total_kept >= P.max_det || wave_end >= Pn) break;
-        __syncthreads();
-        if (t == 0) S.next_cls = 0;
-        __syncthreads();
+            if (S.total_kept >= P.max_det || wave_end >= Pn) break;
+            __syncthreads();
+            if (t == 0) S.next_cls = 0;
+            __syncthreads();
+        }
+        LZ2_TICK(6);
+        total_kept = S.total_kept;
+        bool more = total_kept < P.max_det && Pn < K;         // survivors may hide beyond the prefix ...
+        if (more && topk) {                                   // ... unless every level already saw its k candidates
+            bool full = true;
+            for (int l = 0; l < P.nlev; ++l) full = full && S.lvl_total[l] >= P.topk;
+            more = !full;
+        }
+        if (!more) break;
+        if (attempt == 1 || Pn >= LZ2_CAP) {                  // nothing larger fits: lazy_nms_kernel takes the image
+            if (t == 0) P.need_v1[n] = 1;
+            return;
+        }
+        __syncthreads();                                      // second attempt: everything is rebuilt with the long prefix
     }
-    LZ2_TICK(6);
     // ---- (6) the first max_det kept candidates in global order ----
     {
         const int r0 = 4 * t;                                     // LZ2_CAP = 4 * LZ2_BLOCK
@@ -1214,14 +1277,8 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
             }
         }
         if (t == 0) {
-            bool unfinished = total < P.max_det && Pn < K;        // survivors may hide beyond the prefix ...
-            if (unfinished && topk) {                             // ... unless every level already saw its k candidates
-                bool full = true;
-                for (int l = 0; l < P.nlev; ++l) full = full && S.lvl_total[l] >= P.topk;
-                unfinished = !full;
-            }
             P.out_count[n] = min(total, P.max_det);
-            P.need_v1[n] = unfinished ? 1 : 0;
+            P.need_v1[n] = 0;
         }
     }
 #ifdef RN_LAZY_TIMING

@@ -248,10 +248,14 @@ def test_dropin_calls_in_graph_mode(P):
         want_out, want_gx, want_gb, want_img, want_dets = _dropin(P, cfg, x, bb, anc, tg, b["im_szs"])
         xg, bg = x.detach().requires_grad_(True), bb.detach().requires_grad_(True)     # same storage, fresh autograd leaves
         out = Lg(tg, {"cls_preds": xg, "bbox_preds": bg}, [anc] * n_img)
-        (out["classification_loss"] + out["regression_loss"]).backward()
+        if step % 2:
+            (out["classification_loss"] + out["regression_loss"]).backward()
+            got_gx, got_gb = xg.grad, bg.grad
+        else:       # what a model's backward does: the gradients are passed on, not accumulated into leaves
+            got_gx, got_gb = torch.autograd.grad(out["classification_loss"] + out["regression_loss"], (xg, bg))
         assert torch.equal(out["classification_loss"].detach(), want_out["classification_loss"].detach()), step
         assert torch.equal(out["regression_loss"].detach(), want_out["regression_loss"].detach()), step
-        assert torch.equal(xg.grad, want_gx) and torch.equal(bg.grad, want_gb), step
+        assert torch.equal(got_gx, want_gx) and torch.equal(got_gb, want_gb), step
         assert torch.equal(Lg.last_per_image, want_img), step
         outputs = {"cls_preds": x, "bbox_preds": bb}
         dets = P.process_detections(stub_g, outputs, [anc] * n_img, b["im_szs"])
