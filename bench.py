@@ -505,8 +505,11 @@ def run_ours(args, rank, world, local_rank):
     def loss_only(want_grad):
         return fused_loss_forward(d_cls, d_box, anc, 0, packed, 0.25, 2.0, 0.1, 0.5, 0.4, float(n_img), want_grad)
 
+    g_det = HotPathGraph(C, d_cls, d_box, anc, batch["im_szs"], train=False, detect=True)
+
     kern = {}
     for name, fn in (("loss_fwd_bwd", lambda: loss_only(True)), ("loss_fwd", lambda: loss_only(False)),
+                     ("postprocess_graph", lambda: g_det.step().result()),
                      ("loss_kernel_alone", graph._enqueue_loss),     # loss_kernel<4,grad> + finalize on precomputed codes
                      ("loss_fwd_kernel_alone", lambda: graph._enqueue_loss(False)),
                      ("match_alone", graph._enqueue_match),
@@ -544,6 +547,9 @@ def run_ours(args, rank, world, local_rank):
                                                                       "validation_step path)"),
                            "postprocess": bw(bytes_p, kern["postprocess"], "whole synchronous call: streaming score filter + lazy NMS "
                                                                            "+ the count copy/sync"),
+                           "postprocess_graph": bw(bytes_p, kern["postprocess_graph"], "the same post-processing replayed from a CUDA "
+                                                   "graph (HotPathGraph(train=False) / process_detections in graph mode): one launch + the "
+                                                   "count copy/sync per call"),
                            "loss_fwd_kernel_alone": bw(bytes_f, kern["loss_fwd_kernel_alone"], "forward-only streaming kernel "
                                                                                                 "(+ finalize) on precomputed codes"),
                            "loss_kernel_alone": bw(bytes_fb, kern["loss_kernel_alone"], "loss_kernel<4,grad> + finalize, codes "

@@ -162,6 +162,24 @@ int rn_train_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/
                   float *grad_logits /*[N,A,C] or NULL*/, float *grad_bbox /*[N,A,4] or NULL*/, void *workspace,
                   size_t workspace_bytes, rn_stream_t stream, const rn_exchange_t *exchange_host /*or NULL*/);
 
+/* Both halves of the path on the same head outputs with ONE pass over the logits: rn_train_loss whose loss kernel is
+ * also the score filter of rn_postprocess(RN_PP_LAZY) (retinanet/losses.py:113-145 + retinanet/models.py:160-243 on one
+ * batch, e.g. detections during training).  Arguments and outputs are those of the two calls; results are identical to
+ * calling them one after the other.  Needs C % 4 == 0, 16-byte aligned logits, A*C < 2^32 and the default math mode.
+ * out_status as in rn_postprocess: a candidate-pool overflow or the fallback flag is resolved by calling
+ * rn_postprocess on the same inputs.  workspace: rn_train_detect_workspace_bytes(N, A, C, cand_capacity, max_det).  */
+size_t rn_train_detect_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
+int rn_train_detect(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
+                    const float *gt_boxes, const int64_t *gt_labels, const int32_t *gt_off, int N, int64_t gt_total,
+                    int64_t A, int C, float fg_thr, float bg_thr, float alpha, float gamma, float beta,
+                    const float *weights_host /*[4]*/, float batch_div, int32_t *codes, int32_t *fg_count,
+                    float *out_image /*[N,3]*/, float *out_total /*[4]*/, float *grad_logits /*or NULL*/,
+                    float *grad_bbox /*or NULL*/, const int32_t *im_hw /*[N,2]*/, float score_thr, double nms_thr, int max_det,
+                    int pre_nms_topk, const int64_t *level_off_host /*[L+1] or NULL*/, int num_levels, int64_t cand_capacity,
+                    float *out_boxes, float *out_scores, int64_t *out_labels, int32_t *out_count, int32_t *out_status,
+                    const float *out_ratio_hw /*[N,2] or NULL*/, int out_format, void *workspace, size_t workspace_bytes,
+                    rn_stream_t stream, const rn_exchange_t *exchange_host /*or NULL*/);
+
 /* Dense element-wise losses, API parity with RetinaNetLosses.focal_loss (losses.py:29-47, arbitrary
  * float targets of the logits' shape, NO +1 shift) and RetinaNetLosses.smooth_l1_loss (losses.py:19-27).
  * out_sum [1] = sum over the n elements; grad (optional, [n]) = d out_sum / d input.

@@ -26,6 +26,7 @@
 #include <cstring>
 
 #include "loss_math.cuh"
+#include "pp_internal.cuh"
 #include "rn_common.cuh"
 
 namespace {
@@ -63,9 +64,31 @@ struct LossParams {
     int chunks;
     float alpha, gamma, beta, batch_div;
     float4 wts;
+    rnpp::LazySink sink;         // FILTER variants (rn_train_detect): candidate lists of the post-processing
 };
 
 using namespace rnloss;
+
+// rn_train_detect: the loss kernel is also the score filter of the post-processing — the logits are streamed ONCE for
+// both halves of the path.  Rare path, deliberately not inlined (as in score_filter_kernel): exact sigmoid of the <= 4
+// logits of one vector, strict threshold (models.py:196), key = (~score_bits << 32) | (class * A + anchor), appended to
+// the image's candidate list with one atomic per survivor (~0.1 % of the elements).
+__device__ __noinline__ void emit_candidates_loss(const LossParams &P, float4 v, int f, int n, long long a0, int CV) {
+    const int al = f / CV;
+    const int c0 = (f - al * CV) * 4;
+    const long long anchor = a0 + al;
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!(vals[k] > P.sink.x_lo)) continue;
+        const float s = rn::sigmoid_ref(vals[k]);
+        if (!(s > P.sink.thr)) continue;
+        const unsigned lo = (unsigned)((long long)(c0 + k) * P.A + anchor);
+        const unsigned long long key = ((unsigned long long)(~__float_as_uint(s)) << 32) | (unsigned long long)lo;
+        const unsigned gp = atomicAdd(P.sink.img_count + n, 1u);
+        if (gp < P.sink.cap_n) P.sink.pool_key[(size_t)n * P.sink.cap_n + gp] = key;
+    }
+}
 
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
     __shared__ double s[3][LOSS_BLOCK / 32];
@@ -94,7 +117,7 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c) {
 // loss is exactly 0.  NB: a NaN / +inf logit inside an IGNORED anchor therefore poisons the sum (inf - inf), where
 // the reference, which drops those rows before any arithmetic, stays finite; everywhere else non-finite logits
 // propagate exactly as in the reference.
-template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
+template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE, bool FILTER>
 __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, const int chunk) {
     const long long a0 = (long long)chunk * LOSS_SPAN;
     const int span = (int)min((long long)LOSS_SPAN, P.A - a0);
@@ -106,6 +129,12 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     float *dst = WANT_GRAD ? P.grad_logits + row0 * P.C : nullptr;
 
     if (__ldg(P.gt_off + n + 1) == __ldg(P.gt_off + n)) {      // no GT: nothing contributes, gradients are zero
+        if (FILTER && VEC == 4) {                               // ... but the image still has detections
+            for (int f = t; f < nvec; f += LOSS_BLOCK) {
+                const float4 q = rn::ld_stream_f4((const float4 *)src + f);
+                if (fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)) > P.sink.x_lo) emit_candidates_loss(P, q, f, n, a0, CV);
+            }
+        }
         if (WANT_GRAD) {
             for (int f = t; f < nvec; f += LOSS_BLOCK) {
                 if (VEC == 4) rn::st_stream_f4((float4 *)dst + f, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -148,6 +177,12 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
 #pragma unroll
         for (int u = 0; u < LOSS_U; ++u) {
             float g[VEC];
+            if (FILTER && VEC == 4) {                            // the post-processing's score filter, on the same registers
+                const float vmax = fmaxf(fmaxf(v[u][0], v[u][1]), fmaxf(v[u][VEC > 2 ? 2 : 0], v[u][VEC > 3 ? 3 : 0]));
+                if (vmax > P.sink.x_lo && base + u * LOSS_BLOCK + t < nvec)     // rare
+                    emit_candidates_loss(P, make_float4(v[u][0], v[u][1], v[u][VEC > 2 ? 2 : 0], v[u][VEC > 3 ? 3 : 0]),
+                                         base + u * LOSS_BLOCK + t, n, a0, CV);
+            }
             bool mid = !PRECISE;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) mid = mid && (v[u][k] <= x_mid);       // false for NaN
@@ -264,10 +299,10 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     }
 }
 
-template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE>
+template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE, bool FILTER = false>
 __global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : (WANT_GRAD ? LOSS_MINB : LOSS_MINB_FWD)) loss_kernel(const LossParams P) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.ticket = 0u;   // loss_finalize_kernel runs after this grid
-    loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE>(P, blockIdx.y, blockIdx.x);
+    loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE, FILTER>(P, blockIdx.y, blockIdx.x);
 }
 
 // Fixed-order final reduction: block n reduces image n's chunk partials (thread-strided partial sums, then a
@@ -468,18 +503,20 @@ __global__ void __launch_bounds__(256) scale_kernel(float *__restrict__ buf, lon
 
 
 template <int VEC, bool WANT_GRAD, bool GAMMA2>
-void launch_loss(const LossParams &P, dim3 grid, cudaStream_t s, bool precise) {
-    if (precise)
+void launch_loss(const LossParams &P, dim3 grid, cudaStream_t s, bool precise, bool filter) {
+    if (filter) {
+        if (VEC == 4 && !precise) loss_kernel<4, WANT_GRAD, GAMMA2, false, true><<<grid, LOSS_BLOCK, 0, s>>>(P);
+    } else if (precise)
         loss_kernel<VEC, WANT_GRAD, GAMMA2, true><<<grid, LOSS_BLOCK, 0, s>>>(P);
     else
         loss_kernel<VEC, WANT_GRAD, GAMMA2, false><<<grid, LOSS_BLOCK, 0, s>>>(P);
 }
 template <int VEC, bool WANT_GRAD>
-void launch_loss_g(const LossParams &P, dim3 grid, cudaStream_t s, bool precise) {
+void launch_loss_g(const LossParams &P, dim3 grid, cudaStream_t s, bool precise, bool filter) {
     if (P.gamma == 2.0f)
-        launch_loss<VEC, WANT_GRAD, true>(P, grid, s, precise);
+        launch_loss<VEC, WANT_GRAD, true>(P, grid, s, precise, filter);
     else
-        launch_loss<VEC, WANT_GRAD, false>(P, grid, s, precise);
+        launch_loss<VEC, WANT_GRAD, false>(P, grid, s, precise, filter);
 }
 
 // (host helpers)
@@ -509,12 +546,13 @@ extern "C" size_t rn_loss_workspace_bytes(int N, int64_t A, int C) {
     return ((size_t)N * (size_t)loss_chunks(A) * 2 + (size_t)N * 2 + 2) * sizeof(double);
 }
 
-extern "C" int rn_loss(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
-                       const float *gt_boxes,
-                       const int32_t *gt_off, const int32_t *codes, const int32_t *fg_count, int N, int64_t A, int C,
-                       float alpha, float gamma, float beta, const float *weights_host, float batch_div,
-                       float *out_image, float *out_total, float *grad_logits, float *grad_bbox, void *workspace,
-                       size_t workspace_bytes, rn_stream_t stream, const rn_exchange_t *exchange_host) {
+static int loss_impl(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
+                     const float *gt_boxes,
+                     const int32_t *gt_off, const int32_t *codes, const int32_t *fg_count, int N, int64_t A, int C,
+                     float alpha, float gamma, float beta, const float *weights_host, float batch_div,
+                     float *out_image, float *out_total, float *grad_logits, float *grad_bbox, void *workspace,
+                     size_t workspace_bytes, rn_stream_t stream, const rn_exchange_t *exchange_host,
+                     const rnpp::LazySink *sink) {
     RN_CHECK_ARG(logits && bbox && anchors && gt_off && codes && fg_count && out_total && weights_host, RN_E_BADARG,
                  "rn_loss: null pointer");
     ExchangeDev X;
@@ -540,10 +578,17 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     const bool vec4 = (C % 4 == 0) && (((uintptr_t)logits & 15) == 0) && (!grad_logits || ((uintptr_t)grad_logits & 15) == 0);
     dim3 grid((unsigned)P.chunks, (unsigned)N);
     const bool precise = g_math_mode == 1;
+    const bool filter = sink != nullptr;
+    memset(&P.sink, 0, sizeof(P.sink));
+    if (filter) {
+        RN_CHECK_ARG(vec4 && !precise, RN_E_BADARG, "rn_train_detect needs C %% 4 == 0, 16-byte aligned logits and the default math "
+                                                    "mode (call rn_train_loss and rn_postprocess separately otherwise)");
+        P.sink = *sink;
+    }
     if (vec4) {
-        if (grad_logits) launch_loss_g<4, true>(P, grid, s, precise); else launch_loss_g<4, false>(P, grid, s, precise);
+        if (grad_logits) launch_loss_g<4, true>(P, grid, s, precise, filter); else launch_loss_g<4, false>(P, grid, s, precise, filter);
     } else {
-        if (grad_logits) launch_loss_g<1, true>(P, grid, s, precise); else launch_loss_g<1, false>(P, grid, s, precise);
+        if (grad_logits) launch_loss_g<1, true>(P, grid, s, precise, false); else launch_loss_g<1, false>(P, grid, s, precise, false);
     }
     RN_CHECK_LAUNCH("rn_loss");
     {
@@ -553,6 +598,17 @@ extern "C" int rn_loss(const float *logits, const float *bbox, const float *anch
     }
     RN_CHECK_LAUNCH("rn_loss_finalize");
     return 0;
+}
+
+extern "C" int rn_loss(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
+                       const float *gt_boxes,
+                       const int32_t *gt_off, const int32_t *codes, const int32_t *fg_count, int N, int64_t A, int C,
+                       float alpha, float gamma, float beta, const float *weights_host, float batch_div,
+                       float *out_image, float *out_total, float *grad_logits, float *grad_bbox, void *workspace,
+                       size_t workspace_bytes, rn_stream_t stream, const rn_exchange_t *exchange_host) {
+    return loss_impl(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
+                     weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, workspace_bytes, stream,
+                     exchange_host, nullptr);
 }
 
 // ---- rn_train_loss: the training half of the path behind ONE C call (rn_match, then rn_loss + final reduction on
@@ -578,6 +634,51 @@ extern "C" int rn_train_loss(const float *logits, const float *bbox, const float
     return rn_loss(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
                    weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, workspace_bytes, stream,
                    exchange_host);
+}
+
+// ---- rn_train_detect: BOTH halves of the path on the same head outputs with ONE pass over the logits.  The training
+// step of the reference reads cls_preds for the loss (losses.py:113-145) and, when detections of the same batch are
+// wanted too (evaluation during training, models.py:160-243), a second time for the score threshold.  Here the loss
+// kernel applies the post-processing's score filter to the registers it is streaming anyway and appends the survivors to
+// the lazy NMS's candidate lists: per step 4*A*C bytes per image less HBM traffic (1.03 GB of 3.2 GB at config 2) and
+// one kernel less; the NMS then runs behind the loss instead of beside it.  Same results as rn_train_loss +
+// rn_postprocess(RN_PP_LAZY): the candidate SET is identical, the lists' order is irrelevant (the NMS ranks by key).
+static size_t tdet_loss_bytes(int N, int64_t A, int C) { return (rn_loss_workspace_bytes(N, A, C) + 255) / 256 * 256; }
+
+extern "C" size_t rn_train_detect_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det) {
+    return tdet_loss_bytes(N, A, C) + rn_postprocess_workspace_bytes(N, A, C, cand_capacity, max_det);
+}
+
+extern "C" int rn_train_detect(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
+                               const float *gt_boxes, const int64_t *gt_labels, const int32_t *gt_off, int N, int64_t gt_total,
+                               int64_t A, int C, float fg_thr, float bg_thr, float alpha, float gamma, float beta,
+                               const float *weights_host, float batch_div, int32_t *codes, int32_t *fg_count, float *out_image,
+                               float *out_total, float *grad_logits, float *grad_bbox, const int32_t *im_hw, float score_thr,
+                               double nms_thr, int max_det, int pre_nms_topk, const int64_t *level_off_host, int num_levels,
+                               int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
+                               int32_t *out_count, int32_t *out_status, const float *out_ratio_hw, int out_format,
+                               void *workspace, size_t workspace_bytes, rn_stream_t stream,
+                               const rn_exchange_t *exchange_host) {
+    RN_CHECK_ARG(gt_labels && codes && fg_count && workspace, RN_E_BADARG, "rn_train_detect: null pointer");
+    RN_CHECK_ARG(N > 0 && A > 0 && C > 0, RN_E_BADARG, "rn_train_detect: N, A, C must be positive");
+    const size_t lb = tdet_loss_bytes(N, A, C);
+    RN_CHECK_ARG(workspace_bytes >= lb, RN_E_WORKSPACE, "rn_train_detect: workspace too small");
+    void *pp_ws = (char *)workspace + lb;
+    cudaStream_t s = (cudaStream_t)stream;
+    rnpp::LazySink sink;
+    int rc = rnpp::lazy_begin(N, A, C, score_thr, max_det, pre_nms_topk, level_off_host, num_levels, cand_capacity, out_status,
+                              pp_ws, workspace_bytes - lb, s, &sink);
+    if (rc) return rc;
+    rc = rn_match(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, nullptr, codes,
+                  fg_count, stream);
+    if (rc) return rc;
+    rc = loss_impl(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
+                   weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, lb, stream, exchange_host,
+                   &sink);
+    if (rc) return rc;
+    return rnpp::lazy_end(bbox, anchors, anchor_image_stride, im_hw, N, A, C, score_thr, nms_thr, max_det, weights_host,
+                          pre_nms_topk, level_off_host, num_levels, cand_capacity, out_boxes, out_scores, out_labels, out_count,
+                          out_status, pp_ws, s, out_ratio_hw, out_format);
 }
 
 // ---- per-level NCHW layout -----------------------------------------------------------

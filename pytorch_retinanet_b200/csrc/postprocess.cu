@@ -554,6 +554,7 @@ struct LazyParams {
     long long lvl_off[RN_MAX_LEVELS + 1];   // anchor offsets of the pyramid levels
     int *need_v1;            // [N] or null: written by lazy2_nms_kernel (1 = image left to lazy_nms_kernel), read by lazy_nms_kernel
     int bin_shift;           // lazy2: score-bin width (see lazy2_nms_kernel)
+    int capacity;            // status[1]: candidate capacity of the call (N * cap_n), reported by lazy_nms_kernel
 };
 
 struct LazySmem {
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(LZ_BLOCK, 1) lazy_nms_kernel(const __grid_cons
     u64 *s_cand = reinterpret_cast<u64 *>(lz_raw + ((sizeof(LazySmem) + 15) & ~(size_t)15));
 
     const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (n == 0 && t == 0) P.status[1] = P.capacity;  // (this kernel always closes the lazy pipeline)
     if (P.need_v1 && P.need_v1[n] == 0) return;     // lazy2_nms_kernel finished this image
 #ifdef RN_LAZY_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -1290,8 +1292,6 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
 #undef LZ2_TICK
 }
 
-__global__ void set_status_capacity_kernel(int *status, int capacity) { status[1] = capacity; }
-
 // ------------------------------------------------------------------------------------------- K5
 struct TopkParams {
     const int *seg_off;
@@ -1539,6 +1539,7 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const BoxSource 
             Z.lvl_off[l] = (pre_nms_topk && l <= num_levels) ? (long long)level_off_host[l] : (long long)A;
         Z.need_v1 = nullptr;
         Z.bin_shift = 0;
+        Z.capacity = (int)min((long long)F.cap_n * N, 0x7fffffffLL);
         if (C <= LZ2_MAXC && w.need_v1) {
             // score bins of lazy2_nms_kernel: LZ2_BINS equal-width bins (in float bit patterns) between thr and 1.0
             const float thr_pos = score_thr > 0.0f ? score_thr : 0.0f;
@@ -1560,9 +1561,6 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const BoxSource 
         cudaFuncSetAttribute(lazy_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         lazy_nms_kernel<<<N, LZ_BLOCK, smem, s>>>(Z);
         RN_CHECK_LAUNCH("rn_postprocess/lazy_nms");
-        // status[1] = capacity (N * cap_n) is written by a 1-thread epilogue to keep the call async
-        set_status_capacity_kernel<<<1, 1, 0, s>>>(out_status, (int)min((long long)F.cap_n * N, 0x7fffffffLL));
-        RN_CHECK_LAUNCH("rn_postprocess/status");
         return 0;
     }
 
@@ -1591,6 +1589,67 @@ static int pp_tail(const PPWorkspace &w, const FilterParams &F, const BoxSource 
     image_topk_kernel<<<N, TOPK_BLOCK, topk_smem, s>>>(T);
     RN_CHECK_LAUNCH("rn_postprocess/image_topk");
     return 0;
+}
+
+// ---- pieces of the LAZY post-processing reused by rn_train_detect (loss.cu), whose loss kernel does the score
+// filtering itself while it streams the logits: (a) validation, zeroing and carving of the workspace -> the candidate
+// lists the filter appends to; (b) everything after the filter. ----
+#include "pp_internal.cuh"
+
+static float guard_logit(float thr) {
+    // every x <= x_lo has sigmoid(x) <= thr with a 1e-3 margin (SFU/libm error is ~1e-7)
+    if (!(thr > 0.0f)) return -INFINITY;
+    if (thr >= 1.0f) return INFINITY;
+    const double xt = log((double)thr / (1.0 - (double)thr));
+    return (float)(xt - 1e-3 * fmax(1.0, fabs(xt)));
+}
+
+int rnpp::lazy_begin(int N, int64_t A, int C, float score_thr, int max_det, int pre_nms_topk, const int64_t *level_off_host,
+                     int num_levels, int64_t cand_capacity, int32_t *out_status, void *workspace, size_t workspace_bytes,
+                     cudaStream_t s, rnpp::LazySink *sink) {
+    RN_CHECK_ARG(out_status && workspace && sink, RN_E_BADARG, "rn_train_detect: null pointer");
+    RN_CHECK_ARG(N > 0 && A > 0 && C > 0 && N <= 65535 && C <= 8192, RN_E_BADARG, "rn_train_detect: bad N/A/C");
+    RN_CHECK_ARG(max_det >= 1 && max_det <= MAX_DET_CAP, RN_E_TOOLARGE, "rn_train_detect: max_det=%d outside [1,%d]", max_det, MAX_DET_CAP);
+    RN_CHECK_ARG(cand_capacity >= 1 && cand_capacity < 0x7fffffffLL, RN_E_BADARG, "rn_train_detect: bad cand_capacity");
+    RN_CHECK_ARG(pre_nms_topk >= 0 && (pre_nms_topk == 0 || (level_off_host && num_levels >= 1 && num_levels <= RN_MAX_LEVELS)),
+                 RN_E_BADARG, "rn_train_detect: pre_nms_topk needs 1..%d level offsets", RN_MAX_LEVELS);
+    RN_CHECK_ARG((unsigned long long)A * (unsigned long long)C < (1ULL << 32), RN_E_TOOLARGE,
+                 "rn_train_detect: the lazy algorithm needs A*C < 2^32");
+    PPWorkspace w = carve(workspace, N, C, cand_capacity);
+    RN_CHECK_ARG(workspace_bytes >= w.total_bytes, RN_E_WORKSPACE, "rn_train_detect: post-processing workspace too small (%zu < %zu)",
+                 workspace_bytes, w.total_bytes);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, w.zero_bytes, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out_status, 0, 4 * sizeof(int32_t), s);
+    if (e != cudaSuccess) { rn_set_error("rn_train_detect: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    sink->img_count = w.img_count;
+    sink->pool_key = w.pool_key;
+    sink->cap_n = (u32)max((int64_t)1, cand_capacity / N);
+    sink->x_lo = guard_logit(score_thr);
+    sink->thr = score_thr;
+    return 0;
+}
+
+int rnpp::lazy_end(const float *bbox, const float *anchors, int64_t anchor_image_stride, const int32_t *im_hw, int N, int64_t A,
+                   int C, float score_thr, double nms_thr, int max_det, const float *weights_host, int pre_nms_topk,
+                   const int64_t *level_off_host, int num_levels, int64_t cand_capacity, float *out_boxes, float *out_scores,
+                   int64_t *out_labels, int32_t *out_count, int32_t *out_status, void *workspace, cudaStream_t s,
+                   const float *out_ratio_hw, int out_format) {
+    RN_CHECK_ARG(bbox && anchors && im_hw && weights_host && out_boxes && out_scores && out_labels && out_count, RN_E_BADARG,
+                 "rn_train_detect: null pointer");
+    RN_CHECK_ARG(out_format == 0 || out_format == 1, RN_E_BADARG, "rn_train_detect: out_format must be 0 (xyxy) or 1 (xywh)");
+    PPWorkspace w = carve(workspace, N, C, cand_capacity);
+    FilterParams F;
+    memset(&F, 0, sizeof(F));
+    F.cap = (u32)cand_capacity;
+    F.cap_n = (u32)max((int64_t)1, cand_capacity / N);
+    F.w = w;
+    F.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
+    BoxSource box;
+    memset(&box, 0, sizeof(box));
+    box.nac = (const float4 *)bbox;
+    return pp_tail(w, F, box, anchors, anchor_image_stride, im_hw, N, A, C, score_thr, nms_thr, max_det, pre_nms_topk,
+                   level_off_host, num_levels, true, cand_capacity, out_boxes, out_scores, out_labels, out_count, out_status,
+                   out_ratio_hw, out_format, s);
 }
 
 extern "C" int rn_postprocess(const float *logits, const float *bbox, const float *anchors,

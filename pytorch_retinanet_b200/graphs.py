@@ -111,6 +111,9 @@ class HotPathGraph:
     global batch and the 16-byte loss vector is summed over the ranks exactly as in ``ShardedRetinaNetLosses``:
     inside the captured final reduction kernel over peer-mapped memory (``exchange="peer"``, default — the graph
     launch is then the whole step), or by one NCCL ``all_reduce`` issued after the graph (``"nccl"``).
+    ``fused`` (default: on whenever it applies — train and detect on ``[N,A,C]`` inputs with ``C % 4 == 0``): ONE pass
+    over the logits serves both halves (``rn_train_detect``: the loss kernel is also the score filter; the NMS then runs
+    behind it) instead of two concurrent branches that each stream the logits.  Same results.
     """
 
     def __init__(self, num_classes: int, cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor,
@@ -122,7 +125,7 @@ class HotPathGraph:
                  alpha: float = FOCAL_LOSS_ALPHA, gamma: float = FOCAL_LOSS_GAMMA, beta: float = SMOOTH_L1_LOSS_BETA,
                  match_thr: float = IOU_THRESHOLDS_FOREGROUND, back_thr: float = IOU_THRESHOLDS_BACKGROUND,
                  cand_capacity: Optional[int] = None, concurrent: bool = True, pre_nms_topk: Optional[int] = None,
-                 level_offsets: Optional[Sequence[int]] = None, exchange="peer"):
+                 level_offsets: Optional[Sequence[int]] = None, exchange="peer", fused: Optional[bool] = None):
         if not (train or detect):
             raise ValueError("HotPathGraph: nothing to do (train=False, detect=False)")
         lib = _native.load()
@@ -228,7 +231,17 @@ class HotPathGraph:
             self._pp_ws = torch.empty((self._pp_ws_bytes,), dtype=torch.uint8, device=dev)
         self._stage = None
         self.steps_done, self.grads_taken = 0, False
-        self._side = torch.cuda.Stream(device=dev, priority=-1) if (train and detect and concurrent) else None
+        old_mode = lib.rn_loss_set_math_mode(0)               # (test hook) the fused kernel exists for the default math only
+        lib.rn_loss_set_math_mode(old_mode)
+        can_fuse = (not self.levels) and train and detect and old_mode == 0 and C % 4 == 0 and A * C < (1 << 32) \
+            and cls_preds.data_ptr() % 16 == 0
+        if fused and not can_fuse:
+            raise ValueError("HotPathGraph(fused=True) needs train and detect on [N,A,C] inputs with C % 4 == 0 (default math mode)")
+        self.fused = can_fuse if fused is None else bool(fused)
+        if self.fused:
+            self._td_ws_bytes = lib.rn_train_detect_workspace_bytes(N, A, C, self.cap, self.max_det)
+            self._td_ws = torch.empty((self._td_ws_bytes,), dtype=torch.uint8, device=dev)
+        self._side = torch.cuda.Stream(device=dev, priority=-1) if (train and detect and concurrent and not self.fused) else None
         self.graph = torch.cuda.CUDAGraph()
         self._capture()
 
@@ -306,9 +319,28 @@ class HotPathGraph:
                                 _FORMATS[self.box_format])
         _native.check(rc, "rn_postprocess")
 
+    def _enqueue_fused(self):
+        """rn_train_detect: matcher, loss (+ gradients) that also filters the scores, final reduction, lazy NMS."""
+        lib, N, A, C = self.lib, self.N, self.A, self.C
+        alpha, gamma, beta, match_thr, back_thr = self.hp
+        meta = self.meta.data_ptr()
+        rc = lib.rn_train_detect(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(), self.anchor_stride,
+                                 self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(), self.gt_off.data_ptr(), N, self.max_targets,
+                                 A, C, match_thr, back_thr, alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div,
+                                 self.codes.data_ptr(), self.fg.data_ptr(), self.per_image.data_ptr(), self.total.data_ptr(),
+                                 self.grad_cls_preds.data_ptr(), self.grad_bbox_preds.data_ptr(), self._hw.data_ptr(),
+                                 self.score_thres, self.nms_thres, self.max_det, self.topk, self._lvl,
+                                 (len(self.level_offsets) - 1) if self._lvl is not None else 0, self.cap,
+                                 self.out_boxes.data_ptr(), self.out_scores.data_ptr(), self.out_labels.data_ptr(), meta,
+                                 meta + 4 * N, None if self._ratio is None else self._ratio.data_ptr(), _FORMATS[self.box_format],
+                                 self._td_ws.data_ptr(), self._td_ws_bytes, _native.stream_ptr(self.dev), self._xref)
+        _native.check(rc, "rn_train_detect")
+
     def _enqueue_all(self):
         cur = torch.cuda.current_stream(self.dev)
-        if self._side is not None:
+        if self.fused:
+            self._enqueue_fused()
+        elif self._side is not None:
             self._side.wait_stream(cur)                   # fork
             with torch.cuda.stream(self._side):
                 self._enqueue_detect()

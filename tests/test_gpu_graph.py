@@ -40,9 +40,12 @@ def _assert_same_dets(a, b):
             assert torch.equal(d[k], r[k]), k
 
 
-@pytest.mark.parametrize("concurrent", [True, False])
+@pytest.mark.parametrize("mode", ["fused", "concurrent", "serial"])
 @pytest.mark.parametrize("cid,n_img", [(1, 3), (2, 4)])
-def test_graph_step_equals_dropin_calls(P, cid, n_img, concurrent):
+def test_graph_step_equals_dropin_calls(P, cid, n_img, mode):
+    """fused = rn_train_detect (one pass over the logits for both halves); concurrent / serial = rn_train_loss and
+    rn_postprocess as two branches / back to back."""
+    concurrent, fused = mode == "concurrent", mode == "fused"
     from pytorch_retinanet_b200.graphs import HotPathGraph
     cfg = S.CONFIGS[cid]
     dev = torch.device("cuda")
@@ -50,7 +53,8 @@ def test_graph_step_equals_dropin_calls(P, cid, n_img, concurrent):
     anc = b["anchors"].to(dev)
     x, bb = b["cls_preds"].to(dev), b["bbox_preds"].to(dev)
     tg = to_cuda_targets(b["targets"])
-    g = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"], max_targets=2048, concurrent=concurrent)
+    g = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"], max_targets=2048, concurrent=concurrent, fused=fused)
+    assert g.fused == fused
     for rep in range(3):                      # replays; the 2nd with other targets and inputs written into the static buffers
         if rep == 1:
             b2 = S.make_batch(cfg, 100, n_img, clustered=True)
