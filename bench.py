@@ -340,6 +340,8 @@ def run_ours(args, rank, world, local_rank):
     anc0 = gen(images, fmaps)[0]
     barrier()                                               # ranks leave data generation seconds apart
     gkw = dict(max_targets=max(4096, gsum_max), global_batch=gb, exchange=xch if xch is not None else "nccl")
+    if os.environ.get("RN_BENCH_UNFUSED"):                  # DIAGNOSTIC: the round-1 form of the step (two concurrent branches)
+        gkw["fused"] = False
     graph = HotPathGraph(C, d_cls, d_box, anc0, batch["im_szs"], **gkw)
     d_cls2, d_box2 = d_cls.clone(), d_box.clone()
     graph2 = HotPathGraph(C, d_cls2, d_box2, anc0, batch["im_szs"], **gkw)

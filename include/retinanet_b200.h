@@ -54,7 +54,7 @@ typedef void *rn_stream_t; /* cudaStream_t */
  * A receive buffer (rn_comm_bytes() bytes, zero-initialised, allocated with rn_comm_alloc so that it can be
  * exported) lives on every rank; peers[r] is rank r's buffer as mapped into THIS process (peers[rank] = the local
  * one).  Every rank must run the same sequence of exchanging calls (as with any collective).  A rank that does not
- * hear from a peer within ~60 s writes NaN into out_total and sets the error word (rn_comm_error) instead of hanging. */
+ * hear from a peer within ~5 s writes NaN into out_total and sets the error word (rn_comm_error) instead of hanging. */
 #define RN_MAX_PEERS 16
 typedef struct {
     void *peers[RN_MAX_PEERS]; /* device pointers: receive buffer of every rank, mapped into this process */

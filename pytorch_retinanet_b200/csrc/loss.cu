@@ -73,7 +73,10 @@ using namespace rnloss;
 // both halves of the path.  Rare path, deliberately not inlined (as in score_filter_kernel): exact sigmoid of the <= 4
 // logits of one vector, strict threshold (models.py:196), key = (~score_bits << 32) | (class * A + anchor), appended to
 // the image's candidate list with one atomic per survivor (~0.1 % of the elements).
-__device__ __noinline__ void emit_candidates_loss(const LossParams &P, float4 v, int f, int n, long long a0, int CV) {
+constexpr int LOSS_STAGE = 192;   // candidate keys staged per CTA before ONE global append (a warp must not wait for an
+                                  // L2 atomic's round trip per survivor: ~11 % of the warp-vectors hold one)
+__device__ __noinline__ void emit_candidates_loss(const LossParams &P, float4 v, int f, int n, long long a0, int CV,
+                                                  unsigned long long *s_cand, int *s_ncand) {
     const int al = f / CV;
     const int c0 = (f - al * CV) * 4;
     const long long anchor = a0 + al;
@@ -85,8 +88,27 @@ __device__ __noinline__ void emit_candidates_loss(const LossParams &P, float4 v,
         if (!(s > P.sink.thr)) continue;
         const unsigned lo = (unsigned)((long long)(c0 + k) * P.A + anchor);
         const unsigned long long key = ((unsigned long long)(~__float_as_uint(s)) << 32) | (unsigned long long)lo;
-        const unsigned gp = atomicAdd(P.sink.img_count + n, 1u);
-        if (gp < P.sink.cap_n) P.sink.pool_key[(size_t)n * P.sink.cap_n + gp] = key;
+        const int pos = atomicAdd(s_ncand, 1);
+        if (pos < LOSS_STAGE) {
+            s_cand[pos] = key;
+        } else {                                                // staging full (dense crowd): straight to the list
+            const unsigned gp = atomicAdd(P.sink.img_count + n, 1u);
+            if (gp < P.sink.cap_n) P.sink.pool_key[(size_t)n * P.sink.cap_n + gp] = key;
+        }
+    }
+}
+// all threads of the CTA: one global atomic for the staged candidates, then a coalesced copy
+__device__ __forceinline__ void flush_candidates_loss(const LossParams &P, int n, const unsigned long long *s_cand,
+                                                      const int *s_ncand, unsigned *s_gbase) {
+    __syncthreads();
+    const int staged = min(*s_ncand, LOSS_STAGE);
+    if (staged == 0) return;                                    // block-uniform
+    if (threadIdx.x == 0) *s_gbase = atomicAdd(P.sink.img_count + n, (unsigned)staged);
+    __syncthreads();
+    const unsigned gbase = *s_gbase;
+    for (int i = threadIdx.x; i < staged; i += LOSS_BLOCK) {
+        const unsigned gp = gbase + (unsigned)i;
+        if (gp < P.sink.cap_n) P.sink.pool_key[(size_t)n * P.sink.cap_n + gp] = s_cand[i];
     }
 }
 
@@ -127,13 +149,21 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const float *src = P.logits + row0 * P.C;
     float *dst = WANT_GRAD ? P.grad_logits + row0 * P.C : nullptr;
+    __shared__ unsigned long long s_cand[FILTER ? LOSS_STAGE : 1];
+    __shared__ int s_ncand;
+    __shared__ unsigned s_gbase;
+    if (FILTER) {
+        if (t == 0) s_ncand = 0;
+        __syncthreads();
+    }
 
     if (__ldg(P.gt_off + n + 1) == __ldg(P.gt_off + n)) {      // no GT: nothing contributes, gradients are zero
         if (FILTER && VEC == 4) {                               // ... but the image still has detections
             for (int f = t; f < nvec; f += LOSS_BLOCK) {
                 const float4 q = rn::ld_stream_f4((const float4 *)src + f);
-                if (fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)) > P.sink.x_lo) emit_candidates_loss(P, q, f, n, a0, CV);
+                if (fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)) > P.sink.x_lo) emit_candidates_loss(P, q, f, n, a0, CV, s_cand, &s_ncand);
             }
+            flush_candidates_loss(P, n, s_cand, &s_ncand, &s_gbase);
         }
         if (WANT_GRAD) {
             for (int f = t; f < nvec; f += LOSS_BLOCK) {
@@ -181,7 +211,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
                 const float vmax = fmaxf(fmaxf(v[u][0], v[u][1]), fmaxf(v[u][VEC > 2 ? 2 : 0], v[u][VEC > 3 ? 3 : 0]));
                 if (vmax > P.sink.x_lo && base + u * LOSS_BLOCK + t < nvec)     // rare
                     emit_candidates_loss(P, make_float4(v[u][0], v[u][1], v[u][VEC > 2 ? 2 : 0], v[u][VEC > 3 ? 3 : 0]),
-                                         base + u * LOSS_BLOCK + t, n, a0, CV);
+                                         base + u * LOSS_BLOCK + t, n, a0, CV, s_cand, &s_ncand);
             }
             bool mid = !PRECISE;
 #pragma unroll
@@ -219,6 +249,7 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
         }
     }
 
+    if (FILTER) flush_candidates_loss(P, n, s_cand, &s_ncand, &s_gbase);
     // ---- per-anchor epilogue (thread t <-> anchor t of the span); the gradient rows written above are finished ----
     if (WANT_GRAD) __syncthreads();
     // (1) ignore anchors: the warp takes their rows back, CV vectors over the 32 lanes
@@ -316,7 +347,7 @@ constexpr int FIN_BLOCK = 256;
 // upper half equals the expected sequence number carries a complete value (the LL idea: no flag, no fence).
 // Two parities: a rank can run at most one step ahead of the slowest reader of its previous values.
 constexpr int XCH_SLOT_WORDS = 2 * RN_MAX_PEERS * 4;
-constexpr long long XCH_TIMEOUT_CYCLES = 120000000000LL;       // ~60 s at 1.9 GHz: ranks may be seconds apart at start-up
+constexpr long long XCH_TIMEOUT_CYCLES = 10000000000LL;        // ~5 s at 1.9 GHz (callers align the ranks before the first step)
 struct ExchangeDev {
     unsigned long long *peers[RN_MAX_PEERS];
     int rank, world;

@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(128) pack_targets_kernel(const __grid_constant
 extern "C" int rn_pack_targets(const float *const *boxes_host, const int64_t *const *labels_host, const int32_t *counts_host,
                                int N, const float *ratios_hw_host, float *out_boxes, int64_t *out_labels, int32_t *out_off,
                                rn_stream_t stream) {
-    RN_CHECK_ARG(boxes_host && counts_host && out_off && N >= 0, RN_E_BADARG, "rn_pack_targets: bad argument");
-    RN_CHECK_ARG(!out_labels || labels_host, RN_E_BADARG, "rn_pack_targets: labels requested without label pointers");
+    RN_CHECK_ARG(out_off && N >= 0 && (N == 0 || (boxes_host && counts_host)), RN_E_BADARG, "rn_pack_targets: bad argument");
+    RN_CHECK_ARG(N == 0 || !out_labels || labels_host, RN_E_BADARG, "rn_pack_targets: labels requested without label pointers");
     cudaStream_t s = (cudaStream_t)stream;
     if (N == 0) {
         cudaError_t e = cudaMemsetAsync(out_off, 0, sizeof(int32_t), s);
