@@ -46,6 +46,12 @@ constexpr int LOSS_U = LOSS_U_DEF;   // 128-bit loads in flight per thread
 
 static int g_math_mode = 0;      // 0 fast, 1 precise
 
+// kernel-side form of rn_exchange_t (see peer_exchange below)
+struct ExchangeDev {
+    unsigned long long *peers[RN_MAX_PEERS];
+    int rank, world;
+};
+
 struct LossParams {
     const float *logits;
     const float4 *bbox;
@@ -65,6 +71,12 @@ struct LossParams {
     float alpha, gamma, beta, batch_div;
     float4 wts;
     rnpp::LazySink sink;         // FILTER variants (rn_train_detect): candidate lists of the post-processing
+    // FILTER variants also run the final reduction themselves (the last CTA of an image, by ticket): one node less
+    unsigned *img_ticket;        // [N], zeroed by prep_kernel
+    float *out_image, *out_total;
+    double *tail;
+    int N;
+    ExchangeDev xch;
 };
 
 using namespace rnloss;
@@ -330,10 +342,22 @@ __device__ __forceinline__ void loss_chunk(const LossParams &P, const int n, con
     }
 }
 
+__device__ void finalize_image_fused(const LossParams &P, int n);
+
 template <int VEC, bool WANT_GRAD, bool GAMMA2, bool PRECISE, bool FILTER = false>
-__global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : (WANT_GRAD ? LOSS_MINB : LOSS_MINB_FWD)) loss_kernel(const LossParams P) {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.ticket = 0u;   // loss_finalize_kernel runs after this grid
+__global__ void __launch_bounds__(LOSS_BLOCK, PRECISE ? 1 : (WANT_GRAD ? LOSS_MINB : LOSS_MINB_FWD))
+loss_kernel(const __grid_constant__ LossParams P) {
+    if (!FILTER && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.ticket = 0u;   // loss_finalize_kernel runs after this grid
     loss_chunk<VEC, WANT_GRAD, GAMMA2, PRECISE, FILTER>(P, blockIdx.y, blockIdx.x);
+    if (FILTER) {            // the CTA that completes an image reduces it; the one that completes the batch finishes the step
+        __shared__ bool s_img_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_img_last = atomicAdd(P.img_ticket + blockIdx.y, 1u) == (unsigned)(P.chunks - 1);
+        }
+        __syncthreads();
+        if (s_img_last) finalize_image_fused(P, blockIdx.y);
+    }
 }
 
 // Fixed-order final reduction: block n reduces image n's chunk partials (thread-strided partial sums, then a
@@ -348,10 +372,6 @@ constexpr int FIN_BLOCK = 256;
 // Two parities: a rank can run at most one step ahead of the slowest reader of its previous values.
 constexpr int XCH_SLOT_WORDS = 2 * RN_MAX_PEERS * 4;
 constexpr long long XCH_TIMEOUT_CYCLES = 10000000000LL;        // ~5 s at 1.9 GHz (callers align the ranks before the first step)
-struct ExchangeDev {
-    unsigned long long *peers[RN_MAX_PEERS];
-    int rank, world;
-};
 __device__ __forceinline__ void st_sys_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -503,6 +523,22 @@ __global__ void __launch_bounds__(FIN_BLOCK) loss_finalize_kernel(const double *
     finalize_image(partials, fg_count, blockIdx.x, N, chunks, batch_div, out_image, out_total, tail, X);
 }
 
+__device__ void finalize_image_fused(const LossParams &P, int n) {
+    finalize_image(P.partials, P.fg_count, n, P.N, P.chunks, P.batch_div, P.out_image, P.out_total, P.tail, P.xch);
+}
+
+// rn_train_detect: everything the step's kernels expect to find zeroed, in ONE launch instead of three memset nodes.
+__global__ void __launch_bounds__(256) prep_kernel(int *fg_count, unsigned *img_ticket, unsigned *ticket, int *status,
+                                                   unsigned *img_count, int N) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        fg_count[i] = 0;
+        img_ticket[i] = 0u;
+        img_count[i] = 0u;
+    }
+    if (threadIdx.x < 4) status[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
 // host rn_exchange_t -> kernel parameter; returns false on a malformed descriptor
 inline bool make_exchange(const rn_exchange_t *x, ExchangeDev &X) {
     memset(&X, 0, sizeof(X));
@@ -574,7 +610,7 @@ extern "C" int rn_exchange_total(float *total, const rn_exchange_t *exchange_hos
 extern "C" size_t rn_loss_workspace_bytes(int N, int64_t A, int C) {
     (void)C;
     if (N <= 0 || A <= 0) return 16;
-    return ((size_t)N * (size_t)loss_chunks(A) * 2 + (size_t)N * 2 + 2) * sizeof(double);
+    return ((size_t)N * (size_t)loss_chunks(A) * 2 + (size_t)N * 2 + 2 + ((size_t)N + 1) / 2) * sizeof(double);
 }
 
 static int loss_impl(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
@@ -603,6 +639,9 @@ static int loss_impl(const float *logits, const float *bbox, const float *anchor
     P.gt = (const float4 *)gt_boxes; P.gt_off = gt_off; P.codes = codes; P.fg_count = fg_count;
     P.grad_logits = grad_logits; P.grad_bbox = (float4 *)grad_bbox; P.partials = (double *)workspace;
     P.ticket = (unsigned *)((double *)workspace + (size_t)N * loss_chunks(A) * 2 + 2 * (size_t)N);
+    P.img_ticket = (unsigned *)((double *)workspace + (size_t)N * loss_chunks(A) * 2 + 2 * (size_t)N + 2);
+    P.tail = (double *)workspace + (size_t)N * loss_chunks(A) * 2;
+    P.out_image = out_image; P.out_total = out_total; P.N = N; P.xch = X;
     P.A = A; P.anchor_stride = anchor_image_stride; P.C = C; P.chunks = loss_chunks(A);
     P.alpha = alpha; P.gamma = gamma; P.beta = beta; P.batch_div = batch_div;
     P.wts = make_float4(weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
@@ -622,12 +661,12 @@ static int loss_impl(const float *logits, const float *bbox, const float *anchor
         if (grad_logits) launch_loss_g<1, true>(P, grid, s, precise, false); else launch_loss_g<1, false>(P, grid, s, precise, false);
     }
     RN_CHECK_LAUNCH("rn_loss");
-    {
+    if (!filter) {           // (the FILTER variant of the kernel finishes the reduction itself)
         double *tail = (double *)workspace + (size_t)N * P.chunks * 2;
         loss_finalize_kernel<<<N, FIN_BLOCK, 0, s>>>((const double *)workspace, fg_count, N, P.chunks, batch_div, out_image,
                                                      out_total, tail, X);
+        RN_CHECK_LAUNCH("rn_loss_finalize");
     }
-    RN_CHECK_LAUNCH("rn_loss_finalize");
     return 0;
 }
 
@@ -697,11 +736,17 @@ extern "C" int rn_train_detect(const float *logits, const float *bbox, const flo
     void *pp_ws = (char *)workspace + lb;
     cudaStream_t s = (cudaStream_t)stream;
     rnpp::LazySink sink;
+    RN_CHECK_ARG(out_status && lb >= rn_loss_workspace_bytes(N, A, C), RN_E_BADARG, "rn_train_detect: null status");
     int rc = rnpp::lazy_begin(N, A, C, score_thr, max_det, pre_nms_topk, level_off_host, num_levels, cand_capacity, out_status,
-                              pp_ws, workspace_bytes - lb, s, &sink);
+                              pp_ws, workspace_bytes - lb, s, &sink, false);
     if (rc) return rc;
-    rc = rn_match(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, nullptr, codes,
-                  fg_count, stream);
+    {   // one launch zeroes what the step's kernels accumulate into (instead of three memset nodes)
+        double *base = (double *)workspace + (size_t)N * loss_chunks(A) * 2 + 2 * (size_t)N;
+        prep_kernel<<<1, 256, 0, s>>>(fg_count, (unsigned *)(base + 2), (unsigned *)base, out_status, sink.img_count, N);
+        RN_CHECK_LAUNCH("rn_train_detect/prep");
+    }
+    rc = rnpp::match_impl(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, nullptr,
+                          codes, fg_count, stream, false);
     if (rc) return rc;
     rc = loss_impl(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
                    weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, lb, stream, exchange_host,

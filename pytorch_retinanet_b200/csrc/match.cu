@@ -27,6 +27,7 @@
 //    y2>=y1, anchors with positive area); malformed GT boxes or anchors fall back — per GT box /
 //    per warp — to the unculled NaN-propagating path, other thresholds disable both tricks.
 #include "match_body.cuh"
+#include "pp_internal.cuh"
 
 namespace {
 
@@ -85,6 +86,14 @@ match_kernel(const float4 *__restrict__ anchors, long long A, long long anchor_s
 extern "C" int rn_match(const float *anchors, int64_t A, int64_t anchor_image_stride, const float *gt_boxes, const int64_t *gt_labels,
                         const int32_t *gt_off, int N, int64_t gt_total, float fg_thr, float bg_thr, int64_t *matches,
                         int32_t *codes, int32_t *fg_count, rn_stream_t stream) {
+    return rnpp::match_impl(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, matches,
+                            codes, fg_count, stream, true);
+}
+
+// zero_fg = false: the caller (rn_train_detect's prep kernel) already zeroed fg_count on the stream
+int rnpp::match_impl(const float *anchors, int64_t A, int64_t anchor_image_stride, const float *gt_boxes, const int64_t *gt_labels,
+                     const int32_t *gt_off, int N, int64_t gt_total, float fg_thr, float bg_thr, int64_t *matches,
+                     int32_t *codes, int32_t *fg_count, rn_stream_t stream, bool zero_fg) {
     RN_CHECK_ARG(anchors && gt_off, RN_E_BADARG, "rn_match: null anchors/gt_off");
     RN_CHECK_ARG(A >= 0 && N >= 0, RN_E_BADARG, "rn_match: negative size");
     RN_CHECK_ARG(anchor_image_stride == 0 || anchor_image_stride >= A, RN_E_BADARG, "rn_match: bad anchor_image_stride");
@@ -98,7 +107,7 @@ extern "C" int rn_match(const float *anchors, int64_t A, int64_t anchor_image_st
     RN_CHECK_ARG(N <= 65535, RN_E_TOOLARGE, "rn_match: N=%d exceeds 65535 images per call", N);
     if (A == 0 || N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (fg_count) {   // the per-image counters are accumulated with integer atomics: start from zero
+    if (fg_count && zero_fg) {   // the per-image counters are accumulated with integer atomics: start from zero
         cudaError_t e = cudaMemsetAsync(fg_count, 0, (size_t)N * sizeof(int32_t), s);
         if (e != cudaSuccess) { rn_set_error("rn_match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     }

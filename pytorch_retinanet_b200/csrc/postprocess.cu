@@ -1606,7 +1606,7 @@ static float guard_logit(float thr) {
 
 int rnpp::lazy_begin(int N, int64_t A, int C, float score_thr, int max_det, int pre_nms_topk, const int64_t *level_off_host,
                      int num_levels, int64_t cand_capacity, int32_t *out_status, void *workspace, size_t workspace_bytes,
-                     cudaStream_t s, rnpp::LazySink *sink) {
+                     cudaStream_t s, rnpp::LazySink *sink, bool zero) {
     RN_CHECK_ARG(out_status && workspace && sink, RN_E_BADARG, "rn_train_detect: null pointer");
     RN_CHECK_ARG(N > 0 && A > 0 && C > 0 && N <= 65535 && C <= 8192, RN_E_BADARG, "rn_train_detect: bad N/A/C");
     RN_CHECK_ARG(max_det >= 1 && max_det <= MAX_DET_CAP, RN_E_TOOLARGE, "rn_train_detect: max_det=%d outside [1,%d]", max_det, MAX_DET_CAP);
@@ -1618,9 +1618,11 @@ int rnpp::lazy_begin(int N, int64_t A, int C, float score_thr, int max_det, int 
     PPWorkspace w = carve(workspace, N, C, cand_capacity);
     RN_CHECK_ARG(workspace_bytes >= w.total_bytes, RN_E_WORKSPACE, "rn_train_detect: post-processing workspace too small (%zu < %zu)",
                  workspace_bytes, w.total_bytes);
-    cudaError_t e = cudaMemsetAsync(workspace, 0, w.zero_bytes, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(out_status, 0, 4 * sizeof(int32_t), s);
-    if (e != cudaSuccess) { rn_set_error("rn_train_detect: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    if (zero) {
+        cudaError_t e = cudaMemsetAsync(workspace, 0, w.zero_bytes, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(out_status, 0, 4 * sizeof(int32_t), s);
+        if (e != cudaSuccess) { rn_set_error("rn_train_detect: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     sink->img_count = w.img_count;
     sink->pool_key = w.pool_key;
     sink->cap_n = (u32)max((int64_t)1, cand_capacity / N);

@@ -37,7 +37,7 @@ def test_abi_exports_every_declared_symbol():
     assert lib.rn_exchange_total(one, ctypes.byref(bad), None) == -1
     assert lib.rn_comm_bytes() == 2048
     assert lib.rn_postprocess_workspace_bytes(16, 201600, 80, 1 << 20, 100) > (1 << 20) * 8
-    assert lib.rn_loss_workspace_bytes(16, 201600, 80) == (16 * 788 * 2 + 16 * 2 + 2) * 8
+    assert lib.rn_loss_workspace_bytes(16, 201600, 80) == (16 * 788 * 2 + 16 * 2 + 2 + 8) * 8
 
 
 def test_no_cpu_fallback_and_loud_failure():
