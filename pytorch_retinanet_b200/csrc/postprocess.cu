@@ -1227,6 +1227,7 @@ __global__ void __launch_bounds__(LZ2_BLOCK, 1) lazy2_nms_kernel(const __grid_co
                     __syncwarp();
                     if (__popc(vm) < 32) break;                       // the rest of the class lies beyond this wave
                 }
+                __syncwarp();                                         // every lane has read the class state lane 0 rewrites
                 if (lane == 0) {
                     S.cls_cur[c] = s0;
                     S.cls_kept[c] = kc;
