@@ -308,12 +308,14 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    def timed(fn, steps, streams=()):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        for s_ in streams:                                   # work the step put on its own streams is inside the timed region
+            torch.cuda.current_stream(dev).wait_stream(s_)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -346,13 +348,31 @@ def run_ours(args, rank, world, local_rank):
     d_cls2, d_box2 = d_cls.clone(), d_box.clone()
     graph2 = HotPathGraph(C, d_cls2, d_box2, anc0, batch["im_szs"], **gkw)
     gpend = []
+    use_pipe = not os.environ.get("RN_BENCH_NO_PIPELINE") and graph.fused
+    if use_pipe:
+        # the two buffers' graphs split into front (matcher, loss + filter) and tail (NMS) on two streams: the NMS of step
+        # i runs under the front of step i+1 (graphs.HotPathPipeline)
+        from pytorch_retinanet_b200.graphs import HotPathPipeline
+        pkw = {k: v for k, v in gkw.items() if k != "fused"}
+        pipe = HotPathPipeline(C, [(d_cls, d_box), (d_cls2, d_box2)], anc0, batch["im_szs"], **pkw)
+        pipe_streams = (pipe.front_stream, pipe.tail_stream)
+        nodes_per_step = pipe.kernel_nodes
 
-    def step_graph_pipelined():
-        g = graph if (len(gpend) == 0 or gpend[-1][0] is graph2) else graph2
-        gpend.append((g, g.step(targets)))                  # pack GT + graph launch (exchange inside the graph)
-        if len(gpend) > 1:
-            r = gpend.pop(0)[1]
-            return r.losses, r.detections(), r.grads        # detections() waits for that step's counts
+        def step_graph_pipelined():
+            gpend.append((pipe, pipe.step(targets)))        # pack GT + two graph launches (exchange inside the front)
+            if len(gpend) > 1:
+                r = gpend.pop(0)[1]
+                return r.losses, r.detections(), r.grads    # detections() waits for that step's counts
+    else:
+        pipe_streams = ()
+        nodes_per_step = graph.kernel_nodes
+
+        def step_graph_pipelined():
+            g = graph if (len(gpend) == 0 or gpend[-1][0] is graph2) else graph2
+            gpend.append((g, g.step(targets)))              # pack GT + graph launch (exchange inside the graph)
+            if len(gpend) > 1:
+                r = gpend.pop(0)[1]
+                return r.losses, r.detections(), r.grads    # detections() waits for that step's counts
 
     for _ in range(max(args.warmup, 4)):
         step_graph_pipelined()
@@ -360,9 +380,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = lib.rn_launch_count()
-    ms_step = timed(step_graph_pipelined, args.steps)
+    ms_step = timed(step_graph_pipelined, args.steps, pipe_streams)
     eager_launches = lib.rn_launch_count() - launches0      # launches our library issued directly (rn_pack_targets)
-    gpu_launches = int(eager_launches + args.steps * graph.kernel_nodes)
+    gpu_launches = int(eager_launches + args.steps * nodes_per_step)
     while gpend:
         gpend.pop(0)[1].detections()
     if args.only_step:
@@ -622,11 +642,14 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_roof_note": "raw cudaMemcpyAsync rate of the same pinned buffers with all ranks copying at once, measured in "
                                      "this run: e2e is bound by host->device ingest (PCIe / host memory), not by a kernel",
                     "placement": placement},
-            "api": {"value_through": "HotPathGraph.step: one CUDA graph of rn_train_loss (match+loss fwd+grad, exchange inside) || "
-                                     "rn_postprocess; two graphs / input buffers alternate, every step's losses, gradients and "
-                                     "detections are read one step late; anchors generated once (cached), outside the timed region",
-                    "pipeline": "2 input buffers x 2 CUDA graphs alternate; results of step i are read after step i+1 is launched "
-                                "(graph_sync = no pipelining)",
+            "api": {"value_through": "HotPathPipeline.step: rn_train_detect (matcher, then ONE pass over the logits for the loss with "
+                                     "gradients, the score filter and the final reduction incl. the multi-GPU exchange, then the "
+                                     "lazy NMS) captured as CUDA graphs on two alternating input buffers; every step's losses, "
+                                     "gradients and detections are read one step late; anchors generated once (cached), outside "
+                                     "the timed region" if use_pipe else "HotPathGraph.step on two alternating input buffers",
+                    "pipeline": "front (matcher + loss/filter) and tail (NMS) of a step are two graphs on two streams: the NMS of "
+                                "step i runs under the front of step i+1; results of step i are read after step i+1 is launched "
+                                "(graph_sync = one graph, no pipelining)",
                     "graph_sync": {"value": total / (ms_graph_sync * 1e-3), "unit": "images/s", "ms_per_step": ms_graph_sync,
                                    "note": "one graph, results read in the same step (one host sync per step)"},
                     "graph_host_enqueue_us": host_us_graph,
@@ -641,7 +664,7 @@ def run_ours(args, rank, world, local_rank):
                                          "note": "drop-in calls with process_detections_async: results of step i read while "
                                                  "step i+1 is enqueued"}},
             "gpu_launches": gpu_launches,
-            "gpu_launches_note": f"counted: {graph.kernel_nodes} kernel nodes recorded in the captured graph x {args.steps} replays + "
+            "gpu_launches_note": f"counted: {nodes_per_step} kernel nodes recorded in the captured graph(s) of a step x {args.steps} replays + "
                                  f"{eager_launches} launches issued directly by the library in the timed region (rn_launch_count)",
             "exchange": exchange_used, "parity_check": parity,
             "roofline": roofline, "cpu_baseline": cpu, "cuda_eager_baseline": cuda_eager, "n1_levels": n1, "extra": extra,

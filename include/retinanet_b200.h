@@ -167,7 +167,10 @@ int rn_train_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/
  * batch, e.g. detections during training).  Arguments and outputs are those of the two calls; results are identical to
  * calling them one after the other.  Needs C % 4 == 0, 16-byte aligned logits, A*C < 2^32 and the default math mode.
  * out_status as in rn_postprocess: a candidate-pool overflow or the fallback flag is resolved by calling
- * rn_postprocess on the same inputs.  workspace: rn_train_detect_workspace_bytes(N, A, C, cand_capacity, max_det).  */
+ * rn_postprocess on the same inputs.  workspace: rn_train_detect_workspace_bytes(N, A, C, cand_capacity, max_det).
+ * phases: 3 = the whole step; 1 = front only (zeroing, matcher, loss + score filter + final reduction), 2 = tail only (the
+ * NMS on the candidate lists of an earlier front call with the same arguments) — two calls let a caller put an event
+ * between them, so that the (latency-bound) NMS of one batch overlaps the front of the next on another stream.       */
 size_t rn_train_detect_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
 int rn_train_detect(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
                     const float *gt_boxes, const int64_t *gt_labels, const int32_t *gt_off, int N, int64_t gt_total,
@@ -178,7 +181,7 @@ int rn_train_detect(const float *logits, const float *bbox, const float *anchors
                     int pre_nms_topk, const int64_t *level_off_host /*[L+1] or NULL*/, int num_levels, int64_t cand_capacity,
                     float *out_boxes, float *out_scores, int64_t *out_labels, int32_t *out_count, int32_t *out_status,
                     const float *out_ratio_hw /*[N,2] or NULL*/, int out_format, void *workspace, size_t workspace_bytes,
-                    rn_stream_t stream, const rn_exchange_t *exchange_host /*or NULL*/);
+                    rn_stream_t stream, const rn_exchange_t *exchange_host /*or NULL*/, int phases);
 
 /* Dense element-wise losses, API parity with RetinaNetLosses.focal_loss (losses.py:29-47, arbitrary
  * float targets of the logits' shape, NO +1 shift) and RetinaNetLosses.smooth_l1_loss (losses.py:19-27).

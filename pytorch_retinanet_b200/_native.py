@@ -55,7 +55,7 @@ SIGNATURES = {
     "rn_train_detect_workspace_bytes": (_sz, [_c.c_int, _i64, _c.c_int, _i64, _c.c_int]),
     "rn_train_detect": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _c.c_int, _i64, _i64, _c.c_int, _f32, _f32, _f32, _f32, _f32,
                                    _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f64, _c.c_int, _c.c_int, _vp, _c.c_int,
-                                   _i64, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_int, _vp, _sz, _vp, _xp]),
+                                   _i64, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_int, _vp, _sz, _vp, _xp, _c.c_int]),
     "rn_dense_loss_workspace_bytes": (_sz, []),
     "rn_focal_loss_dense": (_c.c_int, [_vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "rn_smooth_l1_dense": (_c.c_int, [_vp, _vp, _i64, _f32, _vp, _vp, _vp, _sz, _vp]),

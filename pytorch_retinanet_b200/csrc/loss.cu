@@ -728,8 +728,9 @@ extern "C" int rn_train_detect(const float *logits, const float *bbox, const flo
                                int64_t cand_capacity, float *out_boxes, float *out_scores, int64_t *out_labels,
                                int32_t *out_count, int32_t *out_status, const float *out_ratio_hw, int out_format,
                                void *workspace, size_t workspace_bytes, rn_stream_t stream,
-                               const rn_exchange_t *exchange_host) {
+                               const rn_exchange_t *exchange_host, int phases) {
     RN_CHECK_ARG(gt_labels && codes && fg_count && workspace, RN_E_BADARG, "rn_train_detect: null pointer");
+    RN_CHECK_ARG(phases >= 1 && phases <= 3, RN_E_BADARG, "rn_train_detect: phases must be 1 (front), 2 (tail) or 3 (both)");
     RN_CHECK_ARG(N > 0 && A > 0 && C > 0, RN_E_BADARG, "rn_train_detect: N, A, C must be positive");
     const size_t lb = tdet_loss_bytes(N, A, C);
     RN_CHECK_ARG(workspace_bytes >= lb, RN_E_WORKSPACE, "rn_train_detect: workspace too small");
@@ -740,18 +741,21 @@ extern "C" int rn_train_detect(const float *logits, const float *bbox, const flo
     int rc = rnpp::lazy_begin(N, A, C, score_thr, max_det, pre_nms_topk, level_off_host, num_levels, cand_capacity, out_status,
                               pp_ws, workspace_bytes - lb, s, &sink, false);
     if (rc) return rc;
-    {   // one launch zeroes what the step's kernels accumulate into (instead of three memset nodes)
-        double *base = (double *)workspace + (size_t)N * loss_chunks(A) * 2 + 2 * (size_t)N;
-        prep_kernel<<<1, 256, 0, s>>>(fg_count, (unsigned *)(base + 2), (unsigned *)base, out_status, sink.img_count, N);
-        RN_CHECK_LAUNCH("rn_train_detect/prep");
+    if (phases & 1) {
+        {   // one launch zeroes what the step's kernels accumulate into (instead of three memset nodes)
+            double *base = (double *)workspace + (size_t)N * loss_chunks(A) * 2 + 2 * (size_t)N;
+            prep_kernel<<<1, 256, 0, s>>>(fg_count, (unsigned *)(base + 2), (unsigned *)base, out_status, sink.img_count, N);
+            RN_CHECK_LAUNCH("rn_train_detect/prep");
+        }
+        rc = rnpp::match_impl(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, nullptr,
+                              codes, fg_count, stream, false);
+        if (rc) return rc;
+        rc = loss_impl(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
+                       weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, lb, stream,
+                       exchange_host, &sink);
+        if (rc) return rc;
     }
-    rc = rnpp::match_impl(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, nullptr,
-                          codes, fg_count, stream, false);
-    if (rc) return rc;
-    rc = loss_impl(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
-                   weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, lb, stream, exchange_host,
-                   &sink);
-    if (rc) return rc;
+    if (!(phases & 2)) return 0;
     return rnpp::lazy_end(bbox, anchors, anchor_image_stride, im_hw, N, A, C, score_thr, nms_thr, max_det, weights_host,
                           pre_nms_topk, level_off_host, num_levels, cand_capacity, out_boxes, out_scores, out_labels, out_count,
                           out_status, pp_ws, s, out_ratio_hw, out_format);

@@ -45,21 +45,30 @@ class GraphStepResult:
         self._o = owner
         self._event = event
         self._dets = None
+        self._done = None            # set by HotPathPipeline: the step ran on another stream than the consumer's
+
+    def _consumer_waits(self) -> None:
+        if self._done is not None:
+            torch.cuda.current_stream(self._o.dev).wait_event(self._done)
+            self._done = None
 
     @property
     def losses(self) -> Dict[str, Tensor]:
         """{"classification_loss", "regression_loss"} of the (global) batch — device scalars, no sync."""
+        self._consumer_waits()
         t = self._o.total
         return {"classification_loss": t[0], "regression_loss": t[1]}
 
     @property
     def per_image(self) -> Tensor:
         """[N,3] = cls_i / max(1,F_i), reg_i / max(1,F_i), F_i."""
+        self._consumer_waits()
         return self._o.per_image
 
     @property
     def grads(self) -> Tuple[Tensor, Tensor]:
         """d(classification_loss)/d cls_preds and d(regression_loss)/d bbox_preds, already divided by the batch size."""
+        self._consumer_waits()
         return self._o.grad_cls_preds, self._o.grad_bbox_preds
 
     def result(self, cls_preds=None, bbox_preds=None):
@@ -72,6 +81,7 @@ class GraphStepResult:
         if not o.detect:
             raise RuntimeError("HotPathGraph was built with detect=False")
         if self._dets is None:
+            self._consumer_waits()
             self._event.synchronize()
             host = o._host.tolist()
             N = o.N
@@ -114,6 +124,9 @@ class HotPathGraph:
     ``fused`` (default: on whenever it applies — train and detect on ``[N,A,C]`` inputs with ``C % 4 == 0``): ONE pass
     over the logits serves both halves (``rn_train_detect``: the loss kernel is also the score filter; the NMS then runs
     behind it) instead of two concurrent branches that each stream the logits.  Same results.
+    ``split`` (fused graphs): capture the front (zeroing, matcher, loss + score filter + final reduction) and the tail
+    (the NMS) as TWO graphs, ``graph_front`` / ``graph_tail`` — what :class:`HotPathPipeline` launches on two streams so
+    that the NMS of one batch runs under the front of the next.
     """
 
     def __init__(self, num_classes: int, cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor,
@@ -125,7 +138,8 @@ class HotPathGraph:
                  alpha: float = FOCAL_LOSS_ALPHA, gamma: float = FOCAL_LOSS_GAMMA, beta: float = SMOOTH_L1_LOSS_BETA,
                  match_thr: float = IOU_THRESHOLDS_FOREGROUND, back_thr: float = IOU_THRESHOLDS_BACKGROUND,
                  cand_capacity: Optional[int] = None, concurrent: bool = True, pre_nms_topk: Optional[int] = None,
-                 level_offsets: Optional[Sequence[int]] = None, exchange="peer", fused: Optional[bool] = None):
+                 level_offsets: Optional[Sequence[int]] = None, exchange="peer", fused: Optional[bool] = None,
+                 split: bool = False):
         if not (train or detect):
             raise ValueError("HotPathGraph: nothing to do (train=False, detect=False)")
         lib = _native.load()
@@ -238,6 +252,9 @@ class HotPathGraph:
         if fused and not can_fuse:
             raise ValueError("HotPathGraph(fused=True) needs train and detect on [N,A,C] inputs with C % 4 == 0 (default math mode)")
         self.fused = can_fuse if fused is None else bool(fused)
+        self.split = bool(split)
+        if self.split and not self.fused:
+            raise ValueError("split=True needs a fused graph")
         if self.fused:
             self._td_ws_bytes = lib.rn_train_detect_workspace_bytes(N, A, C, self.cap, self.max_det)
             self._td_ws = torch.empty((self._td_ws_bytes,), dtype=torch.uint8, device=dev)
@@ -319,22 +336,29 @@ class HotPathGraph:
                                 _FORMATS[self.box_format])
         _native.check(rc, "rn_postprocess")
 
-    def _enqueue_fused(self):
-        """rn_train_detect: matcher, loss (+ gradients) that also filters the scores, final reduction, lazy NMS."""
+    def _enqueue_fused(self, phases: int = 3):
+        """rn_train_detect: matcher, loss (+ gradients) that also filters the scores and finishes the reduction (phase 1),
+        lazy NMS (phase 2)."""
         lib, N, A, C = self.lib, self.N, self.A, self.C
         alpha, gamma, beta, match_thr, back_thr = self.hp
         meta = self.meta.data_ptr()
-        rc = lib.rn_train_detect(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(), self.anchor_stride,
-                                 self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(), self.gt_off.data_ptr(), N, self.max_targets,
-                                 A, C, match_thr, back_thr, alpha, gamma, beta, _REG_WEIGHTS_C, self.batch_div,
-                                 self.codes.data_ptr(), self.fg.data_ptr(), self.per_image.data_ptr(), self.total.data_ptr(),
-                                 self.grad_cls_preds.data_ptr(), self.grad_bbox_preds.data_ptr(), self._hw.data_ptr(),
-                                 self.score_thres, self.nms_thres, self.max_det, self.topk, self._lvl,
-                                 (len(self.level_offsets) - 1) if self._lvl is not None else 0, self.cap,
-                                 self.out_boxes.data_ptr(), self.out_scores.data_ptr(), self.out_labels.data_ptr(), meta,
-                                 meta + 4 * N, None if self._ratio is None else self._ratio.data_ptr(), _FORMATS[self.box_format],
-                                 self._td_ws.data_ptr(), self._td_ws_bytes, _native.stream_ptr(self.dev), self._xref)
-        _native.check(rc, "rn_train_detect")
+
+        def call(phases):
+            rc = lib.rn_train_detect(self.cls_preds.data_ptr(), self.bbox_preds.data_ptr(), self.anchors.data_ptr(),
+                                     self.anchor_stride, self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(),
+                                     self.gt_off.data_ptr(), N, self.max_targets, A, C, match_thr, back_thr, alpha, gamma, beta,
+                                     _REG_WEIGHTS_C, self.batch_div, self.codes.data_ptr(), self.fg.data_ptr(),
+                                     self.per_image.data_ptr(), self.total.data_ptr(), self.grad_cls_preds.data_ptr(),
+                                     self.grad_bbox_preds.data_ptr(), self._hw.data_ptr(), self.score_thres, self.nms_thres,
+                                     self.max_det, self.topk, self._lvl,
+                                     (len(self.level_offsets) - 1) if self._lvl is not None else 0, self.cap,
+                                     self.out_boxes.data_ptr(), self.out_scores.data_ptr(), self.out_labels.data_ptr(), meta,
+                                     meta + 4 * N, None if self._ratio is None else self._ratio.data_ptr(),
+                                     _FORMATS[self.box_format], self._td_ws.data_ptr(), self._td_ws_bytes,
+                                     _native.stream_ptr(self.dev), self._xref, phases)
+            _native.check(rc, "rn_train_detect")
+
+        call(phases)
 
     def _enqueue_all(self):
         cur = torch.cuda.current_stream(self.dev)
@@ -361,9 +385,16 @@ class HotPathGraph:
             torch.cuda.current_stream(self.dev).wait_stream(warm)
             torch.cuda.synchronize(self.dev)
             recorded = self.lib.rn_launch_count()
-            with torch.cuda.graph(self.graph):
-                self._enqueue_all()
-            self.kernel_nodes = int(self.lib.rn_launch_count() - recorded)    # kernel launches recorded into the graph
+            if self.split:
+                self.graph_front, self.graph_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_front):
+                    self._enqueue_fused(1)
+                with torch.cuda.graph(self.graph_tail):
+                    self._enqueue_fused(2)
+            else:
+                with torch.cuda.graph(self.graph):
+                    self._enqueue_all()
+            self.kernel_nodes = int(self.lib.rn_launch_count() - recorded)    # kernel launches recorded into the graph(s)
 
     # ---- per step ----
     def load_targets(self, targets: Sequence[Dict[str, Tensor]]) -> None:
@@ -435,7 +466,11 @@ class HotPathGraph:
             self.load_targets(targets)
         self.steps_done += 1
         self.grads_taken = False
-        self.graph.replay()
+        if self.split:
+            self.graph_front.replay()
+            self.graph_tail.replay()
+        else:
+            self.graph.replay()
         if self.train and self.world > 1 and self._xch is None:
             import torch.distributed as dist
             dist.all_reduce(self.total, group=self.group)       # exchange="nccl": one 16-byte all-reduce after the graph
@@ -445,3 +480,54 @@ class HotPathGraph:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.dev))
         return GraphStepResult(self, ev)
+
+
+class HotPathPipeline:
+    """Two fused, split :class:`HotPathGraph` s on two input buffers: the fronts (zeroing, matcher, loss + score filter
+    — the HBM-bound part) run back to back on one stream, the tails (the latency-bound NMS: one SM per image) on a second
+    one, so the NMS of step i runs UNDER the front of step i+1.  The loss kernels themselves never overlap (two HBM-bound
+    kernels only slow each other down), and the order of the steps' exchanges is the order of the fronts on every rank.
+    Ordinary stream events order everything: tail(i) after front(i); front(i+2) after tail(i) (same buffer set).
+
+    ``inputs`` = two ``(cls_preds, bbox_preds)`` pairs (the static input buffers, written by the producer — e.g. the
+    head — in alternation); every other argument as for :class:`HotPathGraph`.  ``step(targets)`` runs the next buffer's
+    graphs and returns its :class:`GraphStepResult`; consuming a result one step late keeps the host off the critical
+    path.  Results are those of the single graph (the kernels and their arguments are the same)."""
+
+    def __init__(self, num_classes: int, inputs, anchors: Tensor, im_szs, **kw):
+        if len(inputs) != 2:
+            raise ValueError("HotPathPipeline takes exactly two (cls_preds, bbox_preds) input pairs")
+        dev = inputs[0][0].device
+        self.dev = dev
+        self.front_stream = torch.cuda.Stream(device=dev)
+        self.tail_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.graphs = [HotPathGraph(num_classes, x, b, anchors, im_szs, fused=True, split=True, **kw) for x, b in inputs]
+        self.kernel_nodes = self.graphs[0].kernel_nodes
+        self._tail_done = [None, None]
+        self._next = 0
+
+    def step(self, targets=None) -> GraphStepResult:
+        k = self._next
+        self._next = 1 - k
+        g, F, T = self.graphs[k], self.front_stream, self.tail_stream
+        F.wait_stream(torch.cuda.current_stream(self.dev))          # the producer wrote this buffer on the caller's stream
+        if self._tail_done[k] is not None:
+            F.wait_event(self._tail_done[k])                        # the tail of step i-2 still reads this buffer set
+        with torch.cuda.stream(F):
+            if g.train and targets is not None:
+                g.load_targets(targets)
+            g.steps_done += 1
+            g.grads_taken = False
+            g.graph_front.replay()
+            front = torch.cuda.Event()
+            front.record(F)
+        T.wait_event(front)
+        with torch.cuda.stream(T):
+            g.graph_tail.replay()
+            g._host.copy_(g.meta, non_blocking=True)                # the single D2H copy of the path
+            done = torch.cuda.Event()
+            done.record(T)
+        self._tail_done[k] = done
+        res = GraphStepResult(g, done)
+        res._done = done
+        return res

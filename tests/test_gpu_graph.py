@@ -277,3 +277,41 @@ def test_dropin_calls_in_graph_mode(P):
     out = Lg(tg, {"cls_preds": xg, "bbox_preds": bb}, [anc] * n_img)
     (2.0 * out["classification_loss"]).backward()
     assert torch.equal(xg.grad, 2.0 * want_gx)
+
+
+def test_pipeline_of_split_graphs_equals_single_graph(P):
+    """HotPathPipeline (front and tail of the fused step as two graphs on two streams, two input buffers) gives the
+    single graph's results, step after step, with results consumed one step late."""
+    from pytorch_retinanet_b200.graphs import HotPathGraph, HotPathPipeline
+    cfg = S.CONFIGS[1]
+    dev = torch.device("cuda")
+    n_img = 3
+    anc = S.default_anchors(cfg.padded_hw).to(dev)
+    bufs = [(torch.empty((n_img, anc.shape[0], cfg.num_classes), device=dev), torch.empty((n_img, anc.shape[0], 4), device=dev))
+            for _ in range(2)]
+    ref_x, ref_b = torch.empty_like(bufs[0][0]), torch.empty_like(bufs[0][1])
+    im_szs = [cfg.im_hw] * n_img
+    pipe = HotPathPipeline(cfg.num_classes, bufs, anc, im_szs, max_targets=1024)
+    single = HotPathGraph(cfg.num_classes, ref_x, ref_b, anc, im_szs, max_targets=1024, fused=False)
+    pending, want = [], []
+    for step in range(7):
+        b = S.make_batch(cfg, 20 * step, n_img, clustered=True)
+        tg = to_cuda_targets(b["targets"])
+        x, bb = bufs[step % 2]
+        x.copy_(b["cls_preds"])
+        bb.copy_(b["bbox_preds"])
+        ref_x.copy_(b["cls_preds"])
+        ref_b.copy_(b["bbox_preds"])
+        r = single.step(tg)
+        want.append((r.losses["classification_loss"].clone(), r.losses["regression_loss"].clone(), r.grads[0].clone(),
+                     r.grads[1].clone(), [{k: v.clone() for k, v in d.items()} for d in r.detections()]))
+        pending.append(pipe.step(tg))
+        if len(pending) > 1:                       # consume step-1 after launching this step
+            got, w = pending.pop(0), want.pop(0)
+            assert torch.equal(got.losses["classification_loss"], w[0]) and torch.equal(got.losses["regression_loss"], w[1])
+            # (the gradients of that step are still intact: the other buffer set is in use now)
+            assert torch.equal(got.grads[0], w[2]) and torch.equal(got.grads[1], w[3])
+            _assert_same_dets(got.detections(), w[4])
+    got, w = pending.pop(0), want.pop(0)
+    assert torch.equal(got.losses["classification_loss"], w[0]) and torch.equal(got.grads[0], w[2])
+    _assert_same_dets(got.detections(), w[4])
