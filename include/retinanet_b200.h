@@ -168,9 +168,10 @@ int rn_train_loss(const float *logits /*[N,A,C]*/, const float *bbox /*[N,A,4]*/
  * calling them one after the other.  Needs C % 4 == 0, 16-byte aligned logits, A*C < 2^32 and the default math mode.
  * out_status as in rn_postprocess: a candidate-pool overflow or the fallback flag is resolved by calling
  * rn_postprocess on the same inputs.  workspace: rn_train_detect_workspace_bytes(N, A, C, cand_capacity, max_det).
- * phases: 3 = the whole step; 1 = front only (zeroing, matcher, loss + score filter + final reduction), 2 = tail only (the
- * NMS on the candidate lists of an earlier front call with the same arguments) — two calls let a caller put an event
- * between them, so that the (latency-bound) NMS of one batch overlaps the front of the next on another stream.       */
+ * phases: mask of 1 (zeroing + matcher), 4 (loss + score filter + final reduction) and 2 (the NMS on the candidate lists
+ * the loss phase filled); 7 = the whole step.  Separate calls with the same arguments let a caller put the phases on
+ * different streams: the ALU-bound matcher of the next batch and the latency-bound NMS of the previous one then run
+ * under the HBM-bound loss kernel of the current one (graphs.HotPathPipeline).                                      */
 size_t rn_train_detect_workspace_bytes(int N, int64_t A, int C, int64_t cand_capacity, int max_det);
 int rn_train_detect(const float *logits, const float *bbox, const float *anchors, int64_t anchor_image_stride,
                     const float *gt_boxes, const int64_t *gt_labels, const int32_t *gt_off, int N, int64_t gt_total,

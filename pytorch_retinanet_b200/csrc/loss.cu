@@ -730,7 +730,7 @@ extern "C" int rn_train_detect(const float *logits, const float *bbox, const flo
                                void *workspace, size_t workspace_bytes, rn_stream_t stream,
                                const rn_exchange_t *exchange_host, int phases) {
     RN_CHECK_ARG(gt_labels && codes && fg_count && workspace, RN_E_BADARG, "rn_train_detect: null pointer");
-    RN_CHECK_ARG(phases >= 1 && phases <= 3, RN_E_BADARG, "rn_train_detect: phases must be 1 (front), 2 (tail) or 3 (both)");
+    RN_CHECK_ARG(phases >= 1 && phases <= 7, RN_E_BADARG, "rn_train_detect: phases is a mask of 1 (matcher), 4 (loss), 2 (NMS)");
     RN_CHECK_ARG(N > 0 && A > 0 && C > 0, RN_E_BADARG, "rn_train_detect: N, A, C must be positive");
     const size_t lb = tdet_loss_bytes(N, A, C);
     RN_CHECK_ARG(workspace_bytes >= lb, RN_E_WORKSPACE, "rn_train_detect: workspace too small");
@@ -750,6 +750,8 @@ extern "C" int rn_train_detect(const float *logits, const float *bbox, const flo
         rc = rnpp::match_impl(anchors, A, anchor_image_stride, gt_boxes, gt_labels, gt_off, N, gt_total, fg_thr, bg_thr, nullptr,
                               codes, fg_count, stream, false);
         if (rc) return rc;
+    }
+    if (phases & 4) {
         rc = loss_impl(logits, bbox, anchors, anchor_image_stride, gt_boxes, gt_off, codes, fg_count, N, A, C, alpha, gamma, beta,
                        weights_host, batch_div, out_image, out_total, grad_logits, grad_bbox, workspace, lb, stream,
                        exchange_host, &sink);
