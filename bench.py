@@ -647,9 +647,9 @@ def run_ours(args, rank, world, local_rank):
                                      "lazy NMS) captured as CUDA graphs on two alternating input buffers; every step's losses, "
                                      "gradients and detections are read one step late; anchors generated once (cached), outside "
                                      "the timed region" if use_pipe else "HotPathGraph.step on two alternating input buffers",
-                    "pipeline": "matcher, loss (+filter) and NMS of a step are three graphs on three streams: the matcher of step "
-                                "i+1 and the NMS of step i-1 run under the loss kernel of step i; loss kernels never overlap; "
-                                "results of step i are read after step i+1 is launched (graph_sync = one graph, no pipelining)",
+                    "pipeline": "front (matcher + loss/filter) and tail (NMS) of a step are two graphs on two streams: the NMS of "
+                                "step i runs under the front of step i+1; results of step i are read after step i+1 is launched "
+                                "(graph_sync = one graph, no pipelining)",
                     "graph_sync": {"value": total / (ms_graph_sync * 1e-3), "unit": "images/s", "ms_per_step": ms_graph_sync,
                                    "note": "one graph, results read in the same step (one host sync per step)"},
                     "graph_host_enqueue_us": host_us_graph,

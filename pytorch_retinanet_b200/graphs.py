@@ -124,9 +124,9 @@ class HotPathGraph:
     ``fused`` (default: on whenever it applies — train and detect on ``[N,A,C]`` inputs with ``C % 4 == 0``): ONE pass
     over the logits serves both halves (``rn_train_detect``: the loss kernel is also the score filter; the NMS then runs
     behind it) instead of two concurrent branches that each stream the logits.  Same results.
-    ``split`` (fused graphs): capture the matcher (+ zeroing), the loss (+ score filter + final reduction) and the NMS as
-    THREE graphs, ``graph_match`` / ``graph_loss`` / ``graph_tail`` — what :class:`HotPathPipeline` launches on three
-    streams so that the matcher of the next batch and the NMS of the previous one run under the loss kernel.
+    ``split`` (fused graphs): capture the front (zeroing, matcher, loss + score filter + final reduction) and the tail
+    (the NMS) as TWO graphs, ``graph_front`` / ``graph_tail`` — what :class:`HotPathPipeline` launches on two streams so
+    that the NMS of one batch runs under the front of the next.
     """
 
     def __init__(self, num_classes: int, cls_preds: Tensor, bbox_preds: Tensor, anchors: Tensor,
@@ -386,12 +386,9 @@ class HotPathGraph:
             torch.cuda.synchronize(self.dev)
             recorded = self.lib.rn_launch_count()
             if self.split:
-                self.graph_match, self.graph_loss, self.graph_tail = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(),
-                                                                      torch.cuda.CUDAGraph())
-                with torch.cuda.graph(self.graph_match):
-                    self._enqueue_fused(1)
-                with torch.cuda.graph(self.graph_loss):
-                    self._enqueue_fused(4)
+                self.graph_front, self.graph_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_front):
+                    self._enqueue_fused(1 | 4)
                 with torch.cuda.graph(self.graph_tail):
                     self._enqueue_fused(2)
             else:
@@ -470,8 +467,7 @@ class HotPathGraph:
         self.steps_done += 1
         self.grads_taken = False
         if self.split:
-            self.graph_match.replay()
-            self.graph_loss.replay()
+            self.graph_front.replay()
             self.graph_tail.replay()
         else:
             self.graph.replay()
@@ -487,12 +483,14 @@ class HotPathGraph:
 
 
 class HotPathPipeline:
-    """Two fused, split :class:`HotPathGraph` s on two input buffers, three streams: the loss kernels (one pass over the
-    logits: loss, gradients, score filter, final reduction — the HBM-bound part) run back to back on one stream; the
-    matcher of step i+1 (ALU-bound) and the NMS of step i-1 (latency-bound, one SM per image) run on two other streams,
-    i.e. UNDER the loss kernel of step i.  The loss kernels themselves never overlap (two HBM-bound kernels only slow each
-    other down), and the order of the steps' exchanges is the order of the loss kernels on every rank.  Ordinary stream
-    events order everything: loss(i) after match(i); NMS(i) after loss(i); match(i+2) after NMS(i) (same buffer set).
+    """Two fused, split :class:`HotPathGraph` s on two input buffers: the fronts (zeroing, matcher, loss + score filter
+    — the HBM-bound part) run back to back on one stream, the tails (the latency-bound NMS: one SM per image) on a second
+    one, so the NMS of step i runs UNDER the front of step i+1.  The loss kernels themselves never overlap (two HBM-bound
+    kernels only slow each other down), and the order of the steps' exchanges is the order of the fronts on every rank.
+    Ordinary stream events order everything: tail(i) after front(i); front(i+2) after tail(i) (same buffer set).
+    (Measured on B200, config 2: 0.432 ms per step against 0.468 ms for the single graph.  Putting the ALU-bound matcher
+    of step i+1 on a third stream under the loss kernel of step i as well was measured too: 0.503 ms — its CTAs displace
+    the streaming kernel's, as the single-launch fusions of round 1 already showed; not shipped.)
 
     ``inputs`` = two ``(cls_preds, bbox_preds)`` pairs (the static input buffers, written by the producer — e.g. the
     head — in alternation); every other argument as for :class:`HotPathGraph`.  ``step(targets)`` runs the next buffer's
@@ -504,10 +502,9 @@ class HotPathPipeline:
             raise ValueError("HotPathPipeline takes exactly two (cls_preds, bbox_preds) input pairs")
         dev = inputs[0][0].device
         self.dev = dev
-        self.match_stream = torch.cuda.Stream(device=dev, priority=-1)
-        self.loss_stream = torch.cuda.Stream(device=dev)
+        self.front_stream = torch.cuda.Stream(device=dev)
         self.tail_stream = torch.cuda.Stream(device=dev, priority=-1)
-        self.streams = (self.match_stream, self.loss_stream, self.tail_stream)
+        self.streams = (self.front_stream, self.tail_stream)
         self.graphs = [HotPathGraph(num_classes, x, b, anchors, im_szs, fused=True, split=True, **kw) for x, b in inputs]
         self.kernel_nodes = self.graphs[0].kernel_nodes
         self._tail_done = [None, None]
@@ -516,23 +513,16 @@ class HotPathPipeline:
     def step(self, targets=None) -> GraphStepResult:
         k = self._next
         self._next = 1 - k
-        g, M, F, T = self.graphs[k], self.match_stream, self.loss_stream, self.tail_stream
-        cur = torch.cuda.current_stream(self.dev)
-        M.wait_stream(cur)                                          # (targets may have been produced on the caller's stream)
+        g, F, T = self.graphs[k], self.front_stream, self.tail_stream
+        F.wait_stream(torch.cuda.current_stream(self.dev))          # the producer wrote this buffer on the caller's stream
         if self._tail_done[k] is not None:
-            M.wait_event(self._tail_done[k])                        # the NMS of step i-2 still uses this buffer set
-        with torch.cuda.stream(M):
+            F.wait_event(self._tail_done[k])                        # the tail of step i-2 still reads this buffer set
+        with torch.cuda.stream(F):
             if g.train and targets is not None:
                 g.load_targets(targets)
             g.steps_done += 1
             g.grads_taken = False
-            g.graph_match.replay()
-            matched = torch.cuda.Event()
-            matched.record(M)
-        F.wait_stream(cur)                                          # the producer wrote this buffer on the caller's stream
-        F.wait_event(matched)
-        with torch.cuda.stream(F):
-            g.graph_loss.replay()
+            g.graph_front.replay()
             front = torch.cuda.Event()
             front.record(F)
         T.wait_event(front)
