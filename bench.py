@@ -561,9 +561,9 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "rn_train_loss = match_kernel + loss_kernel<4,grad> + finalize (training loss, "
                                           "fwd+grad in one pass over the logits)",
                 "achieved": ach_fb, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach_fb / peak,
-                "traffic": 2.076e9 + 4.9e6,
-                "traffic_source": "NOT measured in this run: one `ncu --set full` capture of the same launch (loss_kernel 1.047 GB "
-                                  "read + 1.029 GB write, match_kernel 3.3 MB, finalize < 1 MB), profiles/r01_ncu_graph_step_summary.txt",
+                "traffic": 2.094e9 + 3.3e6 + 0.2e6,
+                "traffic_source": "NOT measured in this run: one `ncu --set full` capture of the same launches (loss_kernel 1.059 GB "
+                                  "read + 1.035 GB write, match_kernel 3.3 MB, finalize 0.2 MB), profiles/r02_ncu_loss_summary.txt",
                 "bytes_per_launch": bytes_fb, "ms_per_launch": kern["loss_fwd_bwd"],
                 "others": {"loss_fwd": bw(bytes_f, kern["loss_fwd"], "matcher + forward-only loss kernel + finalize (the reference's "
                                                                       "validation_step path)"),

@@ -523,6 +523,9 @@ class HotPathPipeline:
             g.steps_done += 1
             g.grads_taken = False
             g.graph_front.replay()
+            if g.train and g.world > 1 and g._xch is None:          # exchange="nccl": one 16-byte all-reduce behind the front
+                import torch.distributed as dist
+                dist.all_reduce(g.total, group=g.group)
             front = torch.cuda.Event()
             front.record(F)
         T.wait_event(front)

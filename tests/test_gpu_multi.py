@@ -26,6 +26,7 @@ def _worker(rank, world, port, ret, mode):
 
 def _worker_body(rank, world, port, ret, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))      # the CPU oracle runs in every rank: do not oversubscribe
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     sys.path.insert(0, ROOT)
@@ -149,11 +150,11 @@ def test_sharded_loss_multi_gpu(ranks, mode):
     ret = mgr.dict()
     ctx = mp.spawn(_worker, args=(world, 29700 + (os.getpid() + 7 * ranks + (3 if mode == "peer" else 0)) % 1000, ret, mode),
                    nprocs=world, join=False)
-    deadline = time.time() + 240                    # a rank that stops taking part must not hang the suite
+    deadline = time.time() + 900                    # a rank that stops taking part must not hang the suite (8 ranks: ~3 min)
     try:
         while not ctx.join(timeout=5):
             if time.time() > deadline:
-                raise TimeoutError("multi-GPU worker processes did not finish within 240 s")
+                raise TimeoutError("multi-GPU worker processes did not finish within 900 s")
     finally:
         for p in ctx.processes:
             if p.is_alive():

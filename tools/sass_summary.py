@@ -13,8 +13,8 @@ LIB = os.path.join(ROOT, "pytorch_retinanet_b200", "lib", "librn_b200.so")
 WANT = ["loss_kernel", "loss_levels_kernel", "loss_finalize_kernel", "exchange_kernel", "match_kernel", "score_filter_kernel",
         "score_filter_levels_kernel", "lazy2_nms_kernel", "lazy_nms_kernel", "nms_kernel", "image_topk_kernel",
         "anchor_grid_kernel", "pack_targets_kernel"]
-KEYS = ["LDG.E.128", "LDG.E.NA.128", "LDG.E.64", "LDG.E", "STG.E.128", "STG.E.NA.128", "STG.E", "LD.E.64.STRONG.SYS", "ST.E.64.STRONG.SYS",
-        "LDG.E.64.STRONG.SYS", "STG.E.64.STRONG.SYS", "MUFU.EX2", "MUFU.RCP", "MUFU.LG2", "FFMA", "FMUL", "FADD", "REDUX", "VOTE", "MATCH",
+KEYS = ["LDG.E.64.STRONG.SYS", "STG.E.64.STRONG.SYS", "LD.E.64.STRONG.SYS", "ST.E.64.STRONG.SYS",
+        "LDG.E.128", "LDG.E.NA.128", "LDG.E.64", "LDG.E", "STG.E.128", "STG.E.NA.128", "STG.E", "MUFU.EX2", "MUFU.RCP", "MUFU.LG2", "FFMA", "FMUL", "FADD", "REDUX", "VOTE", "MATCH",
         "SHFL", "ATOMS", "ATOMG", "RED", "BAR.SYNC", "LDS", "STS", "DFMA", "DADD", "CS2R", "UTMALDG", "UTCMMA"]
 
 
