@@ -36,6 +36,15 @@ def test_abi_exports_every_declared_symbol():
     bad.rank, bad.world = 3, 2
     assert lib.rn_exchange_total(one, ctypes.byref(bad), None) == -1
     assert lib.rn_comm_bytes() == 2048
+    # rn_train_detect: argument errors before any launch (phases mask, null pointers, workspace size)
+    args = [one] * 3 + [0] + [one] * 3 + [2, 10, 100, 4, 0.5, 0.4, 0.25, 2.0, 0.1, one, 2.0] + [one] * 7 + \
+           [0.05, 0.5, 100, 0, None, 0, 1 << 16] + [one] * 6 + [0, one, 1 << 30, None, None, 9]
+    assert lib.rn_train_detect(*args) == -1 and b"phases" in lib.rn_last_error()
+    args[-1] = 7
+    args[-4] = 16                                           # workspace far too small
+    assert lib.rn_train_detect(*args) == -3
+    assert lib.rn_train_detect_workspace_bytes(16, 201600, 80, 1 << 20, 100) > \
+        lib.rn_loss_workspace_bytes(16, 201600, 80) + lib.rn_postprocess_workspace_bytes(16, 201600, 80, 1 << 20, 100) - 512
     assert lib.rn_postprocess_workspace_bytes(16, 201600, 80, 1 << 20, 100) > (1 << 20) * 8
     assert lib.rn_loss_workspace_bytes(16, 201600, 80) == (16 * 788 * 2 + 16 * 2 + 2 + 8) * 8
 
