@@ -354,6 +354,8 @@ def run_ours(args, rank, world, local_rank):
         # i runs under the front of step i+1 (graphs.HotPathPipeline)
         from pytorch_retinanet_b200.graphs import HotPathPipeline
         pkw = {k: v for k, v in gkw.items() if k != "fused"}
+        if os.environ.get("RN_BENCH_EXCHANGE_ON_TAIL"):      # EXPERIMENTAL, see HotPathGraph(exchange_on_tail=...)
+            pkw["exchange_on_tail"] = True
         pipe = HotPathPipeline(C, [(d_cls, d_box), (d_cls2, d_box2)], anc0, batch["im_szs"], **pkw)
         pipe_streams = pipe.streams
         nodes_per_step = pipe.kernel_nodes
@@ -421,13 +423,15 @@ def run_ours(args, rank, world, local_rank):
     ms_dropin_graph = None
     if world == 1:                                          # (single-GPU mode: the sharded loss keeps the eager path)
         def step_dropin_graph():
+            # graph mode makes the host side of both calls cheap, so the training half goes FIRST (no host sync in it) and
+            # the inference half — whose result read is the step's one host sync — is enqueued behind it while it runs
             anchors = gen(images, fmaps)
-            dets = P.process_detections(stub_g, {"cls_preds": d_cls, "bbox_preds": d_box}, anchors, batch["im_szs"])
             x, b = d_cls.detach().requires_grad_(True), d_box.detach().requires_grad_(True)
             out = losses_g(targets, {"cls_preds": x, "bbox_preds": b}, anchors)
             # autograd.grad hands the gradients on as a model's backward would (to the head's CatBackward); .backward()
             # on these LEAF tensors would make AccumulateGrad clone the graph's static 1 GB buffer
             gx, gb_ = torch.autograd.grad(out["classification_loss"] + out["regression_loss"], (x, b))
+            dets = P.process_detections(stub_g, {"cls_preds": d_cls, "bbox_preds": d_box}, anchors, batch["im_szs"])
             return out, dets, gx
 
         for _ in range(3):

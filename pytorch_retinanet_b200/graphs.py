@@ -139,7 +139,7 @@ class HotPathGraph:
                  match_thr: float = IOU_THRESHOLDS_FOREGROUND, back_thr: float = IOU_THRESHOLDS_BACKGROUND,
                  cand_capacity: Optional[int] = None, concurrent: bool = True, pre_nms_topk: Optional[int] = None,
                  level_offsets: Optional[Sequence[int]] = None, exchange="peer", fused: Optional[bool] = None,
-                 split: bool = False):
+                 split: bool = False, exchange_on_tail: bool = False):
         if not (train or detect):
             raise ValueError("HotPathGraph: nothing to do (train=False, detect=False)")
         lib = _native.load()
@@ -255,6 +255,10 @@ class HotPathGraph:
         self.split = bool(split)
         if self.split and not self.fused:
             raise ValueError("split=True needs a fused graph")
+        # EXPERIMENTAL (not yet validated on hardware, off by default): in a split graph, leave the loss kernel's total
+        # local and sum it over the ranks with the stand-alone exchange kernel at the head of the TAIL graph — the
+        # lock-step wait for the slowest rank then sits on the tail stream, off the critical path of the fronts.
+        self.exchange_on_tail = bool(exchange_on_tail) and self.split and self._xch is not None
         if self.fused:
             self._td_ws_bytes = lib.rn_train_detect_workspace_bytes(N, A, C, self.cap, self.max_det)
             self._td_ws = torch.empty((self._td_ws_bytes,), dtype=torch.uint8, device=dev)
@@ -355,9 +359,15 @@ class HotPathGraph:
                                      self.out_boxes.data_ptr(), self.out_scores.data_ptr(), self.out_labels.data_ptr(), meta,
                                      meta + 4 * N, None if self._ratio is None else self._ratio.data_ptr(),
                                      _FORMATS[self.box_format], self._td_ws.data_ptr(), self._td_ws_bytes,
-                                     _native.stream_ptr(self.dev), self._xref, phases)
+                                     _native.stream_ptr(self.dev), xref, phases)
             _native.check(rc, "rn_train_detect")
 
+        xref = self._xref
+        if self.exchange_on_tail and phases != 7:            # (the eager warm-up, phases 7, keeps the in-kernel exchange)
+            xref = None
+            if phases & 2:
+                rc = lib.rn_exchange_total(self.total.data_ptr(), self._xref, _native.stream_ptr(self.dev))
+                _native.check(rc, "rn_exchange_total")
         call(phases)
 
     def _enqueue_all(self):
