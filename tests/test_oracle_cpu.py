@@ -153,6 +153,38 @@ def test_oracle_matches_live_reference():
             assert torch.equal(a["boxes"], b_["boxes"])
 
 
+@pytest.mark.skipif(not reference_available(), reason="no reference tree (baseline/_ref, /root/reference)")
+def test_label_zero_and_separate_backward_match_live_reference():
+    """Pins two behaviours the GPU tests check against the oracle: (1) a label 0 is the reference's class id 0 — all-zero
+    class targets after the [:,1:] slice, regression term and foreground count kept (losses.py:96-103); a label > C makes
+    the reference's one_hot raise; (2) the two losses can be back-propagated one after the other (retain_graph), the
+    class loss sends no gradient to bbox_preds."""
+    from oracle.ref_shim import load_reference
+    ref = load_reference()
+    gen = torch.Generator().manual_seed(5)
+    anc = O.image_anchors(O.fpn_grid_sizes(128, 160))
+    gt = S._gt_boxes(gen, 12, (128, 160))
+    lab = torch.randint(1, 8, (12,), generator=gen)
+    lab[::2] = 0
+    cls = (torch.randn((1, anc.shape[0], 7), generator=gen) - 3).requires_grad_(True)
+    bb = (torch.randn((1, anc.shape[0], 4), generator=gen) * 0.2).requires_grad_(True)
+    tg = [{"boxes": gt, "labels": lab}]
+    lr = ref.losses.RetinaNetLosses(7)(tg, {"cls_preds": cls, "bbox_preds": bb}, [anc])
+    co = cls.detach().clone().requires_grad_(True)
+    bo = bb.detach().clone().requires_grad_(True)
+    lo = O.batch_loss(tg, co, bo, [anc], 7)
+    assert all(torch.equal(lr[k], lo[k]) for k in lr) and float(lr["regression_loss"]) > 0
+    lr["classification_loss"].backward(retain_graph=True)
+    lo["classification_loss"].backward(retain_graph=True)
+    assert bb.grad is None and bo.grad is None
+    lr["regression_loss"].backward()
+    lo["regression_loss"].backward()
+    assert torch.equal(cls.grad, co.grad) and torch.equal(bb.grad, bo.grad)
+    lab_bad = torch.full_like(lab, 9)                               # > C: the reference cannot build the one-hot rows
+    with pytest.raises(Exception):
+        ref.losses.RetinaNetLosses(7)([{"boxes": gt, "labels": lab_bad}], {"cls_preds": cls.detach(), "bbox_preds": bb.detach()}, [anc])
+
+
 def test_degenerate_inputs_both_oracles_agree():
     """Adversarial inputs for the two restatements (torch op-for-op and plain C): exact-threshold IoUs, ties, duplicate
     and zero-area boxes, NaN / inf coordinates, equal NMS scores.  The torch oracle is the reference's own op
