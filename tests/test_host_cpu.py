@@ -118,11 +118,12 @@ def _worker(rank, world, port, ret):
                 gt, lab = packed.boxes[off[i]:off[i + 1]], packed.labels[off[i]:off[i + 1]]
                 r, c, _, f = O.image_loss(anchors, cls[i], box[i], lab, gt if off[i + 1] > off[i] else gt[:0], cls.shape[-1])
                 rows.append(torch.stack([c, r, f.float()]))
-            image = torch.stack(rows)
+            image = torch.stack(rows) if rows else torch.zeros((0, 3))
             c, r = image[:, 0].sum() / hp["batch_div"], image[:, 1].sum() / hp["batch_div"]
             total = torch.stack([c.detach(), r.detach(), image[:, 2].sum().detach(), torch.tensor(float(cls.shape[0]))])
             if hp.get("all_reduce_group", False) is not False:
                 dist.all_reduce(total, group=hp["all_reduce_group"])
+            total[:2] *= hp.get("total_scale", 1.0)           # grad_reduction="mean": local values carry a factor world
             # value of the global batch, gradient of the local shard (what the CUDA autograd function does)
             return c + (total[0] - c.detach()), r + (total[1] - r.detach()), image.detach(), total
 
@@ -144,6 +145,18 @@ def _worker(rank, world, port, ret):
           and abs(float(out["regression_loss"]) - float(full["regression_loss"])) <= 1e-5 * float(full["regression_loss"])
           and torch.allclose(x.grad, xf.grad[lo:hi], rtol=1e-5, atol=1e-12)
           and int(L.last_stats[3]) == n_total)
+    # fewer images than ranks: rank 0's shard is EMPTY and must still take part in the exchange (no anchors / targets to
+    # look at on that rank), in both gradient conventions
+    b1 = S.make_batch(cfg, 9, 1, clustered=True)
+    lo, hi = D.shard_range(1, rank, world)
+    full1 = O.batch_loss(b1["targets"], b1["cls_preds"], b1["bbox_preds"], [b1["anchors"]], cfg.num_classes)
+    for red in ("sum", "mean"):
+        L1 = D.ShardedRetinaNetLosses(cfg.num_classes, grad_reduction=red)
+        x1 = b1["cls_preds"][lo:hi].clone().requires_grad_(True)
+        out1 = L1(b1["targets"][lo:hi], {"cls_preds": x1, "bbox_preds": b1["bbox_preds"][lo:hi]}, [b1["anchors"]] * (hi - lo))
+        ok = ok and (hi - lo) == (0 if rank == 0 else 1)
+        ok = ok and abs(float(out1["classification_loss"]) - float(full1["classification_loss"])) <= 1e-5 * float(full1["classification_loss"])
+        ok = ok and int(L1.last_stats[3]) == 1
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
