@@ -715,6 +715,8 @@ def parity_check(P, HotPathGraph, losses_cls, xch, rank, world, dev, dist):
     x = b["cls_preds"][lo:lo + per].to(dev)
     bb = b["bbox_preds"][lo:lo + per].to(dev)
     tg = [{k: v.to(dev) for k, v in t.items()} for t in b["targets"][lo:lo + per]]
+    if world > 1:
+        dist.barrier()                                       # the first exchange follows: the ranks start it together
     g = HotPathGraph(cfg.num_classes, x, bb, anc, b["im_szs"][:per], global_batch=n_tot if world > 1 else None,
                      exchange=xch if xch is not None else "nccl")
     r = g.step(tg)
