@@ -812,6 +812,9 @@ def other_configs(S, P, HotPathGraph, lib, dev, rank, world, timed, peak, xch, a
     b = S.make_batch_device(c3, rank * per, per, dev)
     A, C = b["anchors"].shape[0], c3.num_classes
     gsum = sum(int(t["boxes"].shape[0]) for t in b["targets"])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()                                       # the graph's warm-up exchanges: the ranks start together
     g = HotPathGraph(C, b["cls_preds"], b["bbox_preds"], b["anchors"], b["im_szs"], max_targets=max(4096, gsum),
                      global_batch=c3.batch if world > 1 else None, exchange=xch if xch is not None else "nccl")
 
