@@ -10,10 +10,12 @@ from .anchors import AnchorGenerator, BufferList
 from .box_utils import activ_2_bbox, bbox_2_activ, convert_x1y1x2y2, convert_xywh, matcher
 from .detections import (PendingDetections, postprocess_batch, postprocess_batch_async, process_detections,
                          process_detections_async)
-from .graphs import HotPathGraph
+from .graphs import HotPathGraph, HotPathPipeline
 from .integration import patch_retinanet
 from .losses import RetinaNetLosses
 
 __all__ = ["AnchorGenerator", "BufferList", "matcher", "bbox_2_activ", "activ_2_bbox", "convert_xywh",
            "convert_x1y1x2y2", "RetinaNetLosses", "process_detections", "process_detections_async", "postprocess_batch", "postprocess_batch_async",
-           "PendingDetections", "patch_retinanet", "HotPathGraph"]
+           "PendingDetections", "patch_retinanet", "HotPathGraph", "HotPathPipeline"]
+# image-sharded multi-GPU use: pytorch_retinanet_b200.distributed (ShardedRetinaNetLosses, PeerExchange) — imported on
+# demand, it pulls in torch.distributed
